@@ -1,0 +1,332 @@
+// aqua_device.cuh -- device-side primitives of the batched AquaGym step (sm_100a).
+//
+// One env instance is advanced by one call of step_env<R>() with its whole state in
+// registers.  The kinematics use the closed form of the reference's ICC rotation
+// (gym_aqua/envs/aqua.py:159-183; derivation in DESIGN.md section 3) instead of the reference's
+// "rotate about a centre 1.25e8 px away" formulation, which is unusable in float32.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/aquagym.h"
+
+namespace aqua {
+
+constexpr uint32_t kTimeMask = (1u << AQUA_TIME_BITS) - 1u;  // 2047: time saturates here
+constexpr uint32_t kEpisodeMask = AQUA_EPISODE_MASK;
+constexpr uint32_t kResetMaxTries = 4096u;
+
+enum : uint32_t { kStreamReset = 1u, kStreamWaveInit = 2u, kStreamWaveNoise = 3u, kStreamAction = 4u };
+
+// ------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  key = seed, counter = (env id, c1, c2, stream tag).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                               uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+        const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+__device__ __forceinline__ uint4 philox_env(uint64_t seed, uint32_t env_id, uint32_t c1, uint32_t c2,
+                                            uint32_t tag) {
+    return philox4x32_10(env_id, c1, c2, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+// 24 high bits -> float in [0,1), exact
+__device__ __forceinline__ float u01(uint32_t u) { return __uint2float_rn(u >> 8) * 0x1p-24f; }
+
+// The draws are float32 by definition: every instantiation and the CPU
+// oracle consume bit-identical values.
+constexpr float kPiDnF = 3.1415925f;     // largest float below pi
+constexpr float kTwoPiDnF = 6.283185f;   // 2 * kPiDnF exactly
+__device__ __forceinline__ float draw_pos(uint32_t u) { return __fmul_rn(u01(u), 100.0f); }
+__device__ __forceinline__ float draw_angle(uint32_t u) { return __fmaf_rn(u01(u), kTwoPiDnF, -kPiDnF); }
+__device__ __forceinline__ float draw_wave0(uint32_t u) { return __fmaf_rn(u01(u), 0.1f, -0.05f); }
+__device__ __forceinline__ float draw_noise(uint32_t u) { return __fmaf_rn(u01(u), 0.002f, -0.001f); }
+__device__ __forceinline__ float draw_thrust(uint32_t u) { return __fmaf_rn(u01(u), 0.3f, 0.2f); }
+
+// wave increment of step `t` (env time before the increment) -- aqua.py:188
+__device__ __forceinline__ void draw_wave_noise(uint64_t seed, uint32_t env_id, uint32_t ep, uint32_t t,
+                                                float& nx, float& ny) {
+    const uint4 r = philox_env(seed, env_id, ep, t >> 1, kStreamWaveNoise);
+    const bool odd = (t & 1u) != 0u;
+    nx = draw_noise(odd ? r.z : r.x);
+    ny = draw_noise(odd ? r.w : r.y);
+}
+
+// ------------------------------------------------------------------------------------------
+// precision traits
+// ------------------------------------------------------------------------------------------
+template <typename R> struct Prec;
+template <> struct Prec<float> {
+    static constexpr int V = 4;  // envs per thread: 16-byte plane loads
+    static __device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+    static __device__ __forceinline__ float sqrt_(float v) {
+        float r;
+        asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+        return r;
+    }
+};
+template <> struct Prec<double> {
+    static constexpr int V = 2;
+    static __device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
+    static __device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
+};
+
+// obstacle table in shared memory: nearest-point distance to an axis-aligned box of half
+// extents (hx, hy) (a circle is the box with zero extents) compared with r2 = (clearance
+// radius)^2.  aqua.py:373-390.  All lanes read the same entry (broadcast, conflict free).
+template <typename R> struct alignas(16) ObstacleBox {
+    R cx, cy, hx, hy;
+};
+template <typename R> struct ObstacleTable {
+    ObstacleBox<R> box[AQUA_MAX_OBSTACLES];
+    R r2[AQUA_MAX_OBSTACLES];
+};
+
+// collision of V positions against the whole table: the table entry is read once per obstacle
+template <typename R, int V>
+__device__ __forceinline__ void hits_obstacles(const ObstacleTable<R>& tab, int k_obst, const R (&px)[V],
+                                               const R (&py)[V], bool (&hit)[V]) {
+#pragma unroll 2
+    for (int k = 0; k < k_obst; ++k) {
+        const ObstacleBox<R> o = tab.box[k];
+        const R r2 = tab.r2[k];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const R ddx = fmax(fabs(px[j] - o.cx) - o.hx, R(0));
+            const R ddy = fmax(fabs(py[j] - o.cy) - o.hy, R(0));
+            hit[j] |= (ddx * ddx + ddy * ddy <= r2);
+        }
+    }
+}
+
+// same test against the float64 table in global memory (reset path: rare, always float64 so
+// that accept/reject decisions are those of the float64 reference)
+__device__ __forceinline__ bool hits_obstacle_g(const double* __restrict__ tab64, int k_obst, double px,
+                                                double py) {
+    for (int k = 0; k < k_obst; ++k) {
+        const double* o = tab64 + 5 * k;
+        const double ddx = fmax(fabs(px - o[0]) - o[2], 0.0);
+        const double ddy = fmax(fabs(py - o[1]) - o[3], 0.0);
+        if (ddx * ddx + ddy * ddy <= o[4]) return true;
+    }
+    return false;
+}
+
+// aqua.py:424-427 / 453-455 (strict inequalities; boat and goal radius are both 2.5)
+__device__ __forceinline__ bool outside_border(double px, double py) {
+    return (px - 2.5 < 0.0) || (py - 2.5 < 0.0) || (px + 2.5 > 100.0) || (py + 2.5 > 100.0);
+}
+
+struct WorldFlags {
+    bool waves, random_boat, random_goal;
+};
+
+struct ResetResult {
+    double x, y, th, wx, wy, gx, gy;
+};
+
+// env.reset() for one env: aqua.py:100-126.  `ep` is the NEW episode index.  Try n of the
+// reference's `observation_space.sample()` sequence is Philox(env, ep, n, RESET).
+__device__ __noinline__ ResetResult reset_env(uint64_t seed, uint32_t env_id, uint32_t ep,
+                                              const double* __restrict__ tab64, int k_obst,
+                                              WorldFlags wf) {
+    ResetResult o;
+    uint32_t n = 0;
+    if (wf.random_goal) {  // aqua.py:102-105
+        for (;;) {
+            const uint4 r = philox_env(seed, env_id, ep, n++, kStreamReset);
+            o.gx = (double)draw_pos(r.z);
+            o.gy = (double)draw_pos(r.w);
+            if (n >= kResetMaxTries) break;
+            if (!(outside_border(o.gx, o.gy) || hits_obstacle_g(tab64, k_obst, o.gx, o.gy))) break;
+        }
+    } else {  // aqua.py:107
+        o.gx = 25.0;
+        o.gy = 80.0;
+    }
+    if (wf.random_boat) {  // aqua.py:110-115
+        for (;;) {
+            const uint4 r = philox_env(seed, env_id, ep, n++, kStreamReset);
+            o.x = (double)draw_pos(r.x);
+            o.y = (double)draw_pos(r.y);
+            o.th = (double)draw_angle(r.z);
+            if (n >= kResetMaxTries) break;
+            const double dgx = o.gx - o.x, dgy = o.gy - o.y;
+            const bool reached = sqrt(dgx * dgx + dgy * dgy) - 5.0 <= 0.0;  // aqua.py:421-422
+            if (!(reached || outside_border(o.x, o.y) || hits_obstacle_g(tab64, k_obst, o.x, o.y))) break;
+        }
+    } else {  // aqua.py:117
+        o.x = 85.0;
+        o.y = 45.0;
+        o.th = 0.0;
+    }
+    if (wf.waves) {  // aqua.py:124
+        const uint4 r = philox_env(seed, env_id, ep, 0u, kStreamWaveInit);
+        o.wx = (double)draw_wave0(r.x);
+        o.wy = (double)draw_wave0(r.y);
+    } else {
+        o.wx = 0.0;
+        o.wy = 0.0;
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// one env step, state in registers
+// ------------------------------------------------------------------------------------------
+template <typename R> struct EnvState {
+    R x, y, th, wx, wy, gx, gy;
+    uint32_t tw;  // (episode << 11) | time
+};
+
+// heading wrap to [-pi, pi): aqua.py:128-133
+__device__ __forceinline__ float wrap_angle(float a) {
+    // |a| <= pi + 0.12.  No float lies strictly between pi and 3.14159274f, so the float
+    // comparisons decide exactly like the real-number ones; 2*pi is subtracted as hi + lo.
+    constexpr float kPiUp = 3.14159274f, kTwoPiHi = 6.28318548f, kTwoPiLo = -1.74845553e-7f;
+    if (a >= kPiUp) a = (a - kTwoPiHi) - kTwoPiLo;
+    else if (a < -kPiUp) a = (a + kTwoPiHi) + kTwoPiLo;
+    return a;
+}
+__device__ __forceinline__ double wrap_angle(double a) {
+    // the reference's own expression, same constants and order
+    constexpr double kLow = -3.141592653589793, kHigh = 3.141592653589793;
+    const double width = kHigh - kLow;
+    const double off = a - kLow;
+    return (off - (floor(off / width) * width)) + kLow;
+}
+
+template <typename R> struct MoveTmp {
+    R px, py, dx, dy;  // position before the move, displacement
+};
+
+// Phase 1 of step(): thrusts -> new pose, wave update, time.  (tl, tr) are the thrusts after
+// clamping, (nx, ny) the wave increment of this step.
+template <typename R>
+__device__ __forceinline__ void move_env(EnvState<R>& e, R tl, R tr, R nx, R ny, bool waves,
+                                         MoveTmp<R>& m) {
+    using P = Prec<R>;
+    constexpr bool kF64 = sizeof(R) == 8;
+
+    // ---- differential drive, aqua.py:159-183 in closed form ----
+    R d = tr - tl;
+    if (fabs(d) < R(1e-8)) d = copysign(R(1e-8), d);  // aqua.py:159-160 (epsilon sentinel)
+    R phi, sinc;                                      // phi = w * tau, aqua.py:168
+    if constexpr (kF64) phi = d / R(2.5);
+    else phi = d * R(0.4);
+    const R v = (tr + tl) * R(0.5);                   // |w * r|,  aqua.py:166-170
+    const R h = phi * R(0.5);
+    const R h2 = h * h;
+    // sin(h)/h for |h| <= 0.06
+    if constexpr (kF64)
+        sinc = R(1) + h2 * (R(-1.0 / 6) + h2 * (R(1.0 / 120) + h2 * (R(-1.0 / 5040) + h2 * R(1.0 / 362880))));
+    else
+        sinc = R(1) + h2 * (R(-1.0 / 6) + h2 * R(1.0 / 120));
+    const R chord = v * sinc;
+    R sn, cs;
+    P::sincos_(e.th + h, &sn, &cs);
+    m.dx = e.wx - chord * sn;  // heading 0 = +y; aqua.py:173-181, tau = 1
+    m.dy = e.wy + chord * cs;
+    m.px = e.x;
+    m.py = e.y;
+    e.x = m.px + m.dx;
+    e.y = m.py + m.dy;
+    e.th = wrap_angle(e.th + phi);  // aqua.py:183
+
+    // ---- waves, aqua.py:188-191 (after the move) ----
+    if (waves) {
+        const R wmax = R(0.05);
+        e.wx = fmin(fmax(e.wx + nx, -wmax), wmax);
+        e.wy = fmin(fmax(e.wy + ny, -wmax), wmax);
+    }
+
+    // ---- time, aqua.py:141 ----
+    const uint32_t t = e.tw & kTimeMask;
+    e.tw = (e.tw & ~kTimeMask) | min(t + 1u, kTimeMask);
+}
+
+// Phase 2: termination ladder aqua.py:194-211.  `hit_obstacle` comes from hits_obstacles().
+// Returns the AQUA_FLAG_* byte; `reward` receives the step reward.
+template <typename R>
+__device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveTmp<R>& m, bool hit_obstacle,
+                                               R& reward) {
+    using P = Prec<R>;
+    constexpr bool kF64 = sizeof(R) == 8;
+    const R xn = e.x, yn = e.y;
+    bool collided;
+    if constexpr (kF64)
+        collided = (xn - R(2.5) < R(0)) | (yn - R(2.5) < R(0)) | (xn + R(2.5) > R(100)) | (yn + R(2.5) > R(100));
+    else  // float: p - 2.5 and p + 2.5 are exact near the borders, so this is the same predicate
+        collided = !((xn >= R(2.5)) & (xn <= R(97.5)) & (yn >= R(2.5)) & (yn <= R(97.5)));
+    collided |= hit_obstacle;
+
+    const R gcx = xn - e.gx, gcy = yn - e.gy;
+    const R dc2 = gcx * gcx + gcy * gcy;
+    const R gpx = m.px - e.gx, gpy = m.py - e.gy;
+    const R dp2 = gpx * gpx + gpy * gpy;
+    R step_reward;
+    bool reached;
+    if constexpr (kF64) {  // the reference's expressions: aqua.py:89-90, 392-402, 421-422
+        const R dcur = P::sqrt_(dc2) - R(5), dprev = P::sqrt_(dp2) - R(5);
+        reached = dcur <= R(0);
+        step_reward = (dprev - dcur) * R(0.7);
+    } else {
+        // d_prev - d_cur = (d_prev^2 - d_cur^2) / (d_prev + d_cur), the numerator taken from the
+        // displacement itself: no cancellation of two ~50 px norms in float32
+        reached = dc2 <= R(25);
+        const R num = -(m.dx * (R(2) * gpx + m.dx) + m.dy * (R(2) * gpy + m.dy));
+        const R den = P::sqrt_(dp2) + P::sqrt_(dc2);
+        step_reward = R(0.7) * __fdividef(num, den);
+    }
+    const uint32_t tn = e.tw & kTimeMask;
+    uint32_t flags;
+    if (collided) {
+        flags = AQUA_FLAG_DONE | AQUA_FLAG_COLLIDED;
+        reward = R(-10);
+    } else if (tn > 1000u) {
+        flags = AQUA_FLAG_DONE | AQUA_FLAG_TIME;
+        reward = R(-10);
+    } else if (reached) {
+        flags = AQUA_FLAG_DONE | AQUA_FLAG_SUCCESS;
+        reward = R(10);
+    } else {
+        flags = 0u;
+        reward = step_reward;
+    }
+    return flags;
+}
+
+// action decode ---------------------------------------------------------------------------
+// discrete table aqua.py:33-42: 0 -> (0.2, 0.5) rotate left, 1 -> (0.5, 0.2) rotate right,
+// 2 -> (0.5, 0.5) full throttle.  An index outside {0,1,2} selects full throttle and is counted.
+template <typename R>
+__device__ __forceinline__ void decode_discrete(long long a, R& tl, R& tr, uint32_t& bad) {
+    tl = (a == 0) ? R(0.2) : R(0.5);
+    tr = (a == 1) ? R(0.2) : R(0.5);
+    bad += ((unsigned long long)a > 2ull) ? 1u : 0u;
+}
+// continuous aqua.py:143-151: values outside [0.2, 0.5] are clipped (and counted)
+template <typename R>
+__device__ __forceinline__ void decode_continuous(float al, float ar, R& tl, R& tr, uint32_t& bad) {
+    const R l = (R)al, r = (R)ar;
+    tl = fmin(fmax(l, R(0.2)), R(0.5));
+    tr = fmin(fmax(r, R(0.2)), R(0.5));
+    bad += (tl != l || tr != r) ? 1u : 0u;
+}
+
+}  // namespace aqua

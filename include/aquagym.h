@@ -1,0 +1,184 @@
+/*
+ * aquagym.h -- C ABI of libaquagym.so: the B200-native batched AquaGym environment step.
+ *
+ * This is the drop-in boundary for ONE hot path of ilVecc/AquaticGymEnv: the environment
+ * `reset()` / `step()` of `gym_aqua/envs/aqua.py` (discrete `AquaEnv` and continuous
+ * `AquaContinuousEnv`), batched over N independent env instances that live in GPU memory.
+ * The reference has no native interface (it is pure Python); every entry point below cites
+ * the reference method it replaces (paths relative to the reference repository root).
+ *
+ * Conventions
+ *   - Plain C: opaque handle, raw device pointers, sizes.  No torch / C++ types.
+ *   - Every function returns AQUA_OK (0) or a negative aqua_status; the message of the last
+ *     failure on the calling thread is returned by aqua_last_error().
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All launches
+ *     are asynchronous on that stream; only aqua_get_stats() and aqua_step_host() synchronise.
+ *   - A handle is owned by one host thread at a time; distinct handles are independent.
+ *   - There is no CPU fallback: without a CUDA device aqua_create() fails.
+ *
+ * State layout (structure of arrays, one "plane" per quantity, `ld` elements apart):
+ *     plane 0..6 : x, y, theta, wave_x, wave_y, goal_x, goal_y   (float, or double if
+ *                  precision == AQUA_F64)
+ *     plane 7    : uint32 word  (episode << 11) | time           (time saturates at 2047)
+ *   The observation of the reference (aqua.py:126,213: concat(boat_state[3], goal[2])) is planes
+ *   {0,1,2,5,6}; no separate observation copy is made.
+ */
+#ifndef AQUAGYM_H
+#define AQUAGYM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AQUAGYM_ABI_VERSION 1
+
+typedef struct aqua_env aqua_env;
+
+typedef enum {
+    AQUA_OK = 0,
+    AQUA_ERR_INVALID = -1,   /* bad argument / configuration */
+    AQUA_ERR_CUDA = -2,      /* a CUDA runtime call failed (message has the CUDA error string) */
+    AQUA_ERR_NO_DEVICE = -3, /* no usable CUDA device: there is no CPU fallback */
+    AQUA_ERR_ALLOC = -4
+} aqua_status;
+
+enum { AQUA_F32 = 0, AQUA_F64 = 1 };
+
+/* element type of the `actions` buffer of aqua_step */
+enum {
+    AQUA_ACT_I32 = 0,   /* discrete: int32[N]  action index, aqua.py:33-43,154 */
+    AQUA_ACT_I64 = 1,   /* discrete: int64[N]  (torch argmax / randint default) */
+    AQUA_ACT_U8 = 2,    /* discrete: uint8[N] */
+    AQUA_ACT_F32X2 = 3  /* continuous: float[N][2] = (thrust_left, thrust_right), aqua.py:143-151 */
+};
+
+/* bits of the per-env flags byte written by aqua_step (aqua.py:194-211) */
+#define AQUA_FLAG_DONE 1u      /* `done` */
+#define AQUA_FLAG_COLLIDED 2u  /* info['Termination.collided'] */
+#define AQUA_FLAG_TIME 4u      /* info['Termination.time'] */
+#define AQUA_FLAG_SUCCESS 8u   /* info['Termination.success'] */
+
+#define AQUA_MAX_OBSTACLES 64
+#define AQUA_TIME_BITS 11
+#define AQUA_EPISODE_MASK 0x1FFFFFu
+#define AQUA_N_PLANES 8
+#define AQUA_TILE 1024 /* `ld` must be a multiple of this */
+
+/* index of the counters returned by aqua_get_stats / aqua_stats_reduce */
+enum {
+    AQUA_STAT_EPISODES = 0,   /* finished episodes (steps with done) */
+    AQUA_STAT_COLLIDED = 1,
+    AQUA_STAT_TIMEOUT = 2,
+    AQUA_STAT_SUCCESS = 3,
+    AQUA_STAT_LENGTH_SUM = 4, /* sum of episode lengths of the finished episodes */
+    AQUA_STAT_REWARD_SUM = 5, /* sum of ALL step rewards, fixed point: value * 2^20 */
+    AQUA_STAT_STEPS = 6,      /* env-steps executed */
+    AQUA_STAT_BAD_ACTIONS = 7, /* discrete index outside {0,1,2} or thrust outside [0.2,0.5] */
+    AQUA_N_STATS = 8
+};
+#define AQUA_REWARD_FIXED_POINT 1048576.0
+
+/* Constructor arguments.  Replaces `AquaEnv.__init__(obstacles, waves, random_boat,
+ * random_goal)` (aqua.py:13-98) plus the `continuous` class attribute (aqua.py:11,458-459). */
+typedef struct {
+    uint32_t struct_size;  /* = sizeof(aqua_config), for ABI evolution */
+    int32_t device;        /* CUDA device ordinal */
+    int64_t n_envs;        /* N >= 1 */
+    int32_t continuous;    /* 0: AquaEnv, 1: AquaContinuousEnv */
+    int32_t waves;         /* aqua.py:15   has_waves */
+    int32_t random_boat;   /* aqua.py:16; 0 -> boat starts at (85, 45, 0), aqua.py:117 */
+    int32_t random_goal;   /* aqua.py:17; 0 -> goal at (25, 80), aqua.py:107 */
+    int32_t precision;     /* AQUA_F32 (throughput layout) or AQUA_F64 (parity-grade pose) */
+    int32_t autoreset;     /* 1: a done env is reset inside the step kernel (vector-env
+                              semantics: reward/flags are the terminal step's, the state planes
+                              hold the first observation of the next episode); 0: the terminal
+                              state stays until aqua_reset (the reference's single-env flow) */
+    int32_t n_obstacles;   /* 0..AQUA_MAX_OBSTACLES */
+    int32_t _reserved;
+    /* HOST array [n_obstacles][5] = {cx, cy, type (0 circle / 1 rectangle), a, b}: circle
+     * a = radius; rectangle a = width, b = height, centre anchored (aqua.py:56-68,373-390) */
+    const double* obstacles;
+    uint64_t seed;         /* key of the Philox4x32-10 draw streams */
+    uint64_t env_id_base;  /* global id of env 0 of this slab (rank * n_envs when sharded) */
+    /* Optional caller-owned DEVICE state buffer of AQUA_N_PLANES * ld elements (element =
+     * float or double per `precision`); NULL -> the library allocates it. */
+    void* state;
+    int64_t ld;            /* plane stride in elements, multiple of AQUA_TILE, >= n_envs;
+                              0 -> n_envs rounded up to AQUA_TILE */
+} aqua_config;
+
+typedef struct {
+    void* planes[AQUA_N_PLANES]; /* device pointers, see "State layout" */
+    int64_t ld;
+    int64_t n_envs;
+    int32_t precision;
+    int32_t _pad;
+} aqua_state_view;
+
+/* ---- life cycle ---------------------------------------------------------------------- */
+int aqua_abi_version(void);
+const char* aqua_last_error(void);
+
+/* gym.make(id, **kwargs) -> AquaEnv(...)  (gym_aqua/__init__.py:4-41, aqua.py:13).  The state
+ * is undefined until the first aqua_reset. */
+int aqua_create(aqua_env** out, const aqua_config* cfg);
+/* env.close() (aqua.py:367-371) + release of device memory */
+int aqua_destroy(aqua_env* env);
+int aqua_state(aqua_env* env, aqua_state_view* out);
+
+/* ---- the hot path -------------------------------------------------------------------- */
+/* env.reset() (aqua.py:100-126).  mask: device uint8[N] (non-zero = reset that env) or NULL
+ * for all.  Opens the next episode of each selected env and draws goal, boat pose and wave
+ * speed by the reference's rejection loops from the Philox RESET / WAVE_INIT streams. */
+int aqua_reset(aqua_env* env, void* stream, const uint8_t* mask);
+
+/* env.step(action) (aqua.py:135-213) for all N envs.
+ *   actions : device buffer, element type `action_dtype`
+ *   reward  : device float[N] (double[N] if precision == AQUA_F64)  -- aqua.py:86-90
+ *   flags   : device uint8[N], AQUA_FLAG_* bits                      -- aqua.py:194-208
+ * The observation is the state planes (see aqua_state).  Out-of-range actions are clamped
+ * (aqua.py:145-150 prints and clips; a bad discrete index raises IndexError in the reference,
+ * here it selects "full throttle") and counted in AQUA_STAT_BAD_ACTIONS. */
+int aqua_step(aqua_env* env, void* stream, const void* actions, int action_dtype, void* reward,
+              uint8_t* flags);
+
+/* Same, with the wave-speed increment of aqua.py:188 injected instead of drawn:
+ * noise = device float[2][N] {nx[N], ny[N]} (NULL = Philox stream).  Parity/debug. */
+int aqua_step_ex(aqua_env* env, void* stream, const void* actions, int action_dtype, void* reward,
+                 uint8_t* flags, const float* noise);
+
+/* Synthetic random policy (`action_space.sample()`, test_random.py:19-20) from the Philox
+ * ACTION stream keyed by (global env id, step_index): writes actions of `action_dtype`. */
+int aqua_random_actions(aqua_env* env, void* stream, uint64_t step_index, void* actions,
+                        int action_dtype);
+
+/* `steps` env-steps fused in ONE launch with the synthetic random policy above (state stays in
+ * registers; per-step reward/flags are not materialised, statistics are).  first_step_index is
+ * the ACTION-stream index of the first step. */
+int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t first_step_index);
+
+/* Host-buffer step: the call a host-side gym user makes.  Copies `actions` (HOST, preferably
+ * pinned) to the device, steps, and copies obs (float[5][N] planes x,y,theta,gx,gy; double if
+ * F64), reward and flags back to HOST buffers, chunked and pipelined over internal streams;
+ * returns after everything has landed.  obs/reward/flags may be NULL to skip that copy. */
+int aqua_step_host(aqua_env* env, const void* actions, int action_dtype, void* obs, void* reward,
+                   uint8_t* flags);
+
+/* ---- state access (parity teacher-forcing, checkpoint/restore) ------------------------ */
+/* canonical DEVICE double[9][N]: x, y, theta, wave_x, wave_y, goal_x, goal_y, time, episode */
+int aqua_get_state(aqua_env* env, void* stream, double* out);
+int aqua_set_state(aqua_env* env, void* stream, const double* in);
+
+/* ---- episode statistics --------------------------------------------------------------- */
+/* Fold the per-block counter slots into DEVICE int64[AQUA_N_STATS] (the vector that is
+ * all-reduced across ranks with NCCL); clear != 0 zeroes the internal counters afterwards. */
+int aqua_stats_reduce(aqua_env* env, void* stream, int64_t* out_dev, int clear);
+/* Same into a HOST int64[AQUA_N_STATS]; synchronises `stream`. */
+int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AQUAGYM_H */
