@@ -1,0 +1,98 @@
+"""ctypes binding of ``libaquagym.so`` (C ABI: ``include/aquagym.h``).
+
+The shared library is built in-tree by ``aquaticgymenv_b200.build.build()`` (nvcc, sm_100a).
+There is no CPU fallback: if the library is missing ``load()`` raises, and without a CUDA device
+``aqua_create`` returns ``AQUA_ERR_NO_DEVICE`` which surfaces as :class:`AquaError`.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libaquagym.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aquagym.h")
+
+ABI_VERSION = 1
+OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = 0, -1, -2, -3, -4
+F32, F64 = 0, 1
+ACT_I32, ACT_I64, ACT_U8, ACT_F32X2 = 0, 1, 2, 3
+FLAG_DONE, FLAG_COLLIDED, FLAG_TIME, FLAG_SUCCESS = 1, 2, 4, 8
+MAX_OBSTACLES = 64
+TIME_BITS = 11
+EPISODE_MASK = 0x1FFFFF
+N_PLANES = 8
+TILE = 1024
+N_STATS = 8
+STAT_NAMES = ("episodes", "collided", "timeout", "success", "length_sum", "reward_sum_fx", "steps",
+              "bad_actions")
+REWARD_FIXED_POINT = 1048576.0
+
+
+class AquaError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("libaquagym: %s (status %d)" % (message, status))
+        self.status = status
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_uint32), ("device", C.c_int32), ("n_envs", C.c_int64),
+        ("continuous", C.c_int32), ("waves", C.c_int32), ("random_boat", C.c_int32),
+        ("random_goal", C.c_int32), ("precision", C.c_int32), ("autoreset", C.c_int32),
+        ("n_obstacles", C.c_int32), ("_reserved", C.c_int32),
+        ("obstacles", C.POINTER(C.c_double)), ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
+        ("state", C.c_void_p), ("ld", C.c_int64)]
+
+
+class StateView(C.Structure):
+    _fields_ = [("planes", C.c_void_p * N_PLANES), ("ld", C.c_int64), ("n_envs", C.c_int64),
+                ("precision", C.c_int32), ("_pad", C.c_int32)]
+
+
+_vp, _u64, _i64, _int = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
+# name -> (restype, argtypes); must list every symbol include/aquagym.h declares
+SIGNATURES = {
+    "aqua_abi_version": (_int, []),
+    "aqua_last_error": (C.c_char_p, []),
+    "aqua_create": (_int, [C.POINTER(_vp), C.POINTER(Config)]),
+    "aqua_destroy": (_int, [_vp]),
+    "aqua_state": (_int, [_vp, C.POINTER(StateView)]),
+    "aqua_reset": (_int, [_vp, _vp, _vp]),
+    "aqua_step": (_int, [_vp, _vp, _vp, _int, _vp, _vp]),
+    "aqua_step_ex": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "aqua_random_actions": (_int, [_vp, _vp, _u64, _vp, _int]),
+    "aqua_rollout_random": (_int, [_vp, _vp, _i64, _u64]),
+    "aqua_step_host": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "aqua_get_state": (_int, [_vp, _vp, _vp]),
+    "aqua_set_state": (_int, [_vp, _vp, _vp]),
+    "aqua_stats_reduce": (_int, [_vp, _vp, _vp, _int]),
+    "aqua_get_stats": (_int, [_vp, _vp, C.POINTER(C.c_int64), _int]),
+}
+
+_lib = None
+
+
+def load():
+    """Load libaquagym.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` or "
+            "`make -C aquaticgymenv_b200/csrc` (nvcc, sm_100a). aquaticgymenv_b200 has no CPU "
+            "fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.aqua_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError("libaquagym ABI %d, binding expects %d: rebuild" % (got, ABI_VERSION))
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != OK:
+        raise AquaError(status, load().aqua_last_error().decode("utf-8", "replace"))

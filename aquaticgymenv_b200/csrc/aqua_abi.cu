@@ -1,0 +1,470 @@
+// aqua_abi.cu -- the C ABI of libaquagym.so (include/aquagym.h): handle life cycle, argument
+// validation, launch geometry and the host-buffer step pipeline.  No exceptions cross the ABI;
+// every CUDA failure becomes a status + thread-local message.  There is no CPU fallback.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "aqua_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int status, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return status;
+}
+
+#define AQ_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(AQUA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+// restores the caller's current device on scope exit
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+constexpr int kHostStreams = 4;       // host-step pipeline depth
+constexpr int64_t kHostChunkMin = 64 * 1024;
+
+size_t elem_size(int precision) { return precision == AQUA_F64 ? 8 : 4; }
+
+size_t action_bytes(int dtype) {
+    switch (dtype) {
+        case AQUA_ACT_I32: return 4;
+        case AQUA_ACT_I64: return 8;
+        case AQUA_ACT_U8: return 1;
+        case AQUA_ACT_F32X2: return 8;
+        default: return 0;
+    }
+}
+
+}  // namespace
+
+struct aqua_env {
+    aqua_config cfg;
+    int device = 0;
+    int sm_count = 0;
+    void* state = nullptr;
+    bool owns_state = false;
+    int64_t ld = 0;
+    void* d_tab = nullptr;
+    double* d_tab64 = nullptr;
+    unsigned long long* d_slots = nullptr;
+    int64_t* d_stats_out = nullptr;
+    aqua::World world;
+    // host-step pipeline (lazily created)
+    cudaStream_t hs[kHostStreams] = {};
+    cudaEvent_t ev_in = nullptr;
+    bool host_ready = false;
+    void* d_actions = nullptr;
+    size_t d_actions_bytes = 0;
+    void* d_reward = nullptr;
+    uint8_t* d_flags = nullptr;
+};
+
+namespace {
+
+aqua::StepArgs base_args(const aqua_env* env) {
+    aqua::StepArgs a;
+    memset(&a, 0, sizeof a);
+    a.w = env->world;
+    a.planes = env->state;
+    a.ld = env->ld;
+    a.env_begin = 0;
+    a.env_end = env->cfg.n_envs;
+    a.stats = env->d_slots;
+    return a;
+}
+
+// Launch geometry of the step kernel for `n` envs.  Small slabs use small CTAs so that every SM
+// gets work; large slabs use a persistent grid of (resident CTAs per SM) x (SM count) CTAs.
+int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aqua::LaunchGeom* g) {
+    const int V = env->cfg.precision == AQUA_F64 ? 2 : 4;
+    int threads = 256;
+    while (threads > 64 && n < (int64_t)threads * V * env->sm_count * 2) threads >>= 1;
+    int per_sm = 0;
+    cudaError_t e = rollout ? aqua::rollout_occupancy(env->cfg.precision, env->cfg.continuous, threads, &per_sm)
+                            : aqua::step_occupancy(env->cfg.precision, action_dtype, threads, &per_sm);
+    if (e != cudaSuccess) return fail(AQUA_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
+    if (per_sm < 1) per_sm = 1;
+    const int64_t tiles = (n + (int64_t)threads * V - 1) / ((int64_t)threads * V);
+    const int64_t resident = (int64_t)per_sm * env->sm_count;
+    g->threads = threads;
+    g->blocks = (int)std::max<int64_t>(1, std::min(tiles, resident));
+    return AQUA_OK;
+}
+
+int check_env(const aqua_env* env) {
+    if (env == nullptr) return fail(AQUA_ERR_INVALID, "env handle is NULL");
+    return AQUA_OK;
+}
+
+int check_action_dtype(const aqua_env* env, int dtype) {
+    if (action_bytes(dtype) == 0) return fail(AQUA_ERR_INVALID, "unknown action dtype %d", dtype);
+    if (env->cfg.continuous && dtype != AQUA_ACT_F32X2)
+        return fail(AQUA_ERR_INVALID, "AquaContinuousEnv takes AQUA_ACT_F32X2 actions (aqua.py:143-151), got dtype %d", dtype);
+    if (!env->cfg.continuous && dtype == AQUA_ACT_F32X2)
+        return fail(AQUA_ERR_INVALID, "AquaEnv takes a discrete action index (aqua.py:154), got AQUA_ACT_F32X2");
+    return AQUA_OK;
+}
+
+int ensure_host_pipeline(aqua_env* env, int action_dtype) {
+    if (!env->host_ready) {
+        for (int i = 0; i < kHostStreams; ++i) AQ_CUDA(cudaStreamCreateWithFlags(&env->hs[i], cudaStreamNonBlocking));
+        AQ_CUDA(cudaEventCreateWithFlags(&env->ev_in, cudaEventDisableTiming));
+        AQ_CUDA(cudaMalloc(&env->d_reward, (size_t)env->ld * elem_size(env->cfg.precision)));
+        AQ_CUDA(cudaMalloc(&env->d_flags, (size_t)env->ld));
+        env->host_ready = true;
+    }
+    const size_t need = (size_t)env->ld * action_bytes(action_dtype);
+    if (env->d_actions_bytes < need) {
+        if (env->d_actions) AQ_CUDA(cudaFree(env->d_actions));
+        env->d_actions = nullptr;
+        env->d_actions_bytes = 0;
+        AQ_CUDA(cudaMalloc(&env->d_actions, need));
+        env->d_actions_bytes = need;
+    }
+    return AQUA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int aqua_abi_version(void) { return AQUAGYM_ABI_VERSION; }
+
+const char* aqua_last_error(void) { return g_err; }
+
+int aqua_create(aqua_env** out, const aqua_config* cfg) {
+    if (out == nullptr) return fail(AQUA_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (cfg == nullptr) return fail(AQUA_ERR_INVALID, "cfg is NULL");
+    if (cfg->struct_size != sizeof(aqua_config))
+        return fail(AQUA_ERR_INVALID, "aqua_config.struct_size = %u, this library expects %zu (ABI %d)",
+                    cfg->struct_size, sizeof(aqua_config), AQUAGYM_ABI_VERSION);
+    if (cfg->n_envs < 1) return fail(AQUA_ERR_INVALID, "n_envs must be >= 1, got %lld", (long long)cfg->n_envs);
+    if (cfg->precision != AQUA_F32 && cfg->precision != AQUA_F64)
+        return fail(AQUA_ERR_INVALID, "precision must be AQUA_F32 or AQUA_F64, got %d", cfg->precision);
+    if (cfg->n_obstacles < 0 || cfg->n_obstacles > AQUA_MAX_OBSTACLES)
+        return fail(AQUA_ERR_INVALID, "n_obstacles must be in [0, %d], got %d", AQUA_MAX_OBSTACLES, cfg->n_obstacles);
+    if (cfg->n_obstacles > 0 && cfg->obstacles == nullptr)
+        return fail(AQUA_ERR_INVALID, "n_obstacles = %d but obstacles is NULL", cfg->n_obstacles);
+    for (int k = 0; k < cfg->n_obstacles; ++k) {
+        const double* o = cfg->obstacles + 5 * k;
+        if (!(o[2] == 0.0 || o[2] == 1.0))
+            return fail(AQUA_ERR_INVALID, "obstacle %d: type must be 0 (circle) or 1 (rectangle), got %g", k, o[2]);
+        if (!(o[3] >= 0.0) || !(o[2] == 0.0 || o[4] >= 0.0))
+            return fail(AQUA_ERR_INVALID, "obstacle %d: negative or NaN size", k);
+    }
+    if (cfg->env_id_base + (uint64_t)cfg->n_envs > (1ull << 32))
+        return fail(AQUA_ERR_INVALID, "global env ids must fit 32 bits (env_id_base + n_envs <= 2^32)");
+    int64_t ld = cfg->ld;
+    if (ld == 0) ld = (cfg->n_envs + AQUA_TILE - 1) / AQUA_TILE * AQUA_TILE;
+    if (ld < cfg->n_envs || ld % AQUA_TILE != 0)
+        return fail(AQUA_ERR_INVALID, "ld = %lld must be a multiple of %d and >= n_envs", (long long)ld, AQUA_TILE);
+    if (cfg->state != nullptr && (reinterpret_cast<uintptr_t>(cfg->state) & 15u))
+        return fail(AQUA_ERR_INVALID, "state buffer must be 16-byte aligned");
+
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return fail(AQUA_ERR_NO_DEVICE, "no CUDA device (%s): libaquagym has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= n_dev)
+        return fail(AQUA_ERR_INVALID, "device %d out of range [0, %d)", cfg->device, n_dev);
+
+    DeviceGuard guard(cfg->device);
+    if (!guard.ok) return fail(AQUA_ERR_CUDA, "cudaSetDevice(%d) failed", cfg->device);
+
+    aqua_env* env = new (std::nothrow) aqua_env();
+    if (env == nullptr) return fail(AQUA_ERR_ALLOC, "out of host memory");
+    env->cfg = *cfg;
+    env->cfg.obstacles = nullptr;
+    env->cfg.ld = ld;
+    env->device = cfg->device;
+    env->ld = ld;
+
+#define AQ_CREATE(call)                                                                            \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            const int rc_ = fail(AQUA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));   \
+            aqua_destroy(env);                                                                     \
+            /* aqua_destroy succeeded or not, report the original failure */                       \
+            fail(AQUA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_));                   \
+            return rc_;                                                                            \
+        }                                                                                          \
+    } while (0)
+
+    AQ_CREATE(cudaDeviceGetAttribute(&env->sm_count, cudaDevAttrMultiProcessorCount, env->device));
+    const size_t es = elem_size(cfg->precision);
+    if (cfg->state != nullptr) {
+        env->state = cfg->state;
+    } else {
+        AQ_CREATE(cudaMalloc(&env->state, (size_t)AQUA_N_PLANES * (size_t)ld * es));
+        env->owns_state = true;
+    }
+    // obstacle tables
+    const size_t tab_bytes = aqua::obstacle_table_bytes(cfg->precision);
+    {
+        void* h_tab = malloc(tab_bytes);
+        double h_tab64[AQUA_MAX_OBSTACLES * 5] = {0};
+        if (h_tab == nullptr) {
+            aqua_destroy(env);
+            return fail(AQUA_ERR_ALLOC, "out of host memory");
+        }
+        aqua::build_obstacle_tables(cfg->precision, cfg->n_obstacles, cfg->obstacles, h_tab, h_tab64);
+        cudaError_t e1 = cudaMalloc(&env->d_tab, tab_bytes);
+        if (e1 == cudaSuccess) e1 = cudaMemcpy(env->d_tab, h_tab, tab_bytes, cudaMemcpyHostToDevice);
+        free(h_tab);
+        AQ_CREATE(e1);
+        AQ_CREATE(cudaMalloc(&env->d_tab64, sizeof h_tab64));
+        AQ_CREATE(cudaMemcpy(env->d_tab64, h_tab64, sizeof h_tab64, cudaMemcpyHostToDevice));
+    }
+    AQ_CREATE(cudaMalloc(&env->d_slots, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
+    AQ_CREATE(cudaMemset(env->d_slots, 0, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
+    AQ_CREATE(cudaMalloc(&env->d_stats_out, sizeof(int64_t) * AQUA_N_STATS));
+
+    aqua::World& w = env->world;
+    memset(&w, 0, sizeof w);
+    {
+        uint32_t k0 = (uint32_t)cfg->seed, k1 = (uint32_t)(cfg->seed >> 32);
+        for (int r = 0; r < 10; ++r) {
+            w.keys.rk[2 * r] = k0;
+            w.keys.rk[2 * r + 1] = k1;
+            k0 += 0x9E3779B9u;
+            k1 += 0xBB67AE85u;
+        }
+    }
+    w.env_id_base = cfg->env_id_base;
+    w.tab = env->d_tab;
+    w.tab64 = env->d_tab64;
+    w.grid = nullptr;
+    w.k_obst = cfg->n_obstacles;
+    w.waves = cfg->waves != 0;
+    w.random_boat = cfg->random_boat != 0;
+    w.random_goal = cfg->random_goal != 0;
+    w.autoreset = cfg->autoreset != 0;
+
+    AQ_CREATE(aqua::launch_init_state(cfg->precision, env->state, ld, nullptr));
+    AQ_CREATE(cudaStreamSynchronize(nullptr));
+#undef AQ_CREATE
+    *out = env;
+    return AQUA_OK;
+}
+
+int aqua_destroy(aqua_env* env) {
+    if (env == nullptr) return AQUA_OK;
+    DeviceGuard guard(env->device);
+    cudaError_t first = cudaSuccess;
+    auto keep = [&](cudaError_t e) {
+        if (first == cudaSuccess && e != cudaSuccess) first = e;
+    };
+    if (env->host_ready) {
+        for (int i = 0; i < kHostStreams; ++i)
+            if (env->hs[i]) {
+                keep(cudaStreamSynchronize(env->hs[i]));
+                keep(cudaStreamDestroy(env->hs[i]));
+            }
+        if (env->ev_in) keep(cudaEventDestroy(env->ev_in));
+    }
+    if (env->d_actions) keep(cudaFree(env->d_actions));
+    if (env->d_reward) keep(cudaFree(env->d_reward));
+    if (env->d_flags) keep(cudaFree(env->d_flags));
+    if (env->owns_state && env->state) keep(cudaFree(env->state));
+    if (env->d_tab) keep(cudaFree(env->d_tab));
+    if (env->d_tab64) keep(cudaFree(env->d_tab64));
+    if (env->d_slots) keep(cudaFree(env->d_slots));
+    if (env->d_stats_out) keep(cudaFree(env->d_stats_out));
+    delete env;
+    if (first != cudaSuccess) return fail(AQUA_ERR_CUDA, "aqua_destroy: %s", cudaGetErrorString(first));
+    return AQUA_OK;
+}
+
+int aqua_state(aqua_env* env, aqua_state_view* out) {
+    if (int rc = check_env(env)) return rc;
+    if (out == nullptr) return fail(AQUA_ERR_INVALID, "out is NULL");
+    const size_t es = elem_size(env->cfg.precision);
+    for (int p = 0; p < AQUA_N_PLANES; ++p)
+        out->planes[p] = static_cast<char*>(env->state) + (size_t)p * (size_t)env->ld * es;
+    out->ld = env->ld;
+    out->n_envs = env->cfg.n_envs;
+    out->precision = env->cfg.precision;
+    out->_pad = 0;
+    return AQUA_OK;
+}
+
+int aqua_reset(aqua_env* env, void* stream, const uint8_t* mask) {
+    if (int rc = check_env(env)) return rc;
+    DeviceGuard guard(env->device);
+    const aqua::StepArgs a = base_args(env);
+    AQ_CUDA(aqua::launch_reset(env->cfg.precision, a, mask, static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_step_ex(aqua_env* env, void* stream, const void* actions, int action_dtype, void* reward,
+                 uint8_t* flags, const float* noise) {
+    if (int rc = check_env(env)) return rc;
+    if (int rc = check_action_dtype(env, action_dtype)) return rc;
+    if (actions == nullptr || reward == nullptr || flags == nullptr)
+        return fail(AQUA_ERR_INVALID, "actions, reward and flags must be device pointers, got NULL");
+    if ((reinterpret_cast<uintptr_t>(actions) & 15u) || (reinterpret_cast<uintptr_t>(reward) & 15u) ||
+        (reinterpret_cast<uintptr_t>(flags) & 3u))
+        return fail(AQUA_ERR_INVALID, "actions and reward must be 16-byte aligned, flags 4-byte aligned");
+    DeviceGuard guard(env->device);
+    aqua::StepArgs a = base_args(env);
+    a.actions = actions;
+    a.reward = reward;
+    a.flags = flags;
+    if (noise != nullptr) {
+        a.noise_x = noise;
+        a.noise_y = noise + env->cfg.n_envs;
+    }
+    aqua::LaunchGeom g;
+    if (int rc = pick_geom(env, env->cfg.n_envs, false, action_dtype, &g)) return rc;
+    AQ_CUDA(aqua::launch_step(env->cfg.precision, action_dtype, a, g, static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_step(aqua_env* env, void* stream, const void* actions, int action_dtype, void* reward,
+              uint8_t* flags) {
+    return aqua_step_ex(env, stream, actions, action_dtype, reward, flags, nullptr);
+}
+
+int aqua_random_actions(aqua_env* env, void* stream, uint64_t step_index, void* actions, int action_dtype) {
+    if (int rc = check_env(env)) return rc;
+    if (int rc = check_action_dtype(env, action_dtype)) return rc;
+    if (actions == nullptr) return fail(AQUA_ERR_INVALID, "actions is NULL");
+    DeviceGuard guard(env->device);
+    AQ_CUDA(aqua::launch_random_actions(env->world, env->cfg.n_envs, step_index, actions, action_dtype,
+                                        static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t first_step_index) {
+    if (int rc = check_env(env)) return rc;
+    if (steps < 0) return fail(AQUA_ERR_INVALID, "steps must be >= 0");
+    if (steps == 0) return AQUA_OK;
+    DeviceGuard guard(env->device);
+    aqua::StepArgs a = base_args(env);
+    a.steps = steps;
+    a.step0 = first_step_index;
+    aqua::LaunchGeom g;
+    if (int rc = pick_geom(env, env->cfg.n_envs, true, 0, &g)) return rc;
+    AQ_CUDA(aqua::launch_rollout(env->cfg.precision, env->cfg.continuous, a, g, static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
+                   void* reward, uint8_t* flags) {
+    if (int rc = check_env(env)) return rc;
+    if (int rc = check_action_dtype(env, action_dtype)) return rc;
+    if (actions == nullptr) return fail(AQUA_ERR_INVALID, "actions is NULL");
+    DeviceGuard guard(env->device);
+    if (int rc = ensure_host_pipeline(env, action_dtype)) return rc;
+
+    const int64_t n = env->cfg.n_envs;
+    const size_t es = elem_size(env->cfg.precision);
+    const size_t ab = action_bytes(action_dtype);
+    // chunking: whole AQUA_TILEs, at least kHostChunkMin envs, at most 4 chunks per stream
+    int64_t chunk = (n + kHostStreams * 4 - 1) / (kHostStreams * 4);
+    chunk = std::max(chunk, kHostChunkMin);
+    chunk = (chunk + AQUA_TILE - 1) / AQUA_TILE * AQUA_TILE;
+
+    AQ_CUDA(cudaEventRecord(env->ev_in, static_cast<cudaStream_t>(stream)));
+    for (int i = 0; i < kHostStreams; ++i) AQ_CUDA(cudaStreamWaitEvent(env->hs[i], env->ev_in, 0));
+
+    static const int kObsPlanes[5] = {AQUA_PLANE_X, AQUA_PLANE_Y, AQUA_PLANE_THETA, AQUA_PLANE_GOAL_X,
+                                      AQUA_PLANE_GOAL_Y};  // aqua.py:213
+    int c = 0;
+    for (int64_t lo = 0; lo < n; lo += chunk, ++c) {
+        const int64_t hi = std::min(n, lo + chunk);
+        const int64_t len = hi - lo;
+        cudaStream_t s = env->hs[c % kHostStreams];
+        AQ_CUDA(cudaMemcpyAsync(static_cast<char*>(env->d_actions) + (size_t)lo * ab,
+                                static_cast<const char*>(actions) + (size_t)lo * ab, (size_t)len * ab,
+                                cudaMemcpyHostToDevice, s));
+        aqua::StepArgs a = base_args(env);
+        a.env_begin = lo;
+        a.env_end = hi;
+        a.actions = env->d_actions;
+        a.reward = env->d_reward;
+        a.flags = env->d_flags;
+        aqua::LaunchGeom g;
+        if (int rc = pick_geom(env, len, false, action_dtype, &g)) return rc;
+        AQ_CUDA(aqua::launch_step(env->cfg.precision, action_dtype, a, g, s));
+        if (flags != nullptr)
+            AQ_CUDA(cudaMemcpyAsync(flags + lo, env->d_flags + lo, (size_t)len, cudaMemcpyDeviceToHost, s));
+        if (reward != nullptr)
+            AQ_CUDA(cudaMemcpyAsync(static_cast<char*>(reward) + (size_t)lo * es,
+                                    static_cast<char*>(env->d_reward) + (size_t)lo * es, (size_t)len * es,
+                                    cudaMemcpyDeviceToHost, s));
+        if (obs != nullptr)
+            for (int k = 0; k < 5; ++k)
+                AQ_CUDA(cudaMemcpyAsync(static_cast<char*>(obs) + ((size_t)k * (size_t)n + (size_t)lo) * es,
+                                        static_cast<char*>(env->state) +
+                                            ((size_t)kObsPlanes[k] * (size_t)env->ld + (size_t)lo) * es,
+                                        (size_t)len * es, cudaMemcpyDeviceToHost, s));
+    }
+    for (int i = 0; i < kHostStreams; ++i) AQ_CUDA(cudaStreamSynchronize(env->hs[i]));
+    return AQUA_OK;
+}
+
+int aqua_get_state(aqua_env* env, void* stream, double* out) {
+    if (int rc = check_env(env)) return rc;
+    if (out == nullptr) return fail(AQUA_ERR_INVALID, "out is NULL");
+    DeviceGuard guard(env->device);
+    AQ_CUDA(aqua::launch_get_state(env->cfg.precision, env->state, env->ld, env->cfg.n_envs, out,
+                                   static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_set_state(aqua_env* env, void* stream, const double* in) {
+    if (int rc = check_env(env)) return rc;
+    if (in == nullptr) return fail(AQUA_ERR_INVALID, "in is NULL");
+    DeviceGuard guard(env->device);
+    AQ_CUDA(aqua::launch_set_state(env->cfg.precision, env->state, env->ld, env->cfg.n_envs, in,
+                                   static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_stats_reduce(aqua_env* env, void* stream, int64_t* out_dev, int clear) {
+    if (int rc = check_env(env)) return rc;
+    if (out_dev == nullptr) return fail(AQUA_ERR_INVALID, "out_dev is NULL");
+    DeviceGuard guard(env->device);
+    AQ_CUDA(aqua::launch_stats_reduce(env->d_slots, out_dev, clear, static_cast<cudaStream_t>(stream)));
+    return AQUA_OK;
+}
+
+int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear) {
+    if (int rc = check_env(env)) return rc;
+    if (out_host == nullptr) return fail(AQUA_ERR_INVALID, "out_host is NULL");
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    AQ_CUDA(aqua::launch_stats_reduce(env->d_slots, env->d_stats_out, clear, s));
+    AQ_CUDA(cudaMemcpyAsync(out_host, env->d_stats_out, sizeof(int64_t) * AQUA_N_STATS, cudaMemcpyDeviceToHost, s));
+    AQ_CUDA(cudaStreamSynchronize(s));
+    return AQUA_OK;
+}
+
+}  // extern "C"

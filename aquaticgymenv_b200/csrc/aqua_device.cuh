@@ -1,5 +1,9 @@
 // aqua_device.cuh -- device-side primitives of the batched AquaGym step (sm_100a).
 //
+// Compiled with -fmad=false: every fused multiply-add below is written out as fma(), so the
+// arithmetic (and hence every trajectory) is the same in all kernels that inline these functions
+// and does not depend on the compiler's contraction choices.
+//
 // One env instance is advanced by one call of step_env<R>() with its whole state in
 // registers.  The kinematics use the closed form of the reference's ICC rotation
 // (gym_aqua/envs/aqua.py:159-183; derivation in DESIGN.md section 3) instead of the reference's
@@ -10,6 +14,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/aquagym.h"
+#include "aqua_kernels.cuh"
 
 namespace aqua {
 
@@ -21,28 +26,28 @@ enum : uint32_t { kStreamReset = 1u, kStreamWaveInit = 2u, kStreamWaveNoise = 3u
 
 // ------------------------------------------------------------------------------------------
 // Philox4x32-10 (Salmon et al. 2011).  key = seed, counter = (env id, c1, c2, stream tag).
+// The ten round keys (k0 + r*W0, k1 + r*W1) are computed once on the host and travel in the
+// kernel parameter block, so that they are constant-bank operands of the round's XORs.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1) {
+                                               const PhiloxKeys& k) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
         const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.rk[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.rk[2 * r + 1];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
         c0 = n0;
         c2 = n2;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
 
-__device__ __forceinline__ uint4 philox_env(uint64_t seed, uint32_t env_id, uint32_t c1, uint32_t c2,
+__device__ __forceinline__ uint4 philox_env(const PhiloxKeys& k, uint32_t env_id, uint32_t c1, uint32_t c2,
                                             uint32_t tag) {
-    return philox4x32_10(env_id, c1, c2, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
+    return philox4x32_10(env_id, c1, c2, tag, k);
 }
 
 // 24 high bits -> float in [0,1), exact
@@ -59,9 +64,9 @@ __device__ __forceinline__ float draw_noise(uint32_t u) { return __fmaf_rn(u01(u
 __device__ __forceinline__ float draw_thrust(uint32_t u) { return __fmaf_rn(u01(u), 0.3f, 0.2f); }
 
 // wave increment of step `t` (env time before the increment) -- aqua.py:188
-__device__ __forceinline__ void draw_wave_noise(uint64_t seed, uint32_t env_id, uint32_t ep, uint32_t t,
-                                                float& nx, float& ny) {
-    const uint4 r = philox_env(seed, env_id, ep, t >> 1, kStreamWaveNoise);
+__device__ __forceinline__ void draw_wave_noise(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
+                                                uint32_t t, float& nx, float& ny) {
+    const uint4 r = philox_env(keys, env_id, ep, t >> 1, kStreamWaveNoise);
     const bool odd = (t & 1u) != 0u;
     nx = draw_noise(odd ? r.z : r.x);
     ny = draw_noise(odd ? r.w : r.y);
@@ -109,7 +114,7 @@ __device__ __forceinline__ void hits_obstacles(const ObstacleTable<R>& tab, int 
         for (int j = 0; j < V; ++j) {
             const R ddx = fmax(fabs(px[j] - o.cx) - o.hx, R(0));
             const R ddy = fmax(fabs(py[j] - o.cy) - o.hy, R(0));
-            hit[j] |= (ddx * ddx + ddy * ddy <= r2);
+            hit[j] |= (fma(ddx, ddx, ddy * ddy) <= r2);
         }
     }
 }
@@ -122,7 +127,7 @@ __device__ __forceinline__ bool hits_obstacle_g(const double* __restrict__ tab64
         const double* o = tab64 + 5 * k;
         const double ddx = fmax(fabs(px - o[0]) - o[2], 0.0);
         const double ddy = fmax(fabs(py - o[1]) - o[3], 0.0);
-        if (ddx * ddx + ddy * ddy <= o[4]) return true;
+        if (fma(ddx, ddx, ddy * ddy) <= o[4]) return true;
     }
     return false;
 }
@@ -142,14 +147,14 @@ struct ResetResult {
 
 // env.reset() for one env: aqua.py:100-126.  `ep` is the NEW episode index.  Try n of the
 // reference's `observation_space.sample()` sequence is Philox(env, ep, n, RESET).
-__device__ __noinline__ ResetResult reset_env(uint64_t seed, uint32_t env_id, uint32_t ep,
+__device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
                                               const double* __restrict__ tab64, int k_obst,
                                               WorldFlags wf) {
     ResetResult o;
     uint32_t n = 0;
     if (wf.random_goal) {  // aqua.py:102-105
         for (;;) {
-            const uint4 r = philox_env(seed, env_id, ep, n++, kStreamReset);
+            const uint4 r = philox_env(keys, env_id, ep, n++, kStreamReset);
             o.gx = (double)draw_pos(r.z);
             o.gy = (double)draw_pos(r.w);
             if (n >= kResetMaxTries) break;
@@ -161,13 +166,13 @@ __device__ __noinline__ ResetResult reset_env(uint64_t seed, uint32_t env_id, ui
     }
     if (wf.random_boat) {  // aqua.py:110-115
         for (;;) {
-            const uint4 r = philox_env(seed, env_id, ep, n++, kStreamReset);
+            const uint4 r = philox_env(keys, env_id, ep, n++, kStreamReset);
             o.x = (double)draw_pos(r.x);
             o.y = (double)draw_pos(r.y);
             o.th = (double)draw_angle(r.z);
             if (n >= kResetMaxTries) break;
             const double dgx = o.gx - o.x, dgy = o.gy - o.y;
-            const bool reached = sqrt(dgx * dgx + dgy * dgy) - 5.0 <= 0.0;  // aqua.py:421-422
+            const bool reached = sqrt(fma(dgx, dgx, dgy * dgy)) - 5.0 <= 0.0;  // aqua.py:421-422
             if (!(reached || outside_border(o.x, o.y) || hits_obstacle_g(tab64, k_obst, o.x, o.y))) break;
         }
     } else {  // aqua.py:117
@@ -176,7 +181,7 @@ __device__ __noinline__ ResetResult reset_env(uint64_t seed, uint32_t env_id, ui
         o.th = 0.0;
     }
     if (wf.waves) {  // aqua.py:124
-        const uint4 r = philox_env(seed, env_id, ep, 0u, kStreamWaveInit);
+        const uint4 r = philox_env(keys, env_id, ep, 0u, kStreamWaveInit);
         o.wx = (double)draw_wave0(r.x);
         o.wy = (double)draw_wave0(r.y);
     } else {
@@ -234,14 +239,14 @@ __device__ __forceinline__ void move_env(EnvState<R>& e, R tl, R tr, R nx, R ny,
     const R h2 = h * h;
     // sin(h)/h for |h| <= 0.06
     if constexpr (kF64)
-        sinc = R(1) + h2 * (R(-1.0 / 6) + h2 * (R(1.0 / 120) + h2 * (R(-1.0 / 5040) + h2 * R(1.0 / 362880))));
+        sinc = fma(h2, fma(h2, fma(h2, fma(h2, R(1.0 / 362880), R(-1.0 / 5040)), R(1.0 / 120)), R(-1.0 / 6)), R(1));
     else
-        sinc = R(1) + h2 * (R(-1.0 / 6) + h2 * R(1.0 / 120));
+        sinc = fma(h2, fma(h2, R(1.0 / 120), R(-1.0 / 6)), R(1));
     const R chord = v * sinc;
     R sn, cs;
     P::sincos_(e.th + h, &sn, &cs);
-    m.dx = e.wx - chord * sn;  // heading 0 = +y; aqua.py:173-181, tau = 1
-    m.dy = e.wy + chord * cs;
+    m.dx = fma(-chord, sn, e.wx);  // heading 0 = +y; aqua.py:173-181, tau = 1
+    m.dy = fma(chord, cs, e.wy);
     m.px = e.x;
     m.py = e.y;
     e.x = m.px + m.dx;
@@ -253,6 +258,9 @@ __device__ __forceinline__ void move_env(EnvState<R>& e, R tl, R tr, R nx, R ny,
         const R wmax = R(0.05);
         e.wx = fmin(fmax(e.wx + nx, -wmax), wmax);
         e.wy = fmin(fmax(e.wy + ny, -wmax), wmax);
+    } else {  // has_waves = 0 clips to [0, 0] (aqua.py:23-25,189-191)
+        e.wx = R(0);
+        e.wy = R(0);
     }
 
     // ---- time, aqua.py:141 ----
@@ -276,9 +284,9 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
     collided |= hit_obstacle;
 
     const R gcx = xn - e.gx, gcy = yn - e.gy;
-    const R dc2 = gcx * gcx + gcy * gcy;
+    const R dc2 = fma(gcx, gcx, gcy * gcy);
     const R gpx = m.px - e.gx, gpy = m.py - e.gy;
-    const R dp2 = gpx * gpx + gpy * gpy;
+    const R dp2 = fma(gpx, gpx, gpy * gpy);
     R step_reward;
     bool reached;
     if constexpr (kF64) {  // the reference's expressions: aqua.py:89-90, 392-402, 421-422
@@ -289,7 +297,7 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
         // d_prev - d_cur = (d_prev^2 - d_cur^2) / (d_prev + d_cur), the numerator taken from the
         // displacement itself: no cancellation of two ~50 px norms in float32
         reached = dc2 <= R(25);
-        const R num = -(m.dx * (R(2) * gpx + m.dx) + m.dy * (R(2) * gpy + m.dy));
+        const R num = -fma(m.dx, fma(R(2), gpx, m.dx), m.dy * fma(R(2), gpy, m.dy));
         const R den = P::sqrt_(dp2) + P::sqrt_(dc2);
         step_reward = R(0.7) * __fdividef(num, den);
     }

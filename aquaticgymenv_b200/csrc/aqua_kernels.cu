@@ -1,0 +1,677 @@
+// aqua_kernels.cu -- the sm_100a kernels of the batched AquaGym environment step.
+//
+// Replaces AquaEnv.step()/reset() of the reference (gym_aqua/envs/aqua.py:100-126, 135-213) for
+// N independent env instances.  One thread owns V consecutive envs (V = 4 float / 2 double) so
+// that every state plane is read and written with one 16-byte access; the obstacle table sits in
+// shared memory; episode statistics are folded with warp reductions into per-CTA slots.
+// The step is elementwise: there is no contraction, hence no tensor-core work; the bound is HBM
+// bandwidth (65 B per discrete env-step).
+#include "aqua_device.cuh"
+
+namespace aqua {
+
+// ------------------------------------------------------------------------------------------
+// vector access helpers
+// ------------------------------------------------------------------------------------------
+template <typename T, int V> struct alignas(sizeof(T) * V <= 16 ? sizeof(T) * V : 16) Pack {
+    T v[V];
+};
+template <typename T, int V> __device__ __forceinline__ Pack<T, V> ld_pack(const T* p) {
+    return *reinterpret_cast<const Pack<T, V>*>(p);
+}
+template <typename T, int V> __device__ __forceinline__ void st_pack(T* p, const Pack<T, V>& v) {
+    *reinterpret_cast<Pack<T, V>*>(p) = v;
+}
+// read-only (non-coherent) path for the caller's action / noise buffers
+template <typename T, int V> __device__ __forceinline__ Pack<T, V> ldg_pack(const T* p) {
+    Pack<T, V> out;
+    if constexpr (sizeof(T) * V == 16) {
+        const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+        memcpy(&out, &r, 16);
+    } else if constexpr (sizeof(T) * V == 32) {
+        const uint4 r0 = __ldg(reinterpret_cast<const uint4*>(p));
+        const uint4 r1 = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        memcpy(&out, &r0, 16);
+        memcpy(reinterpret_cast<char*>(&out) + 16, &r1, 16);
+    } else if constexpr (sizeof(T) * V == 8) {
+        const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+        memcpy(&out, &r, 8);
+    } else if constexpr (sizeof(T) * V == 4) {
+        const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
+        memcpy(&out, &r, 4);
+    } else {
+        static_assert(sizeof(T) * V == 2, "unsupported pack");
+        const unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
+        memcpy(&out, &r, 2);
+    }
+    return out;
+}
+
+template <typename R> __device__ __forceinline__ R* plane(void* planes, int64_t ld, int p) {
+    return reinterpret_cast<R*>(planes) + (int64_t)p * ld;
+}
+template <typename R> __device__ __forceinline__ uint32_t* plane_tw(void* planes, int64_t ld) {
+    return reinterpret_cast<uint32_t*>(reinterpret_cast<R*>(planes) + (int64_t)7 * ld);
+}
+
+// ------------------------------------------------------------------------------------------
+// action decode for V envs starting at absolute env index `base`
+// ------------------------------------------------------------------------------------------
+template <typename R, int ACT, int V>
+__device__ __forceinline__ void load_thrusts(const void* actions, int64_t base, int nvalid, R (&tl)[V],
+                                             R (&tr)[V], uint32_t& bad) {
+    if constexpr (ACT == AQUA_ACT_F32X2) {
+        float a[2 * V];
+        const float* src = reinterpret_cast<const float*>(actions) + 2 * base;
+        if (nvalid == V) {
+            const Pack<float, 2 * V> pk = ldg_pack<float, 2 * V>(src);
+#pragma unroll
+            for (int j = 0; j < 2 * V; ++j) a[j] = pk.v[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2 * V; ++j) a[j] = (j < 2 * nvalid) ? __ldg(src + j) : 0.5f;
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            uint32_t b = 0;
+            decode_continuous<R>(a[2 * j], a[2 * j + 1], tl[j], tr[j], b);
+            bad += (j < nvalid) ? b : 0u;
+        }
+    } else {
+        long long a[V];
+        if constexpr (ACT == AQUA_ACT_I32) {
+            const int32_t* src = reinterpret_cast<const int32_t*>(actions) + base;
+            if (nvalid == V) {
+                const Pack<int32_t, V> pk = ldg_pack<int32_t, V>(src);
+#pragma unroll
+                for (int j = 0; j < V; ++j) a[j] = pk.v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? __ldg(src + j) : 2;
+            }
+        } else if constexpr (ACT == AQUA_ACT_I64) {
+            const long long* src = reinterpret_cast<const long long*>(actions) + base;
+            if (nvalid == V) {
+                const Pack<long long, V> pk = ldg_pack<long long, V>(src);
+#pragma unroll
+                for (int j = 0; j < V; ++j) a[j] = pk.v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? __ldg(src + j) : 2;
+            }
+        } else {
+            static_assert(ACT == AQUA_ACT_U8, "unknown action dtype");
+            const uint8_t* src = reinterpret_cast<const uint8_t*>(actions) + base;
+            if (nvalid == V) {
+                const Pack<uint8_t, V> pk = ldg_pack<uint8_t, V>(src);
+#pragma unroll
+                for (int j = 0; j < V; ++j) a[j] = pk.v[j];
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? __ldg(src + j) : 2;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            uint32_t b = 0;
+            decode_discrete<R>(a[j], tl[j], tr[j], b);
+            bad += (j < nvalid) ? b : 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-thread episode statistics and their reduction
+// ------------------------------------------------------------------------------------------
+struct ThreadStats {
+    uint32_t done = 0, collided = 0, timeout = 0, success = 0, length = 0, steps = 0, bad = 0;
+    long long reward_fx = 0;  // sum of step rewards, fixed point 2^-20
+
+    template <typename R> __device__ __forceinline__ void add(uint32_t flags, uint32_t time_after, R reward) {
+        done += flags & 1u;
+        collided += (flags >> 1) & 1u;
+        timeout += (flags >> 2) & 1u;
+        success += (flags >> 3) & 1u;
+        length += (flags & 1u) ? time_after : 0u;
+        steps += 1u;
+        int fx;
+        if constexpr (sizeof(R) == 8) fx = __double2int_rn(reward * R(AQUA_REWARD_FIXED_POINT));
+        else fx = __float2int_rn(reward * R(AQUA_REWARD_FIXED_POINT));
+        reward_fx += fx;
+    }
+};
+
+// warp reduce (REDUX) -> shared slots -> one global atomic per counter per CTA
+__device__ __forceinline__ void flush_stats(const ThreadStats& t, unsigned long long* s_stats,
+                                            unsigned long long* g_slots) {
+    const unsigned full = 0xffffffffu;
+    const uint32_t d = __reduce_add_sync(full, t.done);
+    const uint32_t c = __reduce_add_sync(full, t.collided);
+    const uint32_t o = __reduce_add_sync(full, t.timeout);
+    const uint32_t s = __reduce_add_sync(full, t.success);
+    const uint32_t l = __reduce_add_sync(full, t.length);
+    const uint32_t n = __reduce_add_sync(full, t.steps);
+    const uint32_t b = __reduce_add_sync(full, t.bad);
+    long long r = t.reward_fx;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(full, r, off);
+    if ((threadIdx.x & 31) == 0) {
+        if (d) atomicAdd(&s_stats[AQUA_STAT_EPISODES], (unsigned long long)d);
+        if (c) atomicAdd(&s_stats[AQUA_STAT_COLLIDED], (unsigned long long)c);
+        if (o) atomicAdd(&s_stats[AQUA_STAT_TIMEOUT], (unsigned long long)o);
+        if (s) atomicAdd(&s_stats[AQUA_STAT_SUCCESS], (unsigned long long)s);
+        if (l) atomicAdd(&s_stats[AQUA_STAT_LENGTH_SUM], (unsigned long long)l);
+        if (n) atomicAdd(&s_stats[AQUA_STAT_STEPS], (unsigned long long)n);
+        if (b) atomicAdd(&s_stats[AQUA_STAT_BAD_ACTIONS], (unsigned long long)b);
+        if (r) atomicAdd(&s_stats[AQUA_STAT_REWARD_SUM], (unsigned long long)r);
+    }
+    __syncthreads();
+    if (threadIdx.x < AQUA_N_STATS) {
+        const unsigned long long v = s_stats[threadIdx.x];
+        if (v) atomicAdd(&g_slots[(blockIdx.x % kStatSlots) * AQUA_N_STATS + threadIdx.x], v);
+    }
+}
+
+template <typename R>
+__device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g_tab, int k_obst) {
+    // words of box[] actually used, then r2[]
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(g_tab);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
+    constexpr int kWordsPerBox = sizeof(ObstacleBox<R>) / 4;
+    constexpr int kR2Off = sizeof(ObstacleBox<R>) * AQUA_MAX_OBSTACLES / 4;
+    constexpr int kWordsPerR = sizeof(R) / 4;
+    for (int i = threadIdx.x; i < k_obst * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < k_obst * kWordsPerR; i += blockDim.x) dst[kR2Off + i] = __ldg(src + kR2Off + i);
+}
+
+template <typename R>
+__device__ __forceinline__ void apply_reset(EnvState<R>& e, const ResetResult& r, uint32_t ep) {
+    e.x = (R)r.x;  // draws are float32 values: exact in either precision
+    e.y = (R)r.y;
+    e.th = (R)r.th;
+    e.wx = (R)r.wx;
+    e.wy = (R)r.wy;
+    e.gx = (R)r.gx;
+    e.gy = (R)r.gy;
+    e.tw = ep << AQUA_TIME_BITS;
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: env.step(action) for a range of envs -- aqua.py:135-213 (+ reset aqua.py:100-126 when an
+// env finishes and autoreset is on)
+// ------------------------------------------------------------------------------------------
+template <typename R, int ACT, bool INJECT>
+__global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_constant__ StepArgs p) {
+    constexpr int V = Prec<R>::V;
+    __shared__ ObstacleTable<R> tab;
+    __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    stage_table<R>(tab, p.w.tab, p.w.k_obst);
+    if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const int64_t ld = p.ld;
+    R* const px_ = plane<R>(p.planes, ld, 0);
+    R* const py_ = plane<R>(p.planes, ld, 1);
+    R* const pth_ = plane<R>(p.planes, ld, 2);
+    R* const pwx_ = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X);
+    R* const pwy_ = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y);
+    R* const pgx_ = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X);
+    R* const pgy_ = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y);
+    uint32_t* const ptw_ = plane_tw<R>(p.planes, ld);
+    const bool waves = p.w.waves != 0;
+    const int k_obst = p.w.k_obst;
+    const int64_t tile_envs = (int64_t)blockDim.x * V;
+
+    ThreadStats st;
+    for (int64_t base = p.env_begin + (int64_t)blockIdx.x * tile_envs + (int64_t)threadIdx.x * V;
+         base < p.env_end; base += (int64_t)gridDim.x * tile_envs) {
+        const int nvalid = (int)min((int64_t)V, p.env_end - base);
+
+        // ---- loads: one 16-byte access per plane (the planes are padded to AQUA_TILE) ----
+        const Pack<R, V> vx = ld_pack<R, V>(px_ + base), vy = ld_pack<R, V>(py_ + base);
+        const Pack<R, V> vth = ld_pack<R, V>(pth_ + base);
+        const Pack<R, V> vwx = ld_pack<R, V>(pwx_ + base), vwy = ld_pack<R, V>(pwy_ + base);
+        const Pack<R, V> vgx = ld_pack<R, V>(pgx_ + base), vgy = ld_pack<R, V>(pgy_ + base);
+        const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(ptw_ + base);
+        R tl[V], tr[V];
+        load_thrusts<R, ACT, V>(p.actions, base, nvalid, tl, tr, st.bad);
+
+        EnvState<R> e[V];
+        MoveTmp<R> m[V];
+        R pxn[V], pyn[V];
+        bool hit[V];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
+            e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
+            e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
+            e[j].tw = vtw.v[j];
+            const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
+            float nx = 0.f, ny = 0.f;
+            if constexpr (INJECT) {
+                if (j < nvalid) {
+                    nx = __ldg(p.noise_x + base + j);
+                    ny = __ldg(p.noise_y + base + j);
+                }
+            } else {
+                if (waves)
+                    draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
+            }
+            move_env<R>(e[j], tl[j], tr[j], (R)nx, (R)ny, waves, m[j]);
+            pxn[j] = e[j].x;
+            pyn[j] = e[j].y;
+            hit[j] = false;
+        }
+        hits_obstacles<R, V>(tab, k_obst, pxn, pyn, hit);
+
+        Pack<R, V> vrew;
+        Pack<uint8_t, V> vfl;
+        bool any_reset = false;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            R reward;
+            const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
+            vrew.v[j] = reward;
+            vfl.v[j] = (uint8_t)f;
+            if (j < nvalid) st.add<R>(f, e[j].tw & kTimeMask, reward);
+            if ((f & AQUA_FLAG_DONE) && p.w.autoreset) {  // rare and divergent: out of line
+                const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
+                const uint32_t ep = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+                const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, k_obst,
+                                                 WorldFlags{waves, p.w.random_boat != 0, p.w.random_goal != 0});
+                apply_reset<R>(e[j], rr, ep);
+                any_reset = true;
+            }
+        }
+
+        // ---- stores ----
+        Pack<R, V> ox, oy, oth, owx, owy;
+        Pack<uint32_t, V> otw;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+            owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
+        }
+        st_pack<R, V>(px_ + base, ox);
+        st_pack<R, V>(py_ + base, oy);
+        st_pack<R, V>(pth_ + base, oth);
+        st_pack<R, V>(pwx_ + base, owx);
+        st_pack<R, V>(pwy_ + base, owy);
+        st_pack<uint32_t, V>(ptw_ + base, otw);
+        if (any_reset) {  // the goal only changes at reset
+            Pack<R, V> ogx, ogy;
+#pragma unroll
+            for (int j = 0; j < V; ++j) { ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; }
+            st_pack<R, V>(pgx_ + base, ogx);
+            st_pack<R, V>(pgy_ + base, ogy);
+        }
+        R* const rew = reinterpret_cast<R*>(p.reward) + base;
+        uint8_t* const fl = p.flags + base;
+        if (nvalid == V) {
+            st_pack<R, V>(rew, vrew);
+            st_pack<uint8_t, V>(fl, vfl);
+        } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (j < nvalid) { rew[j] = vrew.v[j]; fl[j] = vfl.v[j]; }
+        }
+    }
+    flush_stats(st, s_stats, p.stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1r: `steps` env-steps per launch under the synthetic random policy (ACTION stream); the
+// state stays in registers between steps, per-step reward/flags are folded into the statistics
+// ------------------------------------------------------------------------------------------
+template <typename R, bool CONTINUOUS>
+__global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_constant__ StepArgs p) {
+    constexpr int V = Prec<R>::V;
+    __shared__ ObstacleTable<R> tab;
+    __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    stage_table<R>(tab, p.w.tab, p.w.k_obst);
+    if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    __syncthreads();
+
+    const int64_t ld = p.ld;
+    const bool waves = p.w.waves != 0;
+    const int k_obst = p.w.k_obst;
+    const int64_t tile_envs = (int64_t)blockDim.x * V;
+    const WorldFlags wf{waves, p.w.random_boat != 0, p.w.random_goal != 0};
+
+    ThreadStats st;
+    for (int64_t base = p.env_begin + (int64_t)blockIdx.x * tile_envs + (int64_t)threadIdx.x * V;
+         base < p.env_end; base += (int64_t)gridDim.x * tile_envs) {
+        const int nvalid = (int)min((int64_t)V, p.env_end - base);
+        EnvState<R> e[V];
+        {
+            const Pack<R, V> vx = ld_pack<R, V>(plane<R>(p.planes, ld, 0) + base);
+            const Pack<R, V> vy = ld_pack<R, V>(plane<R>(p.planes, ld, 1) + base);
+            const Pack<R, V> vth = ld_pack<R, V>(plane<R>(p.planes, ld, 2) + base);
+            const Pack<R, V> vwx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base);
+            const Pack<R, V> vwy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base);
+            const Pack<R, V> vgx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base);
+            const Pack<R, V> vgy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base);
+            const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(plane_tw<R>(p.planes, ld) + base);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
+                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
+                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
+                e[j].tw = vtw.v[j];
+            }
+        }
+        for (int64_t k = 0; k < p.steps; ++k) {
+            const uint64_t step = p.step0 + (uint64_t)k;
+            MoveTmp<R> m[V];
+            R pxn[V], pyn[V];
+            bool hit[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
+                const uint4 ra = philox_env(p.w.keys, env_id, (uint32_t)step, (uint32_t)(step >> 32), kStreamAction);
+                R tl, tr;
+                uint32_t bad = 0;
+                if constexpr (CONTINUOUS) {
+                    decode_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), tl, tr, bad);
+                } else {
+                    decode_discrete<R>((long long)__umulhi(ra.x, 3u), tl, tr, bad);
+                }
+                float nx = 0.f, ny = 0.f;
+                if (waves)
+                    draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
+                move_env<R>(e[j], tl, tr, (R)nx, (R)ny, waves, m[j]);
+                pxn[j] = e[j].x;
+                pyn[j] = e[j].y;
+                hit[j] = false;
+            }
+            hits_obstacles<R, V>(tab, k_obst, pxn, pyn, hit);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                R reward;
+                const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
+                if (j < nvalid) st.add<R>(f, e[j].tw & kTimeMask, reward);
+                if (f & AQUA_FLAG_DONE) {
+                    const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
+                    const uint32_t ep = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+                    const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, k_obst, wf);
+                    apply_reset<R>(e[j], rr, ep);
+                }
+            }
+        }
+        Pack<R, V> ox, oy, oth, owx, owy, ogx, ogy;
+        Pack<uint32_t, V> otw;
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+            owx.v[j] = e[j].wx; owy.v[j] = e[j].wy;
+            ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; otw.v[j] = e[j].tw;
+        }
+        st_pack<R, V>(plane<R>(p.planes, ld, 0) + base, ox);
+        st_pack<R, V>(plane<R>(p.planes, ld, 1) + base, oy);
+        st_pack<R, V>(plane<R>(p.planes, ld, 2) + base, oth);
+        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base, owx);
+        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base, owy);
+        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base, ogx);
+        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base, ogy);
+        st_pack<uint32_t, V>(plane_tw<R>(p.planes, ld) + base, otw);
+    }
+    flush_stats(st, s_stats, p.stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: env.reset() -- aqua.py:100-126.  One thread per env (not a bandwidth path).
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__global__ void __launch_bounds__(kMaxThreads) reset_kernel(const __grid_constant__ StepArgs p,
+                                                            const uint8_t* __restrict__ mask) {
+    const int64_t i = p.env_begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.env_end) return;
+    if (mask != nullptr && mask[i] == 0) return;
+    uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
+    const uint32_t ep = ((ptw[i] >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+    const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
+    const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, p.w.k_obst,
+                                     WorldFlags{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0});
+    EnvState<R> e;
+    apply_reset<R>(e, rr, ep);
+    plane<R>(p.planes, p.ld, 0)[i] = e.x;
+    plane<R>(p.planes, p.ld, 1)[i] = e.y;
+    plane<R>(p.planes, p.ld, 2)[i] = e.th;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_X)[i] = e.wx;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_Y)[i] = e.wy;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_X)[i] = e.gx;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_Y)[i] = e.gy;
+    ptw[i] = e.tw;
+}
+
+// fresh handle: no episode opened yet (the first reset opens episode 0), pose planes zero
+template <typename R>
+__global__ void init_state_kernel(void* planes, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+#pragma unroll
+    for (int pl = 0; pl < 7; ++pl) plane<R>(planes, ld, pl)[i] = R(0);
+    plane_tw<R>(planes, ld)[i] = AQUA_EPISODE_MASK << AQUA_TIME_BITS;
+}
+
+// synthetic random policy: `action_space.sample()` (test_random.py:19-20) from the ACTION stream
+template <int ACT>
+__global__ void random_actions_kernel(const __grid_constant__ World w, int64_t n, uint64_t step, void* actions) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t env_id = (uint32_t)(w.env_id_base + (uint64_t)i);
+    const uint4 r = philox_env(w.keys, env_id, (uint32_t)step, (uint32_t)(step >> 32), kStreamAction);
+    if constexpr (ACT == AQUA_ACT_F32X2) {
+        reinterpret_cast<float2*>(actions)[i] = make_float2(draw_thrust(r.x), draw_thrust(r.y));
+    } else {
+        const uint32_t a = __umulhi(r.x, 3u);
+        if constexpr (ACT == AQUA_ACT_I32) reinterpret_cast<int32_t*>(actions)[i] = (int32_t)a;
+        else if constexpr (ACT == AQUA_ACT_I64) reinterpret_cast<long long*>(actions)[i] = (long long)a;
+        else reinterpret_cast<uint8_t*>(actions)[i] = (uint8_t)a;
+    }
+}
+
+// canonical double[9][n] {x, y, theta, wave_x, wave_y, goal_x, goal_y, time, episode} <-> planes
+__host__ __device__ constexpr int canonical_plane(int k) {
+    return k < 3 ? k : (k < 5 ? AQUA_PLANE_WAVE_X + (k - 3) : AQUA_PLANE_GOAL_X + (k - 5));
+}
+template <typename R>
+__global__ void get_state_kernel(const void* planes, int64_t ld, int64_t n, double* __restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    void* pl = const_cast<void*>(planes);
+#pragma unroll
+    for (int k = 0; k < 7; ++k) out[(int64_t)k * n + i] = (double)plane<R>(pl, ld, canonical_plane(k))[i];
+    const uint32_t tw = plane_tw<R>(pl, ld)[i];
+    out[(int64_t)7 * n + i] = (double)(tw & kTimeMask);
+    out[(int64_t)8 * n + i] = (double)(tw >> AQUA_TIME_BITS);
+}
+template <typename R>
+__global__ void set_state_kernel(void* planes, int64_t ld, int64_t n, const double* __restrict__ in) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) plane<R>(planes, ld, canonical_plane(k))[i] = (R)in[(int64_t)k * n + i];
+    const uint32_t t = min((uint32_t)in[(int64_t)7 * n + i], kTimeMask);
+    const uint32_t ep = (uint32_t)in[(int64_t)8 * n + i] & kEpisodeMask;
+    plane_tw<R>(planes, ld)[i] = (ep << AQUA_TIME_BITS) | t;
+}
+
+// K3: fold the per-CTA slots into int64[AQUA_N_STATS]
+__global__ void stats_reduce_kernel(unsigned long long* slots, int64_t* out, int clear) {
+    __shared__ unsigned long long s[AQUA_N_STATS];
+    if (threadIdx.x < AQUA_N_STATS) s[threadIdx.x] = 0ull;
+    __syncthreads();
+    unsigned long long acc[AQUA_N_STATS];
+#pragma unroll
+    for (int k = 0; k < AQUA_N_STATS; ++k) acc[k] = 0ull;
+    for (int slot = threadIdx.x; slot < kStatSlots; slot += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < AQUA_N_STATS; ++k) {
+            acc[k] += slots[slot * AQUA_N_STATS + k];
+            if (clear) slots[slot * AQUA_N_STATS + k] = 0ull;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < AQUA_N_STATS; ++k) {
+        unsigned long long v = acc[k];
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s[k], v);
+    }
+    __syncthreads();
+    if (threadIdx.x < AQUA_N_STATS) out[threadIdx.x] = (int64_t)s[threadIdx.x];
+}
+
+// ------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------
+template <typename R, int ACT>
+static cudaError_t launch_step_t(const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+    if (a.noise_x != nullptr) step_kernel<R, ACT, true><<<g.blocks, g.threads, 0, s>>>(a);
+    else step_kernel<R, ACT, false><<<g.blocks, g.threads, 0, s>>>(a);
+    return cudaGetLastError();
+}
+template <typename R>
+static cudaError_t launch_step_r(int act, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+    switch (act) {
+        case AQUA_ACT_I32: return launch_step_t<R, AQUA_ACT_I32>(a, g, s);
+        case AQUA_ACT_I64: return launch_step_t<R, AQUA_ACT_I64>(a, g, s);
+        case AQUA_ACT_U8: return launch_step_t<R, AQUA_ACT_U8>(a, g, s);
+        case AQUA_ACT_F32X2: return launch_step_t<R, AQUA_ACT_F32X2>(a, g, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+    return precision == AQUA_F64 ? launch_step_r<double>(action_dtype, a, g, s)
+                                 : launch_step_r<float>(action_dtype, a, g, s);
+}
+
+template <typename R, int ACT> static const void* step_fn() {
+    return reinterpret_cast<const void*>(&step_kernel<R, ACT, false>);
+}
+template <typename R> static const void* step_fn_r(int act) {
+    switch (act) {
+        case AQUA_ACT_I32: return step_fn<R, AQUA_ACT_I32>();
+        case AQUA_ACT_I64: return step_fn<R, AQUA_ACT_I64>();
+        case AQUA_ACT_U8: return step_fn<R, AQUA_ACT_U8>();
+        case AQUA_ACT_F32X2: return step_fn<R, AQUA_ACT_F32X2>();
+        default: return nullptr;
+    }
+}
+cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm) {
+    const void* fn = precision == AQUA_F64 ? step_fn_r<double>(action_dtype) : step_fn_r<float>(action_dtype);
+    if (fn == nullptr) return cudaErrorInvalidValue;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
+}
+
+cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+    if (precision == AQUA_F64) {
+        if (continuous) rollout_kernel<double, true><<<g.blocks, g.threads, 0, s>>>(a);
+        else rollout_kernel<double, false><<<g.blocks, g.threads, 0, s>>>(a);
+    } else {
+        if (continuous) rollout_kernel<float, true><<<g.blocks, g.threads, 0, s>>>(a);
+        else rollout_kernel<float, false><<<g.blocks, g.threads, 0, s>>>(a);
+    }
+    return cudaGetLastError();
+}
+cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* blocks_per_sm) {
+    const void* fn;
+    if (precision == AQUA_F64)
+        fn = continuous ? reinterpret_cast<const void*>(&rollout_kernel<double, true>)
+                        : reinterpret_cast<const void*>(&rollout_kernel<double, false>);
+    else
+        fn = continuous ? reinterpret_cast<const void*>(&rollout_kernel<float, true>)
+                        : reinterpret_cast<const void*>(&rollout_kernel<float, false>);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
+}
+
+static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+cudaError_t launch_reset(int precision, const StepArgs& a, const uint8_t* mask, cudaStream_t s) {
+    const int64_t n = a.env_end - a.env_begin;
+    if (n <= 0) return cudaSuccess;
+    const int threads = 128;
+    if (precision == AQUA_F64) reset_kernel<double><<<blocks_for(n, threads), threads, 0, s>>>(a, mask);
+    else reset_kernel<float><<<blocks_for(n, threads), threads, 0, s>>>(a, mask);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_init_state(int precision, void* planes, int64_t ld, cudaStream_t s) {
+    const int threads = 256;
+    if (precision == AQUA_F64) init_state_kernel<double><<<blocks_for(ld, threads), threads, 0, s>>>(planes, ld);
+    else init_state_kernel<float><<<blocks_for(ld, threads), threads, 0, s>>>(planes, ld);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_random_actions(const World& w, int64_t n, uint64_t step_index, void* actions,
+                                  int action_dtype, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int threads = 256, blocks = blocks_for(n, threads);
+    switch (action_dtype) {
+        case AQUA_ACT_I32: random_actions_kernel<AQUA_ACT_I32><<<blocks, threads, 0, s>>>(w, n, step_index, actions); break;
+        case AQUA_ACT_I64: random_actions_kernel<AQUA_ACT_I64><<<blocks, threads, 0, s>>>(w, n, step_index, actions); break;
+        case AQUA_ACT_U8: random_actions_kernel<AQUA_ACT_U8><<<blocks, threads, 0, s>>>(w, n, step_index, actions); break;
+        case AQUA_ACT_F32X2: random_actions_kernel<AQUA_ACT_F32X2><<<blocks, threads, 0, s>>>(w, n, step_index, actions); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_get_state(int precision, const void* planes, int64_t ld, int64_t n, double* out,
+                             cudaStream_t s) {
+    const int threads = 256;
+    if (precision == AQUA_F64) get_state_kernel<double><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, out);
+    else get_state_kernel<float><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n, const double* in,
+                             cudaStream_t s) {
+    const int threads = 256;
+    if (precision == AQUA_F64) set_state_kernel<double><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, in);
+    else set_state_kernel<float><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, in);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s) {
+    stats_reduce_kernel<<<1, 256, 0, s>>>(slots, out, clear);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side obstacle tables (aqua.py:56-68, 373-390)
+// ------------------------------------------------------------------------------------------
+size_t obstacle_table_bytes(int precision) {
+    return precision == AQUA_F64 ? sizeof(ObstacleTable<double>) : sizeof(ObstacleTable<float>);
+}
+
+template <typename R> static void fill_table(int k, const double* rows5, ObstacleTable<R>* t) {
+    memset(t, 0, sizeof(*t));
+    for (int i = 0; i < k; ++i) {
+        const double* o = rows5 + 5 * i;
+        const bool circle = o[2] == 0.0;
+        t->box[i].cx = (R)o[0];
+        t->box[i].cy = (R)o[1];
+        t->box[i].hx = circle ? R(0) : (R)(o[3] / 2);
+        t->box[i].hy = circle ? R(0) : (R)(o[4] / 2);
+        const double reach = circle ? o[3] + 2.5 : 2.5;  // boat radius 2.5, aqua.py:75
+        t->r2[i] = (R)(reach * reach);
+    }
+}
+
+void build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host) {
+    if (precision == AQUA_F64) fill_table<double>(k, rows5, reinterpret_cast<ObstacleTable<double>*>(tab_host));
+    else fill_table<float>(k, rows5, reinterpret_cast<ObstacleTable<float>*>(tab_host));
+    for (int i = 0; i < k; ++i) {
+        const double* o = rows5 + 5 * i;
+        const bool circle = o[2] == 0.0;
+        double* d = tab64_host + 5 * i;
+        d[0] = o[0];
+        d[1] = o[1];
+        d[2] = circle ? 0.0 : o[3] / 2;
+        d[3] = circle ? 0.0 : o[4] / 2;
+        const double reach = circle ? o[3] + 2.5 : 2.5;
+        d[4] = reach * reach;
+    }
+}
+
+}  // namespace aqua

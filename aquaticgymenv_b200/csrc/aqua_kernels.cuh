@@ -1,0 +1,74 @@
+// aqua_kernels.cuh -- launch interface between the C ABI (aqua_abi.cu) and the kernels
+// (aqua_kernels.cu).  Plain structs and launcher prototypes; no CUDA device code here.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/aquagym.h"
+
+namespace aqua {
+
+constexpr int kMaxThreads = 256;   // threads per CTA upper bound (launch bounds)
+constexpr int kStatSlots = 1024;   // per-CTA statistics slots (CTA b adds into slot b % kStatSlots)
+
+// Philox4x32-10 round keys: rk[2r] = k0 + r*0x9E3779B9, rk[2r+1] = k1 + r*0xBB67AE85 with
+// (k0, k1) = (seed lo, seed hi).  Computed once on the host so that in the kernels they are
+// constant-bank operands of the rounds' XORs.
+struct PhiloxKeys {
+    uint32_t rk[20];
+};
+
+// Everything a kernel needs to know about the world; travels by value in the parameter block.
+struct World {
+    PhiloxKeys keys;
+    uint64_t env_id_base;   // global id of env 0 of this slab
+    const void* tab;        // device ObstacleTable<R> (R = float or double per precision)
+    const double* tab64;    // device double[K][5] = {cx, cy, hx, hy, r2}: float64 table (reset path)
+    const uint32_t* grid;   // device uint32[kGridCells][2]: per-cell obstacle bit masks (or NULL)
+    int32_t k_obst;
+    uint8_t waves, random_boat, random_goal, autoreset;
+};
+
+struct StepArgs {
+    World w;
+    void* planes;           // plane 0; plane p starts p * ld elements later
+    int64_t ld;
+    int64_t env_begin;      // first env of this launch (multiple of AQUA_TILE)
+    int64_t env_end;        // one past the last env of this launch
+    const void* actions;    // indexed by absolute env index
+    void* reward;
+    uint8_t* flags;
+    const float* noise_x;   // injected wave increments (or NULL): indexed by absolute env index
+    const float* noise_y;
+    unsigned long long* stats;  // [kStatSlots][AQUA_N_STATS]
+    int64_t steps;          // rollout kernel: steps per launch
+    uint64_t step0;         // rollout kernel: ACTION-stream index of the first step
+};
+
+struct LaunchGeom {
+    int threads;  // per CTA
+    int blocks;
+};
+
+// every launcher returns the cudaError_t of the launch (cudaGetLastError)
+cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s);
+cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s);
+cudaError_t launch_reset(int precision, const StepArgs& a, const uint8_t* mask, cudaStream_t s);
+cudaError_t launch_init_state(int precision, void* planes, int64_t ld, cudaStream_t s);
+cudaError_t launch_random_actions(const World& w, int64_t n, uint64_t step_index, void* actions,
+                                  int action_dtype, cudaStream_t s);
+cudaError_t launch_get_state(int precision, const void* planes, int64_t ld, int64_t n, double* out,
+                             cudaStream_t s);
+cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n, const double* in,
+                             cudaStream_t s);
+cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s);
+// occupancy of the step kernel for (precision, action dtype) at `threads` per CTA
+cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm);
+cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* blocks_per_sm);
+
+// host-side construction of the device obstacle tables; `out` sized for the precision
+size_t obstacle_table_bytes(int precision);
+void build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host);
+
+}  // namespace aqua

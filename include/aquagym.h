@@ -17,11 +17,11 @@
  *   - There is no CPU fallback: without a CUDA device aqua_create() fails.
  *
  * State layout (structure of arrays, one "plane" per quantity, `ld` elements apart):
- *     plane 0..6 : x, y, theta, wave_x, wave_y, goal_x, goal_y   (float, or double if
+ *     plane 0..6 : x, y, theta, goal_x, goal_y, wave_x, wave_y   (float, or double if
  *                  precision == AQUA_F64)
  *     plane 7    : uint32 word  (episode << 11) | time           (time saturates at 2047)
  *   The observation of the reference (aqua.py:126,213: concat(boat_state[3], goal[2])) is planes
- *   {0,1,2,5,6}; no separate observation copy is made.
+ *   0..4, i.e. the first 5 * ld elements viewed as [5][ld]; no separate observation copy is made.
  */
 #ifndef AQUAGYM_H
 #define AQUAGYM_H
@@ -64,6 +64,10 @@ enum {
 #define AQUA_TIME_BITS 11
 #define AQUA_EPISODE_MASK 0x1FFFFFu
 #define AQUA_N_PLANES 8
+enum {
+    AQUA_PLANE_X = 0, AQUA_PLANE_Y = 1, AQUA_PLANE_THETA = 2, AQUA_PLANE_GOAL_X = 3,
+    AQUA_PLANE_GOAL_Y = 4, AQUA_PLANE_WAVE_X = 5, AQUA_PLANE_WAVE_Y = 6, AQUA_PLANE_TIME = 7
+};
 #define AQUA_TILE 1024 /* `ld` must be a multiple of this */
 
 /* index of the counters returned by aqua_get_stats / aqua_stats_reduce */
@@ -162,9 +166,11 @@ int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t fir
 /* Host-buffer step: the call a host-side gym user makes.  Copies `actions` (HOST, preferably
  * pinned) to the device, steps, and copies obs (float[5][N] planes x,y,theta,gx,gy; double if
  * F64), reward and flags back to HOST buffers, chunked and pipelined over internal streams;
- * returns after everything has landed.  obs/reward/flags may be NULL to skip that copy. */
-int aqua_step_host(aqua_env* env, const void* actions, int action_dtype, void* obs, void* reward,
-                   uint8_t* flags);
+ * returns after everything has landed.  obs/reward/flags may be NULL to skip that copy.
+ * `stream` is the stream earlier asynchronous calls on this handle were issued on: the internal
+ * streams wait for it first. */
+int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
+                   void* reward, uint8_t* flags);
 
 /* ---- state access (parity teacher-forcing, checkpoint/restore) ------------------------ */
 /* canonical DEVICE double[9][N]: x, y, theta, wave_x, wave_y, goal_x, goal_y, time, episode */

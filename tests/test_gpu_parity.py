@@ -1,0 +1,454 @@
+"""Parity of the CUDA path (through the C ABI) against the golden vectors produced by executing
+the reference, and against the C oracle on seeded inputs.
+
+Bar (BASELINE.json north_star): done / collided / time / success flags bit-exact; pose, reward
+and observation within 1e-5 relative, where "relative" is taken against the scale of the
+quantity (tests/helpers.py).  The float64 instantiation is held to 2e-8 and to identical flags
+everywhere.  The float32 instantiation (the throughput layout) is held to 1e-5 and to identical
+flags whenever the reference's own decision margin (distance to the nearest border / obstacle /
+goal rim, aqua.py:404-418) exceeds TAU_F32 = 1e-3 px; a sub-margin flip is counted, must stay
+rare, and the env state is re-synchronised from the oracle (teacher forcing) so that the
+1000-step comparison continues.
+"""
+import numpy as np
+import pytest
+
+from tests.conftest import GOLDEN
+from tests.helpers import (SCALE_POS, SCALE_REWARD, SCALE_WAVE, err_angle, err_scaled, golden_names,
+                           load_golden)
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64 = 2e-8  # x 100 px: the reference's own ICC round-off (~1.5e-8 px per straight step) accumulates
+TOL_F32 = 1e-5
+TAU_F32 = 1e-3  # px: decision margin below which a float32 flag may legitimately differ
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _make_gpu(g, n, precision, autoreset, base=None):
+    from aquaticgymenv_b200 import AquaVecEnv
+    return AquaVecEnv(n, continuous=bool(g["continuous"]), obstacles=np.asarray(g["table"], np.float64),
+                      waves=bool(g["waves"]), random_boat=bool(g.get("random_boat", True)),
+                      random_goal=bool(g.get("random_goal", True)), seed=int(g.get("seed", 0)),
+                      env_id_base=int(g.get("env_id_base", 0)) if base is None else base,
+                      precision=precision, autoreset=autoreset, device="cuda:0")
+
+
+def _make_oracle(g, n, base=None):
+    from oracle import aqua_oracle as ao
+    return ao.OracleVecEnv(n, continuous=bool(g["continuous"]), obstacles=np.asarray(g["table"], np.float64),
+                           waves=bool(g["waves"]), random_boat=bool(g.get("random_boat", True)),
+                           random_goal=bool(g.get("random_goal", True)), seed=int(g.get("seed", 0)),
+                           env_id_base=int(g.get("env_id_base", 0)) if base is None else base)
+
+
+def _actions_tensor(a, continuous):
+    torch = _torch()
+    if continuous:
+        return torch.as_tensor(np.ascontiguousarray(a, np.float32)).cuda()
+    return torch.as_tensor(np.ascontiguousarray(a, np.int32)).cuda()
+
+
+def _state_err(got, ref):
+    """max scaled error over x, y, theta, wave (rows 0..4 of the canonical state)."""
+    return max(err_scaled(got[0], ref[0], SCALE_POS).max(), err_scaled(got[1], ref[1], SCALE_POS).max(),
+               err_angle(got[2], ref[2]).max(), err_scaled(got[3:5], ref[3:5], SCALE_WAVE).max())
+
+
+# ------------------------------------------------------------------ single-step goldens
+@pytest.mark.parametrize("precision,tol", [("float64", TOL_F64), ("float32", TOL_F32)])
+@pytest.mark.parametrize("name", golden_names(GOLDEN, "step_"))
+def test_single_step_golden(name, precision, tol):
+    torch = _torch()
+    g = load_golden(GOLDEN, name)
+    n = g["state_in"].shape[0]
+    env = _make_gpu(g, n, precision, autoreset=False)
+    st = np.zeros((9, n))
+    st[:8] = g["state_in"].T
+    env.set_state(st)
+    noise = torch.as_tensor(np.ascontiguousarray(g["noise"].T, np.float32)).cuda()
+    flags = env.step_flags(_actions_tensor(g["actions"], bool(g["continuous"])), noise=noise)
+    flags = flags.cpu().numpy()
+    out = env.get_state().cpu().numpy()
+    reward = env.reward.cpu().numpy().astype(np.float64)
+    ref = g["state_out"].T
+    if precision == "float64":
+        assert np.array_equal(flags, g["flags"])
+        ok = np.ones(n, bool)
+    else:
+        differ = flags != g["flags"]
+        assert not (differ & (g["margin"] > TAU_F32)).any(), "float32 flag flip outside the margin"
+        assert differ.mean() < 2e-3, differ.sum()
+        ok = ~differ
+    assert _state_err(out[:, ok], ref[:, ok]) < tol
+    assert np.array_equal(out[5:7], ref[5:7])      # the goal is copied through untouched
+    assert np.array_equal(out[7], ref[7])          # time
+    assert err_scaled(reward[ok], g["reward"][ok], SCALE_REWARD).max() < tol
+    env.close()
+
+
+# ------------------------------------------------------------------ golden rollouts, float64
+@pytest.mark.parametrize("name", golden_names(GOLDEN, "roll_"))
+def test_rollout_golden_f64_free_running(name):
+    """1000-step lock-step with the reference's recorded rollout, resets included: the GPU env
+    draws its own noise and reset samples from the Philox streams; nothing is teacher-forced."""
+    g = load_golden(GOLDEN, name)
+    T, n = g["flags"].shape
+    env = _make_gpu(g, n, "float64", autoreset=False)
+    env.reset()
+    assert np.array_equal(env.get_state().cpu().numpy(), g["init_state"])
+    resets = {(int(r[0]), int(r[1])): r for r in g["resets"]}
+    cont = bool(g["continuous"])
+    worst = 0.0
+    for t in range(T):
+        flags = env.step_flags(_actions_tensor(g["actions"][t], cont)).cpu().numpy()
+        st = env.get_state().cpu().numpy()
+        reward = env.reward.cpu().numpy()
+        assert np.array_equal(flags, g["flags"][t]), (name, t)
+        o = g["obs_step"][t]
+        e = max(err_scaled(st[0], o[:, 0], SCALE_POS).max(), err_scaled(st[1], o[:, 1], SCALE_POS).max(),
+                err_angle(st[2], o[:, 2]).max(),
+                err_scaled(st[3], g["wave_step"][t][:, 0], SCALE_WAVE).max(),
+                err_scaled(st[4], g["wave_step"][t][:, 1], SCALE_WAVE).max(),
+                err_scaled(reward, g["reward"][t], SCALE_REWARD).max())
+        worst = max(worst, e)
+        assert e < 1e-7, (name, t, e)  # the reference's own ICC round-off is ~1.5e-8 px per straight step
+        assert np.array_equal(st[5], o[:, 3]) and np.array_equal(st[6], o[:, 4])
+        assert np.array_equal(st[7], g["time_step"][t])
+        done = (flags & 1).astype(np.uint8)
+        if done.any():
+            env.reset(mask=done)
+            st = env.get_state().cpu().numpy()
+            for i in np.nonzero(done)[0]:
+                r = resets[(t, int(i))]
+                assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 8], i], r[2:10]), (name, t, i)
+    env.close()
+
+
+# ------------------------------------------------------------------ lock-step against the oracle
+CONFIGS = {
+    "v0_discrete": dict(continuous=False, table="none", waves=True),
+    "v1_discrete": dict(continuous=False, table="v1", waves=True),
+    "v2_continuous": dict(continuous=True, table="v2", waves=True),
+    "dense64_discrete": dict(continuous=False, table="dense64", waves=True),
+    "dense64_continuous": dict(continuous=True, table="dense64", waves=True),
+    "v1_discrete_nowaves": dict(continuous=False, table="v1", waves=False),
+}
+
+
+def _cfg(name, seed=5, base=0):
+    c = dict(CONFIGS[name])
+    tab = c.pop("table")
+    c["table"] = np.zeros((0, 5)) if tab == "none" else np.load("%s/%s_table.npy" % (GOLDEN, tab))
+    c["seed"], c["env_id_base"] = seed, base
+    return c
+
+
+def _lockstep(cfg, n, steps, precision, autoreset=True, ragged_check=False):
+    """Random-policy lock-step GPU vs oracle with the float32 margin policy; returns counters."""
+    torch = _torch()
+    env = _make_gpu(cfg, n, precision, autoreset=autoreset)
+    ref = _make_oracle(cfg, n)
+    env.reset()
+    ref.reset()
+    assert np.array_equal(env.get_state().cpu().numpy(), ref.get_state())
+    f64 = precision == "float64"
+    tol = TOL_F64 if f64 else TOL_F32
+    flips = 0
+    worst = 0.0
+    for t in range(steps):
+        act = env.random_actions(t)
+        flags = env.step_flags(act).cpu().numpy()
+        reward = env.reward.cpu().numpy().astype(np.float64)
+        _, r_ref, f_ref, margin = ref.step(act.cpu().numpy(), autoreset=autoreset, want_margin=True)
+        differ = flags != f_ref
+        if f64:
+            assert not differ.any(), (t, np.nonzero(differ)[0][:8], margin[differ][:8])
+        else:
+            assert not (differ & (margin > TAU_F32)).any(), (t, margin[differ])
+        flips += int(differ.sum())
+        ok = ~differ
+        got = env.get_state().cpu().numpy()
+        want = ref.get_state()
+        e = max(_state_err(got[:, ok], want[:, ok]), err_scaled(reward[ok], r_ref[ok], SCALE_REWARD).max())
+        worst = max(worst, e)
+        assert e < tol, (t, e)
+        assert np.array_equal(got[5:, ok], want[5:, ok])  # goal, time, episode
+        if differ.any():  # teacher forcing after a sub-margin flip
+            env.set_state(torch.as_tensor(want))
+    env.close()
+    return flips, worst
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_lockstep_oracle_f64(name):
+    flips, worst = _lockstep(_cfg(name), 4096, 300, "float64")
+    assert flips == 0
+
+
+@pytest.mark.parametrize("name", sorted(CONFIGS))
+def test_lockstep_oracle_f32(name):
+    n, steps = 4096, 300
+    flips, worst = _lockstep(_cfg(name), n, steps, "float32")
+    # measured flip rate of the float32 layout: a handful per million env-steps
+    assert flips <= max(3, int(2e-5 * n * steps)), flips
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 1023, 1025, 4099])
+def test_ragged_sizes(n, precision):
+    """N not a multiple of the vector width / tile: tails handled, nothing out of bounds."""
+    flips, _ = _lockstep(_cfg("v1_discrete", seed=9, base=77), n, 40, precision)
+    assert flips <= 1
+    flips, _ = _lockstep(_cfg("v2_continuous", seed=9, base=77), n, 40, precision)
+    assert flips <= 1
+
+
+def test_no_autoreset_terminal_state_stays():
+    flips, _ = _lockstep(_cfg("v1_discrete", seed=3), 2048, 60, "float64", autoreset=False)
+    assert flips == 0
+
+
+# ------------------------------------------------------------------ statistics, dtypes, rollout kernel
+def test_statistics_match_oracle_counts():
+    torch = _torch()
+    cfg = _cfg("v1_discrete", seed=21)
+    n, steps = 8192, 200
+    env = _make_gpu(cfg, n, "float64", autoreset=True)
+    ref = _make_oracle(cfg, n)
+    env.reset()
+    ref.reset()
+    cnt = np.zeros(4, np.int64)
+    length = 0
+    rsum = 0.0
+    for t in range(steps):
+        act = env.random_actions(t)
+        env.step_flags(act)
+        time_before = ref.time.copy()
+        _, r_ref, f_ref, _ = ref.step(act.cpu().numpy(), autoreset=True)
+        done = (f_ref & 1) != 0
+        cnt += [done.sum(), ((f_ref & 2) != 0).sum(), ((f_ref & 4) != 0).sum(), ((f_ref & 8) != 0).sum()]
+        length += int((time_before[done] + 1).sum())
+        rsum += float(r_ref.sum())
+    s = env.stats()
+    assert s["steps"] == n * steps
+    assert [s["episodes"], s["collided"], s["timeout"], s["success"]] == list(cnt)
+    assert s["episodes"] == s["collided"] + s["timeout"] + s["success"]
+    assert s["length_sum"] == length
+    assert abs(s["reward_sum"] - rsum) < 1e-6 * n * steps
+    assert s["bad_actions"] == 0
+    dev = env.stats_tensor(clear=True).cpu().numpy()
+    assert dev[0] == s["episodes"] and dev[6] == s["steps"]
+    assert env.stats()["steps"] == 0  # cleared
+    env.close()
+
+
+def test_action_dtypes_agree():
+    torch = _torch()
+    cfg = _cfg("v1_discrete", seed=4)
+    n = 5000
+    outs = []
+    for dt in (torch.int32, torch.int64, torch.uint8):
+        env = _make_gpu(cfg, n, "float32", autoreset=True)
+        env.reset()
+        for t in range(50):
+            act = env.random_actions(t).to(dt)
+            env.step_flags(act)
+        outs.append((env.get_state().cpu().numpy(), env.reward.cpu().numpy().copy(), env.stats()))
+        env.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1]) and o[2] == outs[0][2]
+
+
+def test_bad_actions_are_clamped_and_counted():
+    torch = _torch()
+    n = 4096
+    env = _make_gpu(_cfg("v1_discrete", seed=4), n, "float32", autoreset=True)
+    env.reset()
+    act = torch.full((n,), 7, dtype=torch.int64, device="cuda")  # outside {0,1,2} -> full throttle
+    env.step_flags(act)
+    env2 = _make_gpu(_cfg("v1_discrete", seed=4), n, "float32", autoreset=True)
+    env2.reset()
+    env2.step_flags(torch.full((n,), 2, dtype=torch.int64, device="cuda"))
+    assert np.array_equal(env.get_state().cpu().numpy(), env2.get_state().cpu().numpy())
+    assert env.stats()["bad_actions"] == n and env2.stats()["bad_actions"] == 0
+    cenv = _make_gpu(_cfg("v2_continuous", seed=4), n, "float32", autoreset=True)
+    cenv.reset()
+    a = torch.rand(n, 2, device="cuda") * 0.6  # partly outside [0.2, 0.5]: clipped (aqua.py:145-150)
+    cenv.step_flags(a)
+    cref = _make_gpu(_cfg("v2_continuous", seed=4), n, "float32", autoreset=True)
+    cref.reset()
+    cref.step_flags(a.clamp(0.2, 0.5))
+    assert np.array_equal(cenv.get_state().cpu().numpy(), cref.get_state().cpu().numpy())
+    want_bad = int(((a < 0.2) | (a > 0.5)).any(dim=1).sum())
+    assert cenv.stats()["bad_actions"] == want_bad
+    for e in (env, env2, cenv, cref):
+        e.close()
+
+
+def test_random_actions_follow_the_oracle_stream():
+    from oracle import draws
+    env = _make_gpu(_cfg("v1_discrete", seed=1234, base=4000000000), 300, "float32", autoreset=True)
+    a = env.random_actions(5_000_000_123).cpu().numpy()
+    want = [draws.action_discrete(1234, 4000000000 + i, 5_000_000_123) for i in range(300)]
+    assert a.tolist() == want
+    cenv = _make_gpu(_cfg("v2_continuous", seed=99, base=17), 200, "float32", autoreset=True)
+    c = cenv.random_actions(42).cpu().numpy()
+    wantc = np.stack([draws.action_continuous(99, 17 + i, 42) for i in range(200)])
+    assert np.array_equal(c, wantc)
+    env.close()
+    cenv.close()
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+@pytest.mark.parametrize("name", ["v1_discrete", "dense64_continuous"])
+def test_rollout_kernel_equals_stepwise(name, precision):
+    """K steps fused in one launch == K single-step launches fed by random_actions: bitwise."""
+    cfg = _cfg(name, seed=31, base=1000)
+    n, K = 10000, 150
+    a = _make_gpu(cfg, n, precision, autoreset=True)
+    b = _make_gpu(cfg, n, precision, autoreset=True)
+    a.reset()
+    b.reset()
+    for t in range(K):
+        a.step_flags(a.random_actions(t))
+    b.rollout_random(K, first_step_index=0)
+    assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy())
+    assert a.stats() == b.stats()
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_step_host_equals_device_step(precision):
+    cfg = _cfg("v1_discrete", seed=8)
+    n = 300000  # several pipeline chunks
+    a = _make_gpu(cfg, n, precision, autoreset=True)
+    b = _make_gpu(cfg, n, precision, autoreset=True)
+    a.reset()
+    b.reset()
+    for t in range(5):
+        act = a.random_actions(t)
+        flags = a.step_flags(act).cpu().numpy()
+        obs_h, rew_h, fl_h = b.step_host(act.cpu().numpy())
+        assert np.array_equal(fl_h, flags)
+        assert np.array_equal(rew_h, a.reward.cpu().numpy())
+        assert np.array_equal(obs_h, a.obs_planes.cpu().numpy())
+    assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy())
+    assert a.stats() == b.stats()
+    a.close()
+    b.close()
+
+
+def test_sharding_invariance():
+    """One slab of N envs == two slabs of N/2 with env_id_base set: bitwise (Philox is keyed by
+    the global env id)."""
+    from aquaticgymenv_b200 import sharding
+    cfg = _cfg("v1_discrete", seed=77)
+    n, K = 20000, 120
+    whole = _make_gpu(cfg, n, "float32", autoreset=True)
+    whole.reset()
+    whole.rollout_random(K, 0)
+    ref = whole.get_state().cpu().numpy()
+    parts, tot = [], None
+    for r in range(3):
+        base, nl = sharding.slab(n, r, 3)
+        e = _make_gpu(cfg, nl, "float32", autoreset=True, base=base)
+        e.reset()
+        e.rollout_random(K, 0)
+        parts.append(e.get_state().cpu().numpy())
+        s = e.stats_tensor().cpu().numpy().copy()
+        tot = s if tot is None else tot + s
+        e.close()
+    assert np.array_equal(np.concatenate(parts, axis=1), ref)
+    assert np.array_equal(tot, whole.stats_tensor().cpu().numpy())
+    whole.close()
+
+
+# ------------------------------------------------------------------ full-size properties
+@pytest.mark.parametrize("name,n", [("v1_discrete", 1 << 20), ("v2_continuous", 1 << 20),
+                                    ("dense64_discrete", 1 << 19)])
+def test_full_size_invariants(name, n):
+    """BASELINE sizes (1M envs; 512k/GPU dense-64): properties that need no oracle."""
+    torch = _torch()
+    cfg = _cfg(name, seed=2)
+    env = _make_gpu(cfg, n, "float32", autoreset=True)
+    env.reset()
+    T = 120
+    done_total = 0
+    for t in range(T):
+        flags = env.step_flags(env.random_actions(t))
+        done_total += int((flags & 1).sum())
+        valid = (flags == 0) | (flags == 3) | (flags == 5) | (flags == 9)
+        assert bool(valid.all())
+    st = env.get_state()
+    x, y, th, wx, wy, gx, gy, tm, ep = st
+    assert bool(((x >= 2.5) & (x <= 97.5) & (y >= 2.5) & (y <= 97.5)).all())  # auto-reset: all alive
+    assert bool(((th >= -np.pi) & (th < np.pi)).all())
+    assert bool((wx.abs() <= 0.05 + 1e-9).all()) and bool((wy.abs() <= 0.05 + 1e-9).all())
+    assert bool(((gx >= 2.5) & (gx <= 97.5) & (gy >= 2.5) & (gy <= 97.5)).all())
+    assert bool((tm <= T).all()) and bool((ep >= 0).all())
+    assert bool((((x - gx) ** 2 + (y - gy) ** 2) > 25.0 - 1e-3).all())      # nobody sits inside the goal
+    s = env.stats()
+    assert s["steps"] == n * T and s["episodes"] == done_total
+    assert s["episodes"] == s["collided"] + s["timeout"] + s["success"]
+    assert int(ep.sum()) == s["episodes"]                                   # one episode opened per done
+    assert 5 < s["mean_episode_length"] < 200
+    # replay: same seed -> bitwise the same slab
+    env2 = _make_gpu(cfg, n, "float32", autoreset=True)
+    env2.reset()
+    env2.rollout_random(T, 0)
+    assert torch.equal(env2.get_state(), st)
+    env.close()
+    env2.close()
+
+
+# ------------------------------------------------------------------ the reference-facing single env
+def test_single_env_dropin_api():
+    from aquaticgymenv_b200 import gym_aqua
+    env = gym_aqua.make("AquaEnv-v0", obstacles=True, random_boat=False, random_goal=False, waves=False)
+    obs = env.reset()
+    assert obs.dtype == np.float64 and obs.shape == (5,)
+    assert obs.tolist() == [85.0, 45.0, 0.0, 25.0, 80.0]           # aqua.py:107,117
+    assert env.observation_space.shape == (5,) and env.action_space.n == 3
+    assert len(env.obstacles) == 5
+    obs, reward, done, info = env.step(2)                            # full throttle: +0.5 along +y
+    assert abs(obs[0] - 85.0) < 1e-7 and abs(obs[1] - 45.5) < 1e-7 and abs(obs[2] - 4e-9) < 1e-12
+    assert isinstance(done, bool) and not done
+    assert set(info) == {'Termination.collided', 'Termination.time', 'Termination.success'}
+    with pytest.raises(IndexError):
+        env.step(3)
+    total, steps = 0.0, 0
+    while not done:                                                  # main/testing/__init__.py:26-34
+        obs, reward, done, info = env.step(0)
+        total += reward
+        steps += 1
+    assert steps == 1000 and info['Termination.time'] and reward == -10   # time > 1000 at step 1001
+    env.close()
+    cenv = gym_aqua.make("AquaContinuousEnv-v2")
+    o = cenv.reset()
+    o2, r, d, i = cenv.step(np.array([0.3, 0.4]))
+    assert o2.shape == (5,) and np.isfinite(r)
+    assert len(cenv.obstacles) == 6
+    cenv.close()
+
+
+def test_wrong_action_kind_is_an_error():
+    torch = _torch()
+    from aquaticgymenv_b200 import _native as N
+    env = _make_gpu(_cfg("v2_continuous"), 64, "float32", autoreset=True)
+    with pytest.raises(ValueError):
+        env.step_flags(torch.zeros(64, dtype=torch.int32, device="cuda"))
+    denv = _make_gpu(_cfg("v1_discrete"), 64, "float32", autoreset=True)
+    with pytest.raises(TypeError):
+        denv.step_flags(torch.zeros(64, dtype=torch.float32, device="cuda"))
+    import ctypes as C
+    rc = denv.lib.aqua_step(denv._h, None, C.c_void_p(denv.reward.data_ptr()), N.ACT_F32X2,
+                            C.c_void_p(denv.reward.data_ptr()), C.c_void_p(denv.flags.data_ptr()))
+    assert rc == N.ERR_INVALID and b"discrete" in denv.lib.aqua_last_error()
+    env.close()
+    denv.close()
