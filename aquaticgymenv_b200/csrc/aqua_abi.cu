@@ -72,6 +72,9 @@ struct aqua_env {
     unsigned long long* d_slots = nullptr;
     int64_t* d_stats_out = nullptr;
     aqua::World world;
+    // resident CTAs per SM, queried once at create: [action dtype][64 / 128 / 256 threads]
+    int occ_step[4][3] = {};
+    int occ_rollout[3] = {};
     // host-step pipeline (lazily created)
     cudaStream_t hs[kHostStreams] = {};
     cudaEvent_t ev_in = nullptr;
@@ -102,11 +105,8 @@ int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aq
     const int V = env->cfg.precision == AQUA_F64 ? 2 : 4;
     int threads = 256;
     while (threads > 64 && n < (int64_t)threads * V * env->sm_count * 2) threads >>= 1;
-    int per_sm = 0;
-    cudaError_t e = rollout ? aqua::rollout_occupancy(env->cfg.precision, env->cfg.continuous, threads, &per_sm)
-                            : aqua::step_occupancy(env->cfg.precision, action_dtype, threads, &per_sm);
-    if (e != cudaSuccess) return fail(AQUA_ERR_CUDA, "occupancy query failed: %s", cudaGetErrorString(e));
-    if (per_sm < 1) per_sm = 1;
+    const int ti = threads == 256 ? 2 : (threads == 128 ? 1 : 0);
+    const int per_sm = rollout ? env->occ_rollout[ti] : env->occ_step[action_dtype][ti];
     const int64_t tiles = (n + (int64_t)threads * V - 1) / ((int64_t)threads * V);
     const int64_t resident = (int64_t)per_sm * env->sm_count;
     g->threads = threads;
@@ -266,6 +266,15 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.random_goal = cfg->random_goal != 0;
     w.autoreset = cfg->autoreset != 0;
 
+    for (int ti = 0; ti < 3; ++ti) {
+        const int threads = 64 << ti;
+        for (int act = 0; act < 4; ++act) {
+            AQ_CREATE(aqua::step_occupancy(cfg->precision, act, threads, &env->occ_step[act][ti]));
+            env->occ_step[act][ti] = std::max(env->occ_step[act][ti], 1);
+        }
+        AQ_CREATE(aqua::rollout_occupancy(cfg->precision, cfg->continuous, threads, &env->occ_rollout[ti]));
+        env->occ_rollout[ti] = std::max(env->occ_rollout[ti], 1);
+    }
     AQ_CREATE(aqua::launch_init_state(cfg->precision, env->state, ld, nullptr));
     AQ_CREATE(cudaStreamSynchronize(nullptr));
 #undef AQ_CREATE
