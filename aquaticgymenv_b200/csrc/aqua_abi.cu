@@ -226,6 +226,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     }
     // obstacle tables
     const size_t tab_bytes = aqua::obstacle_table_bytes(cfg->precision);
+    int k_circ = 0;
     {
         void* h_tab = malloc(tab_bytes);
         double h_tab64[AQUA_MAX_OBSTACLES * 5] = {0};
@@ -233,7 +234,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
             aqua_destroy(env);
             return fail(AQUA_ERR_ALLOC, "out of host memory");
         }
-        aqua::build_obstacle_tables(cfg->precision, cfg->n_obstacles, cfg->obstacles, h_tab, h_tab64);
+        k_circ = aqua::build_obstacle_tables(cfg->precision, cfg->n_obstacles, cfg->obstacles, h_tab, h_tab64);
         cudaError_t e1 = cudaMalloc(&env->d_tab, tab_bytes);
         if (e1 == cudaSuccess) e1 = cudaMemcpy(env->d_tab, h_tab, tab_bytes, cudaMemcpyHostToDevice);
         free(h_tab);
@@ -261,6 +262,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.tab64 = env->d_tab64;
     w.grid = nullptr;
     w.k_obst = cfg->n_obstacles;
+    w.k_circ = k_circ;
     w.waves = cfg->waves != 0;
     w.random_boat = cfg->random_boat != 0;
     w.random_goal = cfg->random_goal != 0;

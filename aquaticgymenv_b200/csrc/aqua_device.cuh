@@ -50,18 +50,20 @@ __device__ __forceinline__ uint4 philox_env(const PhiloxKeys& k, uint32_t env_id
     return philox4x32_10(env_id, c1, c2, tag, k);
 }
 
-// 24 high bits -> float in [0,1), exact
-__device__ __forceinline__ float u01(uint32_t u) { return __uint2float_rn(u >> 8) * 0x1p-24f; }
+// 24 high bits -> float in [0,1): u01 = (u >> 8) * 2^-24, exact.  The draw maps below fold the
+// power-of-two factor into their constant, which is bit-identical (the product is the same real
+// number, rounded once) and saves a multiply per draw.
+__device__ __forceinline__ float u24(uint32_t u) { return __uint2float_rn(u >> 8); }
 
 // The draws are float32 by definition: every instantiation and the CPU
 // oracle consume bit-identical values.
 constexpr float kPiDnF = 3.1415925f;     // largest float below pi
 constexpr float kTwoPiDnF = 6.283185f;   // 2 * kPiDnF exactly
-__device__ __forceinline__ float draw_pos(uint32_t u) { return __fmul_rn(u01(u), 100.0f); }
-__device__ __forceinline__ float draw_angle(uint32_t u) { return __fmaf_rn(u01(u), kTwoPiDnF, -kPiDnF); }
-__device__ __forceinline__ float draw_wave0(uint32_t u) { return __fmaf_rn(u01(u), 0.1f, -0.05f); }
-__device__ __forceinline__ float draw_noise(uint32_t u) { return __fmaf_rn(u01(u), 0.002f, -0.001f); }
-__device__ __forceinline__ float draw_thrust(uint32_t u) { return __fmaf_rn(u01(u), 0.3f, 0.2f); }
+__device__ __forceinline__ float draw_pos(uint32_t u) { return __fmul_rn(u24(u), 100.0f * 0x1p-24f); }
+__device__ __forceinline__ float draw_angle(uint32_t u) { return __fmaf_rn(u24(u), kTwoPiDnF * 0x1p-24f, -kPiDnF); }
+__device__ __forceinline__ float draw_wave0(uint32_t u) { return __fmaf_rn(u24(u), 0.1f * 0x1p-24f, -0.05f); }
+__device__ __forceinline__ float draw_noise(uint32_t u) { return __fmaf_rn(u24(u), 0.002f * 0x1p-24f, -0.001f); }
+__device__ __forceinline__ float draw_thrust(uint32_t u) { return __fmaf_rn(u24(u), 0.3f * 0x1p-24f, 0.2f); }
 
 // wave increment of step `t` (env time before the increment) -- aqua.py:188
 __device__ __forceinline__ void draw_wave_noise(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
@@ -78,7 +80,25 @@ __device__ __forceinline__ void draw_wave_noise(const PhiloxKeys& keys, uint32_t
 template <typename R> struct Prec;
 template <> struct Prec<float> {
     static constexpr int V = 4;  // envs per thread: 16-byte plane loads
-    static __device__ __forceinline__ void sincos_(float a, float* s, float* c) { sincosf(a, s, c); }
+    // sin and cos of a heading: |a| <= pi + 0.06, so two quadrant-reduction terms suffice and no
+    // large-argument path is needed.  Cephes single-precision minimax kernels on [-pi/4, pi/4]
+    // (about 1 ulp); quadrant fix-up on the sign bits.
+    static __device__ __forceinline__ void sincos_(float a, float* s, float* c) {
+        const float t = fmaf(a, 0.636619772f, 12582912.0f);      // 1.5 * 2^23: round to nearest integer
+        const uint32_t q = __float_as_uint(t);                   // low bits = quadrant (two's complement)
+        const float fq = t - 12582912.0f;
+        float r = fmaf(fq, -1.57079637f, a);                     // pi/2 = 1.57079637 - 4.37113883e-8
+        r = fmaf(fq, 4.37113883e-8f, r);
+        const float r2 = r * r;
+        const float ps = fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f);
+        const float sr = fmaf(r * r2, ps, r);
+        const float pc = fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f);
+        const float cr = fmaf(r2 * r2, pc, fmaf(r2, -0.5f, 1.0f));
+        const bool swap = (q & 1u) != 0u;
+        const float ss = swap ? cr : sr, cc = swap ? sr : cr;
+        *s = __uint_as_float(__float_as_uint(ss) ^ ((q & 2u) << 30));
+        *c = __uint_as_float(__float_as_uint(cc) ^ (((q + 1u) & 2u) << 30));
+    }
     static __device__ __forceinline__ float sqrt_(float v) {
         float r;
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
@@ -91,30 +111,40 @@ template <> struct Prec<double> {
     static __device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
 };
 
-// obstacle table in shared memory: nearest-point distance to an axis-aligned box of half
-// extents (hx, hy) (a circle is the box with zero extents) compared with r2 = (clearance
-// radius)^2.  aqua.py:373-390.  All lanes read the same entry (broadcast, conflict free).
+// Obstacle table in shared memory (aqua.py:56-68, 373-390).  Circles come first (k < k_circ):
+// entry = {cx, cy, r2, -} with r2 = (radius + 2.5)^2; then rectangles: {cx, cy, hx, hy} (half
+// extents), whose clearance is the boat / goal radius 2.5 alone (kRectR2).  The distance of a
+// point to an axis-aligned box is the norm of max(|p - c| - h, 0); a circle is the box with zero
+// extents, so both tests are the reference's `distance <= 0` written on squared distances.
+// All lanes read the same entry (one 16-byte broadcast LDS per obstacle, conflict free).
 template <typename R> struct alignas(16) ObstacleBox {
-    R cx, cy, hx, hy;
+    R cx, cy, a, b;
 };
 template <typename R> struct ObstacleTable {
     ObstacleBox<R> box[AQUA_MAX_OBSTACLES];
-    R r2[AQUA_MAX_OBSTACLES];
 };
+constexpr double kRectR2 = 6.25;  // (boat or goal radius 2.5)^2, aqua.py:72,75
 
 // collision of V positions against the whole table: the table entry is read once per obstacle
 template <typename R, int V>
-__device__ __forceinline__ void hits_obstacles(const ObstacleTable<R>& tab, int k_obst, const R (&px)[V],
-                                               const R (&py)[V], bool (&hit)[V]) {
+__device__ __forceinline__ void hits_obstacles(const ObstacleTable<R>& tab, int k_circ, int k_obst,
+                                               const R (&px)[V], const R (&py)[V], bool (&hit)[V]) {
 #pragma unroll 2
-    for (int k = 0; k < k_obst; ++k) {
+    for (int k = 0; k < k_circ; ++k) {
         const ObstacleBox<R> o = tab.box[k];
-        const R r2 = tab.r2[k];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            const R ddx = fmax(fabs(px[j] - o.cx) - o.hx, R(0));
-            const R ddy = fmax(fabs(py[j] - o.cy) - o.hy, R(0));
-            hit[j] |= (fma(ddx, ddx, ddy * ddy) <= r2);
+            const R ddx = px[j] - o.cx, ddy = py[j] - o.cy;
+            hit[j] |= (fma(ddx, ddx, ddy * ddy) <= o.a);
+        }
+    }
+    for (int k = k_circ; k < k_obst; ++k) {
+        const ObstacleBox<R> o = tab.box[k];
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const R ddx = fmax(fabs(px[j] - o.cx) - o.a, R(0));
+            const R ddy = fmax(fabs(py[j] - o.cy) - o.b, R(0));
+            hit[j] |= (fma(ddx, ddx, ddy * ddy) <= R(kRectR2));
         }
     }
 }
@@ -187,6 +217,136 @@ __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t e
     } else {
         o.wx = 0.0;
         o.wy = 0.0;
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// Cooperative reset (in-kernel auto-reset).  Finished envs are rare (about 1 in 70 env-steps) and
+// a rejection loop run by the owning lane alone would serialise the whole warp behind it.  The
+// step kernels therefore queue finished envs per CTA and hand each one to a group of
+// kCoopLanes lanes that evaluates kCoopLanes consecutive tries of the reference's sampling
+// sequence at once: lane l of round q tests try n = 8q + l (one Philox call yields both the goal
+// candidate, words z/w, and the boat candidate, words x/y/z of `observation_space.sample()`).
+// The accepted goal is the first passing try g, the accepted boat the first passing try > g
+// (aqua.py:102-115): exactly the sequential result, found in one round almost always.
+//
+// Accept/reject decisions are those of float64 arithmetic on the float32 draws: the float table
+// is used with a guard band and anything inside the band is re-evaluated in float64.
+// ------------------------------------------------------------------------------------------
+constexpr int kCoopLanes = 8;
+
+__device__ __forceinline__ bool outside_border_f(float x, float y) {
+    // (double)x - 2.5 and (double)x + 2.5 are exact for a float x in [0, 128): same predicate
+    return !((x >= 2.5f) & (x <= 97.5f) & (y >= 2.5f) & (y <= 97.5f));
+}
+
+template <typename R>
+__device__ __forceinline__ bool reset_blocked(const ObstacleTable<R>& tab, const double* __restrict__ tab64,
+                                              int k_circ, int k_obst, float x, float y) {
+    if constexpr (sizeof(R) == 8) {
+        const double px[1] = {(double)x}, py[1] = {(double)y};
+        bool hit[1] = {false};
+        hits_obstacles<double, 1>(tab, k_circ, k_obst, px, py, hit);
+        return hit[0];
+    } else {
+        bool hit = false, unsure = false;
+        for (int k = 0; k < k_circ; ++k) {
+            const ObstacleBox<float> o = tab.box[k];
+            const float ddx = x - o.cx, ddy = y - o.cy;
+            const float sd = fmaf(ddx, ddx, ddy * ddy) - o.a;
+            hit |= sd <= 0.f;
+            unsure |= fabsf(sd) <= 1e-4f * o.a;
+        }
+        for (int k = k_circ; k < k_obst; ++k) {
+            const ObstacleBox<float> o = tab.box[k];
+            const float ddx = fmaxf(fabsf(x - o.cx) - o.a, 0.f);
+            const float ddy = fmaxf(fabsf(y - o.cy) - o.b, 0.f);
+            const float sd = fmaf(ddx, ddx, ddy * ddy) - (float)kRectR2;
+            hit |= sd <= 0.f;
+            unsure |= fabsf(sd) <= 1e-4f * (float)kRectR2;
+        }
+        if (unsure) hit = hits_obstacle_g(tab64, k_obst, (double)x, (double)y);
+        return hit;
+    }
+}
+
+// aqua.py:421-422 at reset: goal and boat radius 2.5 each
+template <typename R> __device__ __forceinline__ bool reset_reached(float gx, float gy, float x, float y) {
+    if constexpr (sizeof(R) == 4) {
+        const float dgx = gx - x, dgy = gy - y;
+        const float sd = fmaf(dgx, dgx, dgy * dgy) - 25.f;
+        if (fabsf(sd) > 2.5e-3f) return sd <= 0.f;
+    }
+    const double dgx = (double)gx - (double)x, dgy = (double)gy - (double)y;
+    return sqrt(fma(dgx, dgx, dgy * dgy)) - 5.0 <= 0.0;
+}
+
+struct CoopResetResult {
+    float x, y, th, wx, wy, gx, gy;  // float32 draws: exact in either precision
+};
+
+// Must be called by all 32 lanes of a warp (it uses full-mask ballots and shuffles).  Lanes
+// [8s, 8s+8) serve one env: `valid`, `env_id`, `ep` (the NEW episode index) are group-uniform.
+// The result is returned to every lane of the group.
+template <typename R>
+__device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, const ObstacleTable<R>& tab,
+                                                      const double* __restrict__ tab64, int k_circ, int k_obst,
+                                                      WorldFlags wf, bool valid, uint32_t env_id, uint32_t ep) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned sub = lane & ~(unsigned)(kCoopLanes - 1);  // first lane of this group
+    const unsigned l = lane - sub;
+    CoopResetResult o;
+    o.gx = 25.f; o.gy = 80.f;            // aqua.py:107
+    o.x = 85.f; o.y = 45.f; o.th = 0.f;  // aqua.py:117
+    bool goal_done = !wf.random_goal || !valid;
+    bool boat_done = !wf.random_boat || !valid;
+    uint32_t n0 = 0;
+    while (__any_sync(full, !(goal_done && boat_done))) {
+        const uint32_t n = n0 + l;
+        const uint4 r = philox_env(keys, env_id, ep, n, kStreamReset);
+        const bool force = n >= kResetMaxTries - 1u;  // bounded loop: this try is accepted as is
+        // goal candidate of try n: aqua.py:103-105
+        const float cgx = draw_pos(r.z), cgy = draw_pos(r.w);
+        bool ok_g = false;
+        if (!goal_done)
+            ok_g = force || !(outside_border_f(cgx, cgy) || reset_blocked<R>(tab, tab64, k_circ, k_obst, cgx, cgy));
+        const unsigned mg = (__ballot_sync(full, ok_g) >> sub) & ((1u << kCoopLanes) - 1u);
+        unsigned first_boat = goal_done ? 0u : (unsigned)kCoopLanes;  // first lane whose try follows the goal's
+        const unsigned lg = mg ? (unsigned)(__ffs(mg) - 1) : 0u;
+        const float sgx = __shfl_sync(full, cgx, sub + lg), sgy = __shfl_sync(full, cgy, sub + lg);
+        if (!goal_done && mg) {
+            o.gx = sgx;
+            o.gy = sgy;
+            goal_done = true;
+            first_boat = lg + 1u;
+        }
+        // boat candidate of try n: aqua.py:110-115
+        const float cbx = draw_pos(r.x), cby = draw_pos(r.y), cbt = draw_angle(r.z);
+        bool ok_b = false;
+        if (goal_done && !boat_done && l >= first_boat)
+            ok_b = force || !(reset_reached<R>(o.gx, o.gy, cbx, cby) || outside_border_f(cbx, cby) ||
+                              reset_blocked<R>(tab, tab64, k_circ, k_obst, cbx, cby));
+        const unsigned mb = (__ballot_sync(full, ok_b) >> sub) & ((1u << kCoopLanes) - 1u);
+        const unsigned lb = mb ? (unsigned)(__ffs(mb) - 1) : 0u;
+        const float sbx = __shfl_sync(full, cbx, sub + lb), sby = __shfl_sync(full, cby, sub + lb);
+        const float sbt = __shfl_sync(full, cbt, sub + lb);
+        if (mb) {
+            o.x = sbx;
+            o.y = sby;
+            o.th = sbt;
+            boat_done = true;
+        }
+        n0 += kCoopLanes;
+    }
+    if (wf.waves) {  // aqua.py:124
+        const uint4 r = philox_env(keys, env_id, ep, 0u, kStreamWaveInit);
+        o.wx = draw_wave0(r.x);
+        o.wy = draw_wave0(r.y);
+    } else {
+        o.wx = 0.f;
+        o.wy = 0.f;
     }
     return o;
 }
@@ -280,7 +440,7 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
     if constexpr (kF64)
         collided = (xn - R(2.5) < R(0)) | (yn - R(2.5) < R(0)) | (xn + R(2.5) > R(100)) | (yn + R(2.5) > R(100));
     else  // float: p - 2.5 and p + 2.5 are exact near the borders, so this is the same predicate
-        collided = !((xn >= R(2.5)) & (xn <= R(97.5)) & (yn >= R(2.5)) & (yn <= R(97.5)));
+        collided = !((fmin(xn, yn) >= R(2.5)) & (fmax(xn, yn) <= R(97.5)));
     collided |= hit_obstacle;
 
     const R gcx = xn - e.gx, gcy = yn - e.gy;
@@ -322,11 +482,9 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
 // action decode ---------------------------------------------------------------------------
 // discrete table aqua.py:33-42: 0 -> (0.2, 0.5) rotate left, 1 -> (0.5, 0.2) rotate right,
 // 2 -> (0.5, 0.5) full throttle.  An index outside {0,1,2} selects full throttle and is counted.
-template <typename R>
-__device__ __forceinline__ void decode_discrete(long long a, R& tl, R& tr, uint32_t& bad) {
+template <typename R> __device__ __forceinline__ void decode_discrete(long long a, R& tl, R& tr) {
     tl = (a == 0) ? R(0.2) : R(0.5);
     tr = (a == 1) ? R(0.2) : R(0.5);
-    bad += ((unsigned long long)a > 2ull) ? 1u : 0u;
 }
 // continuous aqua.py:143-151: values outside [0.2, 0.5] are clipped (and counted)
 template <typename R>

@@ -8,6 +8,8 @@
 // bandwidth (65 B per discrete env-step).
 #include "aqua_device.cuh"
 
+#include <cstring>
+
 namespace aqua {
 
 // ------------------------------------------------------------------------------------------
@@ -57,6 +59,19 @@ template <typename R> __device__ __forceinline__ uint32_t* plane_tw(void* planes
 // ------------------------------------------------------------------------------------------
 // action decode for V envs starting at absolute env index `base`
 // ------------------------------------------------------------------------------------------
+template <typename T, int V>
+__device__ __forceinline__ void load_discrete(const void* actions, int64_t base, int nvalid, long long (&a)[V]) {
+    const T* src = reinterpret_cast<const T*>(actions) + base;
+    if (nvalid == V) {
+        const Pack<T, V> pk = ldg_pack<T, V>(src);
+#pragma unroll
+        for (int j = 0; j < V; ++j) a[j] = (long long)pk.v[j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? (long long)__ldg(src + j) : 2ll;
+    }
+}
+
 template <typename R, int ACT, int V>
 __device__ __forceinline__ void load_thrusts(const void* actions, int64_t base, int nvalid, R (&tl)[V],
                                              R (&tr)[V], uint32_t& bad) {
@@ -75,47 +90,22 @@ __device__ __forceinline__ void load_thrusts(const void* actions, int64_t base, 
         for (int j = 0; j < V; ++j) {
             uint32_t b = 0;
             decode_continuous<R>(a[2 * j], a[2 * j + 1], tl[j], tr[j], b);
-            bad += (j < nvalid) ? b : 0u;
+            bad += b;  // padding lanes hold 0.5: never counted
         }
     } else {
         long long a[V];
-        if constexpr (ACT == AQUA_ACT_I32) {
-            const int32_t* src = reinterpret_cast<const int32_t*>(actions) + base;
-            if (nvalid == V) {
-                const Pack<int32_t, V> pk = ldg_pack<int32_t, V>(src);
-#pragma unroll
-                for (int j = 0; j < V; ++j) a[j] = pk.v[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? __ldg(src + j) : 2;
-            }
-        } else if constexpr (ACT == AQUA_ACT_I64) {
-            const long long* src = reinterpret_cast<const long long*>(actions) + base;
-            if (nvalid == V) {
-                const Pack<long long, V> pk = ldg_pack<long long, V>(src);
-#pragma unroll
-                for (int j = 0; j < V; ++j) a[j] = pk.v[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? __ldg(src + j) : 2;
-            }
-        } else {
-            static_assert(ACT == AQUA_ACT_U8, "unknown action dtype");
-            const uint8_t* src = reinterpret_cast<const uint8_t*>(actions) + base;
-            if (nvalid == V) {
-                const Pack<uint8_t, V> pk = ldg_pack<uint8_t, V>(src);
-#pragma unroll
-                for (int j = 0; j < V; ++j) a[j] = pk.v[j];
-            } else {
-#pragma unroll
-                for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? __ldg(src + j) : 2;
-            }
-        }
+        if constexpr (ACT == AQUA_ACT_I32) load_discrete<int32_t, V>(actions, base, nvalid, a);
+        else if constexpr (ACT == AQUA_ACT_I64) load_discrete<long long, V>(actions, base, nvalid, a);
+        else load_discrete<uint8_t, V>(actions, base, nvalid, a);
+        unsigned long long worst = 0ull;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            uint32_t b = 0;
-            decode_discrete<R>(a[j], tl[j], tr[j], b);
-            bad += (j < nvalid) ? b : 0u;
+            decode_discrete<R>(a[j], tl[j], tr[j]);
+            worst = max(worst, (unsigned long long)a[j]);
+        }
+        if (worst > 2ull) {  // rare: an index outside {0, 1, 2} (padding lanes hold 2)
+#pragma unroll
+            for (int j = 0; j < V; ++j) bad += ((unsigned long long)a[j] > 2ull) ? 1u : 0u;
         }
     }
 }
@@ -123,17 +113,33 @@ __device__ __forceinline__ void load_thrusts(const void* actions, int64_t base, 
 // ------------------------------------------------------------------------------------------
 // per-thread episode statistics and their reduction
 // ------------------------------------------------------------------------------------------
+// The four flag bits of the V envs of a thread arrive packed one byte per env; they are
+// accumulated byte-wise (one add per counter per tile instead of per env) and widened before a
+// byte lane can overflow.
 struct ThreadStats {
+    uint32_t pk_done = 0, pk_coll = 0, pk_time = 0, pk_succ = 0;  // 4 byte lanes each
+    uint32_t pk_n = 0;
     uint32_t done = 0, collided = 0, timeout = 0, success = 0, length = 0, steps = 0, bad = 0;
     long long reward_fx = 0;  // sum of step rewards, fixed point 2^-20
 
-    template <typename R> __device__ __forceinline__ void add(uint32_t flags, uint32_t time_after, R reward) {
-        done += flags & 1u;
-        collided += (flags >> 1) & 1u;
-        timeout += (flags >> 2) & 1u;
-        success += (flags >> 3) & 1u;
+    __device__ __forceinline__ void widen() {
+        done += __dp4a(pk_done, 0x01010101u, 0u);
+        collided += __dp4a(pk_coll, 0x01010101u, 0u);
+        timeout += __dp4a(pk_time, 0x01010101u, 0u);
+        success += __dp4a(pk_succ, 0x01010101u, 0u);
+        pk_done = pk_coll = pk_time = pk_succ = pk_n = 0u;
+    }
+    // w: flags of the thread's envs, byte j = env j (bytes of padding envs must be 0)
+    __device__ __forceinline__ void add_flags(uint32_t w, int nvalid) {
+        pk_done += w & 0x01010101u;
+        pk_coll += (w >> 1) & 0x01010101u;
+        pk_time += (w >> 2) & 0x01010101u;
+        pk_succ += (w >> 3) & 0x01010101u;
+        steps += (uint32_t)nvalid;
+        if (++pk_n == 255u) widen();
+    }
+    template <typename R> __device__ __forceinline__ void add_env(uint32_t flags, uint32_t time_after, R reward) {
         length += (flags & 1u) ? time_after : 0u;
-        steps += 1u;
         int fx;
         if constexpr (sizeof(R) == 8) fx = __double2int_rn(reward * R(AQUA_REWARD_FIXED_POINT));
         else fx = __float2int_rn(reward * R(AQUA_REWARD_FIXED_POINT));
@@ -142,8 +148,9 @@ struct ThreadStats {
 };
 
 // warp reduce (REDUX) -> shared slots -> one global atomic per counter per CTA
-__device__ __forceinline__ void flush_stats(const ThreadStats& t, unsigned long long* s_stats,
+__device__ __forceinline__ void flush_stats(ThreadStats& t, unsigned long long* s_stats,
                                             unsigned long long* g_slots) {
+    t.widen();
     const unsigned full = 0xffffffffu;
     const uint32_t d = __reduce_add_sync(full, t.done);
     const uint32_t c = __reduce_add_sync(full, t.collided);
@@ -174,26 +181,53 @@ __device__ __forceinline__ void flush_stats(const ThreadStats& t, unsigned long 
 
 template <typename R>
 __device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g_tab, int k_obst) {
-    // words of box[] actually used, then r2[]
     const uint32_t* src = reinterpret_cast<const uint32_t*>(g_tab);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
     constexpr int kWordsPerBox = sizeof(ObstacleBox<R>) / 4;
-    constexpr int kR2Off = sizeof(ObstacleBox<R>) * AQUA_MAX_OBSTACLES / 4;
-    constexpr int kWordsPerR = sizeof(R) / 4;
     for (int i = threadIdx.x; i < k_obst * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
-    for (int i = threadIdx.x; i < k_obst * kWordsPerR; i += blockDim.x) dst[kR2Off + i] = __ldg(src + kR2Off + i);
 }
 
+// ------------------------------------------------------------------------------------------
+// Phase B of a step: the CTA resets the envs its threads queued (tile-local indices), kCoopLanes
+// lanes per env.  The owner has already stored the terminal time word; the fresh episode goes
+// straight to the state planes (aqua.py:100-126).  Called by every thread of the CTA.
+// ------------------------------------------------------------------------------------------
 template <typename R>
-__device__ __forceinline__ void apply_reset(EnvState<R>& e, const ResetResult& r, uint32_t ep) {
-    e.x = (R)r.x;  // draws are float32 values: exact in either precision
-    e.y = (R)r.y;
-    e.th = (R)r.th;
-    e.wx = (R)r.wx;
-    e.wy = (R)r.wy;
-    e.gx = (R)r.gx;
-    e.gy = (R)r.gy;
-    e.tw = ep << AQUA_TIME_BITS;
+__device__ __forceinline__ void reset_queued(const StepArgs& p, const ObstacleTable<R>& tab,
+                                             const uint16_t* s_queue, int nq, int64_t tile_base) {
+    constexpr int kGroupsPerWarp = 32 / kCoopLanes;
+    const int groups = (int)blockDim.x / kCoopLanes;
+    const int grp = (int)threadIdx.x / kCoopLanes;
+    const bool leader = (threadIdx.x % kCoopLanes) == 0;
+    const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
+    uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
+    for (int q0 = 0; q0 < nq; q0 += groups) {
+        if (q0 + ((int)threadIdx.x / 32) * kGroupsPerWarp >= nq) continue;  // this warp has no env this round
+        const int q = q0 + grp;
+        const bool valid = q < nq;
+        const int64_t i = tile_base + (valid ? (int64_t)s_queue[q] : 0);
+        const uint32_t tw = valid ? ptw[i] : 0u;
+        const uint32_t ep = ((tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+        const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
+        const CoopResetResult rr = coop_reset<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst, wf, valid, env_id, ep);
+        if (valid && leader) {
+            plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_Y)[i] = (R)rr.y;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_THETA)[i] = (R)rr.th;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_X)[i] = (R)rr.gx;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_Y)[i] = (R)rr.gy;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_X)[i] = (R)rr.wx;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_Y)[i] = (R)rr.wy;
+            ptw[i] = ep << AQUA_TIME_BITS;
+        }
+    }
+}
+
+template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8_t, V>& f, int nvalid) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) w |= (j < nvalid ? (uint32_t)f.v[j] : 0u) << (8 * j);
+    return w;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -205,115 +239,118 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
     constexpr int V = Prec<R>::V;
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    __shared__ uint16_t s_queue[kMaxThreads * V];
+    __shared__ int s_nq[2];
     stage_table<R>(tab, p.w.tab, p.w.k_obst);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
     __syncthreads();
 
     const int64_t ld = p.ld;
-    R* const px_ = plane<R>(p.planes, ld, 0);
-    R* const py_ = plane<R>(p.planes, ld, 1);
-    R* const pth_ = plane<R>(p.planes, ld, 2);
+    R* const px_ = plane<R>(p.planes, ld, AQUA_PLANE_X);
+    R* const py_ = plane<R>(p.planes, ld, AQUA_PLANE_Y);
+    R* const pth_ = plane<R>(p.planes, ld, AQUA_PLANE_THETA);
     R* const pwx_ = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X);
     R* const pwy_ = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y);
     R* const pgx_ = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X);
     R* const pgy_ = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y);
     uint32_t* const ptw_ = plane_tw<R>(p.planes, ld);
     const bool waves = p.w.waves != 0;
-    const int k_obst = p.w.k_obst;
+    const bool autoreset = p.w.autoreset != 0;
+    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
     const int64_t tile_envs = (int64_t)blockDim.x * V;
 
     ThreadStats st;
-    for (int64_t base = p.env_begin + (int64_t)blockIdx.x * tile_envs + (int64_t)threadIdx.x * V;
-         base < p.env_end; base += (int64_t)gridDim.x * tile_envs) {
-        const int nvalid = (int)min((int64_t)V, p.env_end - base);
+    int it = 0;
+    // the loop is uniform over the CTA (phase B synchronises it)
+    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base < p.env_end;
+         tile_base += (int64_t)gridDim.x * tile_envs, ++it) {
+        const int64_t base = tile_base + (int64_t)threadIdx.x * V;
+        const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
+        const int qb = it & 1;
+        if (nvalid > 0) {
+            // ---- loads: one 16-byte access per plane (the planes are padded to AQUA_TILE) ----
+            const Pack<R, V> vx = ld_pack<R, V>(px_ + base), vy = ld_pack<R, V>(py_ + base);
+            const Pack<R, V> vth = ld_pack<R, V>(pth_ + base);
+            const Pack<R, V> vwx = ld_pack<R, V>(pwx_ + base), vwy = ld_pack<R, V>(pwy_ + base);
+            const Pack<R, V> vgx = ld_pack<R, V>(pgx_ + base), vgy = ld_pack<R, V>(pgy_ + base);
+            const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(ptw_ + base);
+            R tl[V], tr[V];
+            load_thrusts<R, ACT, V>(p.actions, base, nvalid, tl, tr, st.bad);
 
-        // ---- loads: one 16-byte access per plane (the planes are padded to AQUA_TILE) ----
-        const Pack<R, V> vx = ld_pack<R, V>(px_ + base), vy = ld_pack<R, V>(py_ + base);
-        const Pack<R, V> vth = ld_pack<R, V>(pth_ + base);
-        const Pack<R, V> vwx = ld_pack<R, V>(pwx_ + base), vwy = ld_pack<R, V>(pwy_ + base);
-        const Pack<R, V> vgx = ld_pack<R, V>(pgx_ + base), vgy = ld_pack<R, V>(pgy_ + base);
-        const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(ptw_ + base);
-        R tl[V], tr[V];
-        load_thrusts<R, ACT, V>(p.actions, base, nvalid, tl, tr, st.bad);
-
-        EnvState<R> e[V];
-        MoveTmp<R> m[V];
-        R pxn[V], pyn[V];
-        bool hit[V];
+            EnvState<R> e[V];
+            MoveTmp<R> m[V];
+            R pxn[V], pyn[V];
+            bool hit[V];
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
-            e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
-            e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
-            e[j].tw = vtw.v[j];
-            const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-            float nx = 0.f, ny = 0.f;
-            if constexpr (INJECT) {
-                if (j < nvalid) {
-                    nx = __ldg(p.noise_x + base + j);
-                    ny = __ldg(p.noise_y + base + j);
+            for (int j = 0; j < V; ++j) {
+                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
+                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
+                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
+                e[j].tw = vtw.v[j];
+                float nx = 0.f, ny = 0.f;
+                if constexpr (INJECT) {
+                    if (j < nvalid) {
+                        nx = __ldg(p.noise_x + base + j);
+                        ny = __ldg(p.noise_y + base + j);
+                    }
+                } else {
+                    const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
+                    if (waves)
+                        draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
                 }
+                move_env<R>(e[j], tl[j], tr[j], (R)nx, (R)ny, waves, m[j]);
+                pxn[j] = e[j].x;
+                pyn[j] = e[j].y;
+                hit[j] = false;
+            }
+            hits_obstacles<R, V>(tab, k_circ, k_obst, pxn, pyn, hit);
+
+            Pack<R, V> vrew, ox, oy, oth, owx, owy;
+            Pack<uint8_t, V> vfl;
+            Pack<uint32_t, V> otw;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                R reward;
+                const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
+                vrew.v[j] = reward;
+                vfl.v[j] = (uint8_t)f;
+                if (j < nvalid) st.add_env<R>(f, e[j].tw & kTimeMask, reward);
+                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
+            }
+            const uint32_t fw = flags_word<V>(vfl, nvalid);
+            st.add_flags(fw, nvalid);
+            if (autoreset && fw != 0u) {  // rare: queue the finished envs for phase B
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if ((fw >> (8 * j)) & 1u) s_queue[atomicAdd(&s_nq[qb], 1)] = (uint16_t)(threadIdx.x * V + j);
+            }
+
+            // ---- stores (the goal only changes at reset: phase B writes it) ----
+            st_pack<R, V>(px_ + base, ox);
+            st_pack<R, V>(py_ + base, oy);
+            st_pack<R, V>(pth_ + base, oth);
+            st_pack<R, V>(pwx_ + base, owx);
+            st_pack<R, V>(pwy_ + base, owy);
+            st_pack<uint32_t, V>(ptw_ + base, otw);
+            R* const rew = reinterpret_cast<R*>(p.reward) + base;
+            uint8_t* const fl = p.flags + base;
+            if (nvalid == V) {
+                st_pack<R, V>(rew, vrew);
+                st_pack<uint8_t, V>(fl, vfl);
             } else {
-                if (waves)
-                    draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
-            }
-            move_env<R>(e[j], tl[j], tr[j], (R)nx, (R)ny, waves, m[j]);
-            pxn[j] = e[j].x;
-            pyn[j] = e[j].y;
-            hit[j] = false;
-        }
-        hits_obstacles<R, V>(tab, k_obst, pxn, pyn, hit);
-
-        Pack<R, V> vrew;
-        Pack<uint8_t, V> vfl;
-        bool any_reset = false;
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            R reward;
-            const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
-            vrew.v[j] = reward;
-            vfl.v[j] = (uint8_t)f;
-            if (j < nvalid) st.add<R>(f, e[j].tw & kTimeMask, reward);
-            if ((f & AQUA_FLAG_DONE) && p.w.autoreset) {  // rare and divergent: out of line
-                const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                const uint32_t ep = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
-                const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, k_obst,
-                                                 WorldFlags{waves, p.w.random_boat != 0, p.w.random_goal != 0});
-                apply_reset<R>(e[j], rr, ep);
-                any_reset = true;
+                for (int j = 0; j < V; ++j)
+                    if (j < nvalid) { rew[j] = vrew.v[j]; fl[j] = vfl.v[j]; }
             }
         }
-
-        // ---- stores ----
-        Pack<R, V> ox, oy, oth, owx, owy;
-        Pack<uint32_t, V> otw;
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
-            owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
-        }
-        st_pack<R, V>(px_ + base, ox);
-        st_pack<R, V>(py_ + base, oy);
-        st_pack<R, V>(pth_ + base, oth);
-        st_pack<R, V>(pwx_ + base, owx);
-        st_pack<R, V>(pwy_ + base, owy);
-        st_pack<uint32_t, V>(ptw_ + base, otw);
-        if (any_reset) {  // the goal only changes at reset
-            Pack<R, V> ogx, ogy;
-#pragma unroll
-            for (int j = 0; j < V; ++j) { ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; }
-            st_pack<R, V>(pgx_ + base, ogx);
-            st_pack<R, V>(pgy_ + base, ogy);
-        }
-        R* const rew = reinterpret_cast<R*>(p.reward) + base;
-        uint8_t* const fl = p.flags + base;
-        if (nvalid == V) {
-            st_pack<R, V>(rew, vrew);
-            st_pack<uint8_t, V>(fl, vfl);
-        } else {
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-                if (j < nvalid) { rew[j] = vrew.v[j]; fl[j] = vfl.v[j]; }
+        if (autoreset) {
+            __syncthreads();
+            const int nq = s_nq[qb];
+            if (threadIdx.x == 0) s_nq[qb ^ 1] = 0;  // the other counter is idle between the two barriers
+            if (nq > 0) reset_queued<R>(p, tab, s_queue, nq, tile_base);
+            __syncthreads();
         }
     }
     flush_stats(st, s_stats, p.stats);
@@ -328,30 +365,34 @@ __global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_co
     constexpr int V = Prec<R>::V;
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    __shared__ uint16_t s_queue[kMaxThreads * V];
+    __shared__ int s_nq[2];
     stage_table<R>(tab, p.w.tab, p.w.k_obst);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
     __syncthreads();
 
     const int64_t ld = p.ld;
     const bool waves = p.w.waves != 0;
-    const int k_obst = p.w.k_obst;
+    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
     const int64_t tile_envs = (int64_t)blockDim.x * V;
-    const WorldFlags wf{waves, p.w.random_boat != 0, p.w.random_goal != 0};
+    uint32_t* const ptw_ = plane_tw<R>(p.planes, ld);
 
     ThreadStats st;
-    for (int64_t base = p.env_begin + (int64_t)blockIdx.x * tile_envs + (int64_t)threadIdx.x * V;
-         base < p.env_end; base += (int64_t)gridDim.x * tile_envs) {
-        const int nvalid = (int)min((int64_t)V, p.env_end - base);
+    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base < p.env_end;
+         tile_base += (int64_t)gridDim.x * tile_envs) {
+        const int64_t base = tile_base + (int64_t)threadIdx.x * V;
+        const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
         EnvState<R> e[V];
-        {
-            const Pack<R, V> vx = ld_pack<R, V>(plane<R>(p.planes, ld, 0) + base);
-            const Pack<R, V> vy = ld_pack<R, V>(plane<R>(p.planes, ld, 1) + base);
-            const Pack<R, V> vth = ld_pack<R, V>(plane<R>(p.planes, ld, 2) + base);
+        if (nvalid > 0) {
+            const Pack<R, V> vx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_X) + base);
+            const Pack<R, V> vy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_Y) + base);
+            const Pack<R, V> vth = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_THETA) + base);
             const Pack<R, V> vwx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base);
             const Pack<R, V> vwy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base);
             const Pack<R, V> vgx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base);
             const Pack<R, V> vgy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base);
-            const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(plane_tw<R>(p.planes, ld) + base);
+            const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(ptw_ + base);
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
@@ -361,59 +402,91 @@ __global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_co
             }
         }
         for (int64_t k = 0; k < p.steps; ++k) {
-            const uint64_t step = p.step0 + (uint64_t)k;
-            MoveTmp<R> m[V];
-            R pxn[V], pyn[V];
-            bool hit[V];
+            const int qb = (int)(k & 1);
+            uint32_t fw = 0u;
+            if (nvalid > 0) {
+                const uint64_t step = p.step0 + (uint64_t)k;
+                MoveTmp<R> m[V];
+                R pxn[V], pyn[V];
+                bool hit[V];
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
-                const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                const uint4 ra = philox_env(p.w.keys, env_id, (uint32_t)step, (uint32_t)(step >> 32), kStreamAction);
-                R tl, tr;
-                uint32_t bad = 0;
-                if constexpr (CONTINUOUS) {
-                    decode_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), tl, tr, bad);
-                } else {
-                    decode_discrete<R>((long long)__umulhi(ra.x, 3u), tl, tr, bad);
-                }
-                float nx = 0.f, ny = 0.f;
-                if (waves)
-                    draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
-                move_env<R>(e[j], tl, tr, (R)nx, (R)ny, waves, m[j]);
-                pxn[j] = e[j].x;
-                pyn[j] = e[j].y;
-                hit[j] = false;
-            }
-            hits_obstacles<R, V>(tab, k_obst, pxn, pyn, hit);
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                R reward;
-                const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
-                if (j < nvalid) st.add<R>(f, e[j].tw & kTimeMask, reward);
-                if (f & AQUA_FLAG_DONE) {
+                for (int j = 0; j < V; ++j) {
                     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                    const uint32_t ep = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
-                    const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, k_obst, wf);
-                    apply_reset<R>(e[j], rr, ep);
+                    const uint4 ra = philox_env(p.w.keys, env_id, (uint32_t)step, (uint32_t)(step >> 32), kStreamAction);
+                    R tl, tr;
+                    if constexpr (CONTINUOUS) {
+                        uint32_t bad = 0;
+                        decode_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), tl, tr, bad);
+                    } else {
+                        decode_discrete<R>((long long)__umulhi(ra.x, 3u), tl, tr);
+                    }
+                    float nx = 0.f, ny = 0.f;
+                    if (waves)
+                        draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
+                    move_env<R>(e[j], tl, tr, (R)nx, (R)ny, waves, m[j]);
+                    pxn[j] = e[j].x;
+                    pyn[j] = e[j].y;
+                    hit[j] = false;
+                }
+                hits_obstacles<R, V>(tab, k_circ, k_obst, pxn, pyn, hit);
+                Pack<uint8_t, V> vfl;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    R reward;
+                    const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
+                    vfl.v[j] = (uint8_t)f;
+                    if (j < nvalid) st.add_env<R>(f, e[j].tw & kTimeMask, reward);
+                }
+                fw = flags_word<V>(vfl, nvalid);
+                st.add_flags(fw, nvalid);
+                if (fw != 0u) {  // rare: publish the terminal time word and queue the env for phase B
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+                        if ((fw >> (8 * j)) & 1u) {
+                            ptw_[base + j] = e[j].tw;
+                            s_queue[atomicAdd(&s_nq[qb], 1)] = (uint16_t)(threadIdx.x * V + j);
+                        }
                 }
             }
-        }
-        Pack<R, V> ox, oy, oth, owx, owy, ogx, ogy;
-        Pack<uint32_t, V> otw;
+            __syncthreads();
+            const int nq = s_nq[qb];
+            if (threadIdx.x == 0) s_nq[qb ^ 1] = 0;
+            if (nq > 0) reset_queued<R>(p, tab, s_queue, nq, tile_base);
+            __syncthreads();
+            if (fw != 0u) {  // pick the fresh episode up from the planes
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
-            owx.v[j] = e[j].wx; owy.v[j] = e[j].wy;
-            ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; otw.v[j] = e[j].tw;
+                for (int j = 0; j < V; ++j)
+                    if ((fw >> (8 * j)) & 1u) {
+                        const int64_t i = base + j;
+                        e[j].x = plane<R>(p.planes, ld, AQUA_PLANE_X)[i];
+                        e[j].y = plane<R>(p.planes, ld, AQUA_PLANE_Y)[i];
+                        e[j].th = plane<R>(p.planes, ld, AQUA_PLANE_THETA)[i];
+                        e[j].gx = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X)[i];
+                        e[j].gy = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y)[i];
+                        e[j].wx = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X)[i];
+                        e[j].wy = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y)[i];
+                        e[j].tw = ptw_[i];
+                    }
+            }
         }
-        st_pack<R, V>(plane<R>(p.planes, ld, 0) + base, ox);
-        st_pack<R, V>(plane<R>(p.planes, ld, 1) + base, oy);
-        st_pack<R, V>(plane<R>(p.planes, ld, 2) + base, oth);
-        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base, owx);
-        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base, owy);
-        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base, ogx);
-        st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base, ogy);
-        st_pack<uint32_t, V>(plane_tw<R>(p.planes, ld) + base, otw);
+        if (nvalid > 0) {
+            Pack<R, V> ox, oy, oth, owx, owy, ogx, ogy;
+            Pack<uint32_t, V> otw;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy;
+                ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; otw.v[j] = e[j].tw;
+            }
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_X) + base, ox);
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_Y) + base, oy);
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_THETA) + base, oth);
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base, owx);
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base, owy);
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base, ogx);
+            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base, ogy);
+            st_pack<uint32_t, V>(ptw_ + base, otw);
+        }
     }
     flush_stats(st, s_stats, p.stats);
 }
@@ -432,16 +505,15 @@ __global__ void __launch_bounds__(kMaxThreads) reset_kernel(const __grid_constan
     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
     const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, p.w.k_obst,
                                      WorldFlags{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0});
-    EnvState<R> e;
-    apply_reset<R>(e, rr, ep);
-    plane<R>(p.planes, p.ld, 0)[i] = e.x;
-    plane<R>(p.planes, p.ld, 1)[i] = e.y;
-    plane<R>(p.planes, p.ld, 2)[i] = e.th;
-    plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_X)[i] = e.wx;
-    plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_Y)[i] = e.wy;
-    plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_X)[i] = e.gx;
-    plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_Y)[i] = e.gy;
-    ptw[i] = e.tw;
+    // the draws are float32 values: exact in either precision
+    plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_Y)[i] = (R)rr.y;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_THETA)[i] = (R)rr.th;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_X)[i] = (R)rr.wx;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_Y)[i] = (R)rr.wy;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_X)[i] = (R)rr.gx;
+    plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_Y)[i] = (R)rr.gy;
+    ptw[i] = ep << AQUA_TIME_BITS;
 }
 
 // fresh handle: no episode opened yet (the first reset opens episode 0), pose planes zero
@@ -644,6 +716,20 @@ size_t obstacle_table_bytes(int precision) {
     return precision == AQUA_F64 ? sizeof(ObstacleTable<double>) : sizeof(ObstacleTable<float>);
 }
 
+// circles first (stable), then rectangles; returns the number of circles
+static int sorted_rows(int k, const double* rows5, double* out5) {
+    int n = 0;
+    for (int pass = 0; pass < 2; ++pass)
+        for (int i = 0; i < k; ++i)
+            if ((rows5[5 * i + 2] == 0.0) == (pass == 0)) {
+                memcpy(out5 + 5 * n, rows5 + 5 * i, 5 * sizeof(double));
+                ++n;
+            }
+    int k_circ = 0;
+    for (int i = 0; i < k; ++i) k_circ += rows5[5 * i + 2] == 0.0;
+    return k_circ;
+}
+
 template <typename R> static void fill_table(int k, const double* rows5, ObstacleTable<R>* t) {
     memset(t, 0, sizeof(*t));
     for (int i = 0; i < k; ++i) {
@@ -651,18 +737,24 @@ template <typename R> static void fill_table(int k, const double* rows5, Obstacl
         const bool circle = o[2] == 0.0;
         t->box[i].cx = (R)o[0];
         t->box[i].cy = (R)o[1];
-        t->box[i].hx = circle ? R(0) : (R)(o[3] / 2);
-        t->box[i].hy = circle ? R(0) : (R)(o[4] / 2);
-        const double reach = circle ? o[3] + 2.5 : 2.5;  // boat radius 2.5, aqua.py:75
-        t->r2[i] = (R)(reach * reach);
+        if (circle) {
+            const double reach = o[3] + 2.5;  // boat / goal radius 2.5, aqua.py:72,75
+            t->box[i].a = (R)(reach * reach);
+            t->box[i].b = R(0);
+        } else {
+            t->box[i].a = (R)(o[3] / 2);
+            t->box[i].b = (R)(o[4] / 2);
+        }
     }
 }
 
-void build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host) {
-    if (precision == AQUA_F64) fill_table<double>(k, rows5, reinterpret_cast<ObstacleTable<double>*>(tab_host));
-    else fill_table<float>(k, rows5, reinterpret_cast<ObstacleTable<float>*>(tab_host));
+int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host) {
+    double sorted[AQUA_MAX_OBSTACLES * 5];
+    const int k_circ = sorted_rows(k, rows5, sorted);
+    if (precision == AQUA_F64) fill_table<double>(k, sorted, reinterpret_cast<ObstacleTable<double>*>(tab_host));
+    else fill_table<float>(k, sorted, reinterpret_cast<ObstacleTable<float>*>(tab_host));
     for (int i = 0; i < k; ++i) {
-        const double* o = rows5 + 5 * i;
+        const double* o = sorted + 5 * i;
         const bool circle = o[2] == 0.0;
         double* d = tab64_host + 5 * i;
         d[0] = o[0];
@@ -672,6 +764,7 @@ void build_obstacle_tables(int precision, int k, const double* rows5, void* tab_
         const double reach = circle ? o[3] + 2.5 : 2.5;
         d[4] = reach * reach;
     }
+    return k_circ;
 }
 
 }  // namespace aqua

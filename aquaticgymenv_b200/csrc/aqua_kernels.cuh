@@ -27,6 +27,7 @@ struct World {
     const double* tab64;    // device double[K][5] = {cx, cy, hx, hy, r2}: float64 table (reset path)
     const uint32_t* grid;   // device uint32[kGridCells][2]: per-cell obstacle bit masks (or NULL)
     int32_t k_obst;
+    int32_t k_circ;         // obstacles [0, k_circ) are circles, [k_circ, k_obst) rectangles
     uint8_t waves, random_boat, random_goal, autoreset;
 };
 
@@ -69,6 +70,7 @@ cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* b
 
 // host-side construction of the device obstacle tables; `out` sized for the precision
 size_t obstacle_table_bytes(int precision);
-void build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host);
+// (circles first, then rectangles); returns the number of circles
+int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host);
 
 }  // namespace aqua
