@@ -248,15 +248,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
 
     aqua::World& w = env->world;
     memset(&w, 0, sizeof w);
-    {
-        uint32_t k0 = (uint32_t)cfg->seed, k1 = (uint32_t)(cfg->seed >> 32);
-        for (int r = 0; r < 10; ++r) {
-            w.keys.rk[2 * r] = k0;
-            w.keys.rk[2 * r + 1] = k1;
-            k0 += 0x9E3779B9u;
-            k1 += 0xBB67AE85u;
-        }
-    }
+    aqua::make_philox_keys(cfg->seed, &w.keys);
     w.env_id_base = cfg->env_id_base;
     w.tab = env->d_tab;
     w.tab64 = env->d_tab64;

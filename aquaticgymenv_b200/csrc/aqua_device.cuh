@@ -35,8 +35,8 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     for (int r = 0; r < 10; ++r) {
         const unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
         const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.rk[2 * r];
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.rk[2 * r + 1];
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k.rk4[2 * r];
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k.rk4[2 * r + 1];
         c1 = (uint32_t)p1;
         c3 = (uint32_t)p0;
         c0 = n0;
@@ -48,6 +48,20 @@ __device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
 __device__ __forceinline__ uint4 philox_env(const PhiloxKeys& k, uint32_t env_id, uint32_t c1, uint32_t c2,
                                             uint32_t tag) {
     return philox4x32_10(env_id, c1, c2, tag, k);
+}
+
+// Philox2x32-10: the per-step draws need two words only (half the multiplies of the 4x32 form).
+// `rk` = the stream's ten round keys; `key_add` shifts the key (ACTION stream: high step word).
+__device__ __forceinline__ uint2 philox2x32_10(uint32_t c0, uint32_t c1, const uint32_t (&rk)[10],
+                                               uint32_t key_add = 0u) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned long long p = (unsigned long long)0xD256D193u * c0;
+        const uint32_t n0 = (uint32_t)(p >> 32) ^ c1 ^ (rk[r] + key_add);
+        c1 = (uint32_t)p;
+        c0 = n0;
+    }
+    return make_uint2(c0, c1);
 }
 
 // 24 high bits -> float in [0,1): u01 = (u >> 8) * 2^-24, exact.  The draw maps below fold the
@@ -65,13 +79,23 @@ __device__ __forceinline__ float draw_wave0(uint32_t u) { return __fmaf_rn(u24(u
 __device__ __forceinline__ float draw_noise(uint32_t u) { return __fmaf_rn(u24(u), 0.002f * 0x1p-24f, -0.001f); }
 __device__ __forceinline__ float draw_thrust(uint32_t u) { return __fmaf_rn(u24(u), 0.3f * 0x1p-24f, 0.2f); }
 
-// wave increment of step `t` (env time before the increment) -- aqua.py:188
-__device__ __forceinline__ void draw_wave_noise(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
-                                                uint32_t t, float& nx, float& ny) {
-    const uint4 r = philox_env(keys, env_id, ep, t >> 1, kStreamWaveNoise);
-    const bool odd = (t & 1u) != 0u;
-    nx = draw_noise(odd ? r.z : r.x);
-    ny = draw_noise(odd ? r.w : r.y);
+// wave increment of the step taken at time word `tw` = (episode << 11) | t -- aqua.py:188
+__device__ __forceinline__ void draw_wave_noise(const PhiloxKeys& keys, uint32_t env_id, uint32_t tw,
+                                                float& nx, float& ny) {
+    const uint2 r = philox2x32_10(env_id, tw, keys.noise);
+    nx = draw_noise(r.x);
+    ny = draw_noise(r.y);
+}
+// wave speed of a fresh episode -- aqua.py:124
+__device__ __forceinline__ void draw_wave_init(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
+                                               float& wx, float& wy) {
+    const uint2 r = philox2x32_10(env_id, ep, keys.winit);
+    wx = draw_wave0(r.x);
+    wy = draw_wave0(r.y);
+}
+// synthetic random policy (test_random.py:19-20)
+__device__ __forceinline__ uint2 draw_action_words(const PhiloxKeys& keys, uint32_t env_id, uint64_t step) {
+    return philox2x32_10(env_id, (uint32_t)step, keys.action, (uint32_t)(step >> 32));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -125,17 +149,18 @@ template <typename R> struct ObstacleTable {
 };
 constexpr double kRectR2 = 6.25;  // (boat or goal radius 2.5)^2, aqua.py:72,75
 
-// collision of V positions against the whole table: the table entry is read once per obstacle
+// Signed squared clearance of V positions against the whole table, min-accumulated: an env
+// collides iff the minimum is <= 0.  The table entry is read once per obstacle.
 template <typename R, int V>
-__device__ __forceinline__ void hits_obstacles(const ObstacleTable<R>& tab, int k_circ, int k_obst,
-                                               const R (&px)[V], const R (&py)[V], bool (&hit)[V]) {
+__device__ __forceinline__ void obstacle_clearance(const ObstacleTable<R>& tab, int k_circ, int k_obst,
+                                                   const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
 #pragma unroll 2
     for (int k = 0; k < k_circ; ++k) {
         const ObstacleBox<R> o = tab.box[k];
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             const R ddx = px[j] - o.cx, ddy = py[j] - o.cy;
-            hit[j] |= (fma(ddx, ddx, ddy * ddy) <= o.a);
+            clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, -o.a)));
         }
     }
     for (int k = k_circ; k < k_obst; ++k) {
@@ -144,10 +169,11 @@ __device__ __forceinline__ void hits_obstacles(const ObstacleTable<R>& tab, int 
         for (int j = 0; j < V; ++j) {
             const R ddx = fmax(fabs(px[j] - o.cx) - o.a, R(0));
             const R ddy = fmax(fabs(py[j] - o.cy) - o.b, R(0));
-            hit[j] |= (fma(ddx, ddx, ddy * ddy) <= R(kRectR2));
+            clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, R(-kRectR2))));
         }
     }
 }
+constexpr float kClearFar = 1e30f;  // initial clearance: "no obstacle near"
 
 // same test against the float64 table in global memory (reset path: rare, always float64 so
 // that accept/reject decisions are those of the float64 reference)
@@ -157,7 +183,7 @@ __device__ __forceinline__ bool hits_obstacle_g(const double* __restrict__ tab64
         const double* o = tab64 + 5 * k;
         const double ddx = fmax(fabs(px - o[0]) - o[2], 0.0);
         const double ddy = fmax(fabs(py - o[1]) - o[3], 0.0);
-        if (fma(ddx, ddx, ddy * ddy) <= o[4]) return true;
+        if (fma(ddx, ddx, fma(ddy, ddy, -o[4])) <= 0.0) return true;
     }
     return false;
 }
@@ -211,9 +237,10 @@ __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t e
         o.th = 0.0;
     }
     if (wf.waves) {  // aqua.py:124
-        const uint4 r = philox_env(keys, env_id, ep, 0u, kStreamWaveInit);
-        o.wx = (double)draw_wave0(r.x);
-        o.wy = (double)draw_wave0(r.y);
+        float wx, wy;
+        draw_wave_init(keys, env_id, ep, wx, wy);
+        o.wx = (double)wx;
+        o.wy = (double)wy;
     } else {
         o.wx = 0.0;
         o.wy = 0.0;
@@ -246,9 +273,9 @@ __device__ __forceinline__ bool reset_blocked(const ObstacleTable<R>& tab, const
                                               int k_circ, int k_obst, float x, float y) {
     if constexpr (sizeof(R) == 8) {
         const double px[1] = {(double)x}, py[1] = {(double)y};
-        bool hit[1] = {false};
-        hits_obstacles<double, 1>(tab, k_circ, k_obst, px, py, hit);
-        return hit[0];
+        double clr[1] = {(double)kClearFar};
+        obstacle_clearance<double, 1>(tab, k_circ, k_obst, px, py, clr);
+        return clr[0] <= 0.0;
     } else {
         bool hit = false, unsure = false;
         for (int k = 0; k < k_circ; ++k) {
@@ -341,9 +368,7 @@ __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, co
         n0 += kCoopLanes;
     }
     if (wf.waves) {  // aqua.py:124
-        const uint4 r = philox_env(keys, env_id, ep, 0u, kStreamWaveInit);
-        o.wx = draw_wave0(r.x);
-        o.wy = draw_wave0(r.y);
+        draw_wave_init(keys, env_id, ep, o.wx, o.wy);
     } else {
         o.wx = 0.f;
         o.wy = 0.f;
@@ -424,14 +449,13 @@ __device__ __forceinline__ void move_env(EnvState<R>& e, R tl, R tr, R nx, R ny,
     }
 
     // ---- time, aqua.py:141 ----
-    const uint32_t t = e.tw & kTimeMask;
-    e.tw = (e.tw & ~kTimeMask) | min(t + 1u, kTimeMask);
+    e.tw += ((e.tw & kTimeMask) != kTimeMask) ? 1u : 0u;  // saturates at 2047
 }
 
-// Phase 2: termination ladder aqua.py:194-211.  `hit_obstacle` comes from hits_obstacles().
+// Phase 2: termination ladder aqua.py:194-211.  `clearance` comes from obstacle_clearance().
 // Returns the AQUA_FLAG_* byte; `reward` receives the step reward.
 template <typename R>
-__device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveTmp<R>& m, bool hit_obstacle,
+__device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveTmp<R>& m, R clearance,
                                                R& reward) {
     using P = Prec<R>;
     constexpr bool kF64 = sizeof(R) == 8;
@@ -441,7 +465,7 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
         collided = (xn - R(2.5) < R(0)) | (yn - R(2.5) < R(0)) | (xn + R(2.5) > R(100)) | (yn + R(2.5) > R(100));
     else  // float: p - 2.5 and p + 2.5 are exact near the borders, so this is the same predicate
         collided = !((fmin(xn, yn) >= R(2.5)) & (fmax(xn, yn) <= R(97.5)));
-    collided |= hit_obstacle;
+    collided |= clearance <= R(0);
 
     const R gcx = xn - e.gx, gcy = yn - e.gy;
     const R dc2 = fma(gcx, gcx, gcy * gcy);
@@ -482,9 +506,9 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
 // action decode ---------------------------------------------------------------------------
 // discrete table aqua.py:33-42: 0 -> (0.2, 0.5) rotate left, 1 -> (0.5, 0.2) rotate right,
 // 2 -> (0.5, 0.5) full throttle.  An index outside {0,1,2} selects full throttle and is counted.
-template <typename R> __device__ __forceinline__ void decode_discrete(long long a, R& tl, R& tr) {
-    tl = (a == 0) ? R(0.2) : R(0.5);
-    tr = (a == 1) ? R(0.2) : R(0.5);
+template <typename R> __device__ __forceinline__ void decode_discrete(uint32_t a, R& tl, R& tr) {
+    tl = (a == 0u) ? R(0.2) : R(0.5);
+    tr = (a == 1u) ? R(0.2) : R(0.5);
 }
 // continuous aqua.py:143-151: values outside [0.2, 0.5] are clipped (and counted)
 template <typename R>

@@ -59,16 +59,27 @@ template <typename R> __device__ __forceinline__ uint32_t* plane_tw(void* planes
 // ------------------------------------------------------------------------------------------
 // action decode for V envs starting at absolute env index `base`
 // ------------------------------------------------------------------------------------------
+// discrete indices as 32-bit words; an int64 index outside 32 bits maps to 0xffffffff (invalid)
 template <typename T, int V>
-__device__ __forceinline__ void load_discrete(const void* actions, int64_t base, int nvalid, long long (&a)[V]) {
+__device__ __forceinline__ void load_discrete(const void* actions, int64_t base, int nvalid, uint32_t (&a)[V]) {
     const T* src = reinterpret_cast<const T*>(actions) + base;
+    T raw[V];
     if (nvalid == V) {
         const Pack<T, V> pk = ldg_pack<T, V>(src);
 #pragma unroll
-        for (int j = 0; j < V; ++j) a[j] = (long long)pk.v[j];
+        for (int j = 0; j < V; ++j) raw[j] = pk.v[j];
     } else {
 #pragma unroll
-        for (int j = 0; j < V; ++j) a[j] = (j < nvalid) ? (long long)__ldg(src + j) : 2ll;
+        for (int j = 0; j < V; ++j) raw[j] = (j < nvalid) ? __ldg(src + j) : (T)2;
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        if constexpr (sizeof(T) == 8) {
+            const unsigned long long u = (unsigned long long)raw[j];
+            a[j] = (u >> 32) ? 0xffffffffu : (uint32_t)u;
+        } else {
+            a[j] = (uint32_t)raw[j];
+        }
     }
 }
 
@@ -93,19 +104,19 @@ __device__ __forceinline__ void load_thrusts(const void* actions, int64_t base, 
             bad += b;  // padding lanes hold 0.5: never counted
         }
     } else {
-        long long a[V];
+        uint32_t a[V];
         if constexpr (ACT == AQUA_ACT_I32) load_discrete<int32_t, V>(actions, base, nvalid, a);
         else if constexpr (ACT == AQUA_ACT_I64) load_discrete<long long, V>(actions, base, nvalid, a);
         else load_discrete<uint8_t, V>(actions, base, nvalid, a);
-        unsigned long long worst = 0ull;
+        uint32_t worst = 0u;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             decode_discrete<R>(a[j], tl[j], tr[j]);
-            worst = max(worst, (unsigned long long)a[j]);
+            worst = max(worst, a[j]);
         }
-        if (worst > 2ull) {  // rare: an index outside {0, 1, 2} (padding lanes hold 2)
+        if (worst > 2u) {  // rare: an index outside {0, 1, 2} (padding lanes hold 2)
 #pragma unroll
-            for (int j = 0; j < V; ++j) bad += ((unsigned long long)a[j] > 2ull) ? 1u : 0u;
+            for (int j = 0; j < V; ++j) bad += (a[j] > 2u) ? 1u : 0u;
         }
     }
 }
@@ -188,24 +199,37 @@ __device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase B of a step: the CTA resets the envs its threads queued (tile-local indices), kCoopLanes
-// lanes per env.  The owner has already stored the terminal time word; the fresh episode goes
-// straight to the state planes (aqua.py:100-126).  Called by every thread of the CTA.
+// Phase B of a step, per warp: the warp resets the envs its lanes finished in this tile,
+// kCoopLanes lanes per env (no CTA barrier).  `fw` holds the flags of the lane's V envs, one
+// byte each (0 for padding / inactive lanes); the owner has already stored the terminal time
+// word, the fresh episode goes straight to the state planes (aqua.py:100-126).
+// Must be called by all 32 lanes.
 // ------------------------------------------------------------------------------------------
-template <typename R>
-__device__ __forceinline__ void reset_queued(const StepArgs& p, const ObstacleTable<R>& tab,
-                                             const uint16_t* s_queue, int nq, int64_t tile_base) {
-    constexpr int kGroupsPerWarp = 32 / kCoopLanes;
-    const int groups = (int)blockDim.x / kCoopLanes;
-    const int grp = (int)threadIdx.x / kCoopLanes;
-    const bool leader = (threadIdx.x % kCoopLanes) == 0;
+template <typename R, int V>
+__device__ __forceinline__ void warp_reset(const StepArgs& p, const ObstacleTable<R>& tab, uint8_t* wq,
+                                           uint32_t fw, int64_t warp_base) {
+    constexpr int kGroups = 32 / kCoopLanes;
+    const unsigned full = 0xffffffffu;
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned lt = (1u << lane) - 1u;
+    // enumerate the finished envs of the warp into its queue (tile-local index lane * V + j)
+    int n = 0;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const bool d = ((fw >> (8 * j)) & 1u) != 0u;
+        const unsigned mj = __ballot_sync(full, d);
+        if (d) wq[n + __popc(mj & lt)] = (uint8_t)(lane * V + j);
+        n += __popc(mj);
+    }
+    __syncwarp();
     const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
     uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
-    for (int q0 = 0; q0 < nq; q0 += groups) {
-        if (q0 + ((int)threadIdx.x / 32) * kGroupsPerWarp >= nq) continue;  // this warp has no env this round
+    const int grp = (int)(lane / kCoopLanes);
+    const bool leader = (lane % kCoopLanes) == 0u;
+    for (int q0 = 0; q0 < n; q0 += kGroups) {
         const int q = q0 + grp;
-        const bool valid = q < nq;
-        const int64_t i = tile_base + (valid ? (int64_t)s_queue[q] : 0);
+        const bool valid = q < n;
+        const int64_t i = warp_base + (valid ? (int64_t)wq[q] : 0);
         const uint32_t tw = valid ? ptw[i] : 0u;
         const uint32_t ep = ((tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
         const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
@@ -221,6 +245,7 @@ __device__ __forceinline__ void reset_queued(const StepArgs& p, const ObstacleTa
             ptw[i] = ep << AQUA_TIME_BITS;
         }
     }
+    __syncwarp();
 }
 
 template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8_t, V>& f, int nvalid) {
@@ -239,11 +264,9 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
     constexpr int V = Prec<R>::V;
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
-    __shared__ uint16_t s_queue[kMaxThreads * V];
-    __shared__ int s_nq[2];
+    __shared__ uint8_t s_wq[kMaxThreads / 32][32 * V];
     stage_table<R>(tab, p.w.tab, p.w.k_obst);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
-    if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
     __syncthreads();
 
     const int64_t ld = p.ld;
@@ -259,15 +282,15 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
     const bool autoreset = p.w.autoreset != 0;
     const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
     const int64_t tile_envs = (int64_t)blockDim.x * V;
+    const int64_t warp_off = (int64_t)(threadIdx.x & ~31u) * V;  // first env of this warp within the tile
 
     ThreadStats st;
-    int it = 0;
-    // the loop is uniform over the CTA (phase B synchronises it)
-    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base < p.env_end;
-         tile_base += (int64_t)gridDim.x * tile_envs, ++it) {
+    // the loop is uniform over each warp (phase B is warp-collective)
+    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base + warp_off < p.env_end;
+         tile_base += (int64_t)gridDim.x * tile_envs) {
         const int64_t base = tile_base + (int64_t)threadIdx.x * V;
         const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
-        const int qb = it & 1;
+        uint32_t fw = 0u;
         if (nvalid > 0) {
             // ---- loads: one 16-byte access per plane (the planes are padded to AQUA_TILE) ----
             const Pack<R, V> vx = ld_pack<R, V>(px_ + base), vy = ld_pack<R, V>(py_ + base);
@@ -280,8 +303,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
 
             EnvState<R> e[V];
             MoveTmp<R> m[V];
-            R pxn[V], pyn[V];
-            bool hit[V];
+            R pxn[V], pyn[V], clr[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
@@ -296,15 +318,14 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
                     }
                 } else {
                     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                    if (waves)
-                        draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
+                    if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx, ny);
                 }
                 move_env<R>(e[j], tl[j], tr[j], (R)nx, (R)ny, waves, m[j]);
                 pxn[j] = e[j].x;
                 pyn[j] = e[j].y;
-                hit[j] = false;
+                clr[j] = R(kClearFar);
             }
-            hits_obstacles<R, V>(tab, k_circ, k_obst, pxn, pyn, hit);
+            obstacle_clearance<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
 
             Pack<R, V> vrew, ox, oy, oth, owx, owy;
             Pack<uint8_t, V> vfl;
@@ -312,20 +333,15 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 R reward;
-                const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
+                const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
                 vrew.v[j] = reward;
                 vfl.v[j] = (uint8_t)f;
                 if (j < nvalid) st.add_env<R>(f, e[j].tw & kTimeMask, reward);
                 ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
                 owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
             }
-            const uint32_t fw = flags_word<V>(vfl, nvalid);
+            fw = flags_word<V>(vfl, nvalid);
             st.add_flags(fw, nvalid);
-            if (autoreset && fw != 0u) {  // rare: queue the finished envs for phase B
-#pragma unroll
-                for (int j = 0; j < V; ++j)
-                    if ((fw >> (8 * j)) & 1u) s_queue[atomicAdd(&s_nq[qb], 1)] = (uint16_t)(threadIdx.x * V + j);
-            }
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
             st_pack<R, V>(px_ + base, ox);
@@ -345,14 +361,10 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
                     if (j < nvalid) { rew[j] = vrew.v[j]; fl[j] = vfl.v[j]; }
             }
         }
-        if (autoreset) {
-            __syncthreads();
-            const int nq = s_nq[qb];
-            if (threadIdx.x == 0) s_nq[qb ^ 1] = 0;  // the other counter is idle between the two barriers
-            if (nq > 0) reset_queued<R>(p, tab, s_queue, nq, tile_base);
-            __syncthreads();
-        }
+        if (autoreset && __any_sync(0xffffffffu, fw != 0u))
+            warp_reset<R, V>(p, tab, s_wq[threadIdx.x >> 5], fw, tile_base + warp_off);
     }
+    __syncthreads();
     flush_stats(st, s_stats, p.stats);
 }
 
@@ -365,21 +377,20 @@ __global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_co
     constexpr int V = Prec<R>::V;
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
-    __shared__ uint16_t s_queue[kMaxThreads * V];
-    __shared__ int s_nq[2];
+    __shared__ uint8_t s_wq[kMaxThreads / 32][32 * V];
     stage_table<R>(tab, p.w.tab, p.w.k_obst);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
-    if (threadIdx.x < 2) s_nq[threadIdx.x] = 0;
     __syncthreads();
 
     const int64_t ld = p.ld;
     const bool waves = p.w.waves != 0;
     const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
     const int64_t tile_envs = (int64_t)blockDim.x * V;
+    const int64_t warp_off = (int64_t)(threadIdx.x & ~31u) * V;
     uint32_t* const ptw_ = plane_tw<R>(p.planes, ld);
 
     ThreadStats st;
-    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base < p.env_end;
+    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base + warp_off < p.env_end;
          tile_base += (int64_t)gridDim.x * tile_envs) {
         const int64_t base = tile_base + (int64_t)threadIdx.x * V;
         const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
@@ -402,71 +413,63 @@ __global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_co
             }
         }
         for (int64_t k = 0; k < p.steps; ++k) {
-            const int qb = (int)(k & 1);
             uint32_t fw = 0u;
             if (nvalid > 0) {
                 const uint64_t step = p.step0 + (uint64_t)k;
                 MoveTmp<R> m[V];
-                R pxn[V], pyn[V];
-                bool hit[V];
+                R pxn[V], pyn[V], clr[V];
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                    const uint4 ra = philox_env(p.w.keys, env_id, (uint32_t)step, (uint32_t)(step >> 32), kStreamAction);
+                    const uint2 ra = draw_action_words(p.w.keys, env_id, step);
                     R tl, tr;
                     if constexpr (CONTINUOUS) {
                         uint32_t bad = 0;
                         decode_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), tl, tr, bad);
                     } else {
-                        decode_discrete<R>((long long)__umulhi(ra.x, 3u), tl, tr);
+                        decode_discrete<R>(__umulhi(ra.x, 3u), tl, tr);
                     }
                     float nx = 0.f, ny = 0.f;
-                    if (waves)
-                        draw_wave_noise(p.w.keys, env_id, e[j].tw >> AQUA_TIME_BITS, e[j].tw & kTimeMask, nx, ny);
+                    if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx, ny);
                     move_env<R>(e[j], tl, tr, (R)nx, (R)ny, waves, m[j]);
                     pxn[j] = e[j].x;
                     pyn[j] = e[j].y;
-                    hit[j] = false;
+                    clr[j] = R(kClearFar);
                 }
-                hits_obstacles<R, V>(tab, k_circ, k_obst, pxn, pyn, hit);
+                obstacle_clearance<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
                 Pack<uint8_t, V> vfl;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     R reward;
-                    const uint32_t f = finish_env<R>(e[j], m[j], hit[j], reward);
+                    const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
                     vfl.v[j] = (uint8_t)f;
                     if (j < nvalid) st.add_env<R>(f, e[j].tw & kTimeMask, reward);
                 }
                 fw = flags_word<V>(vfl, nvalid);
                 st.add_flags(fw, nvalid);
-                if (fw != 0u) {  // rare: publish the terminal time word and queue the env for phase B
+                if (fw != 0u) {  // rare: publish the terminal time word for phase B
+#pragma unroll
+                    for (int j = 0; j < V; ++j)
+                        if ((fw >> (8 * j)) & 1u) ptw_[base + j] = e[j].tw;
+                }
+            }
+            if (__any_sync(0xffffffffu, fw != 0u)) {
+                warp_reset<R, V>(p, tab, s_wq[threadIdx.x >> 5], fw, tile_base + warp_off);
+                if (fw != 0u) {  // pick the fresh episode up from the planes
 #pragma unroll
                     for (int j = 0; j < V; ++j)
                         if ((fw >> (8 * j)) & 1u) {
-                            ptw_[base + j] = e[j].tw;
-                            s_queue[atomicAdd(&s_nq[qb], 1)] = (uint16_t)(threadIdx.x * V + j);
+                            const int64_t i = base + j;
+                            e[j].x = plane<R>(p.planes, ld, AQUA_PLANE_X)[i];
+                            e[j].y = plane<R>(p.planes, ld, AQUA_PLANE_Y)[i];
+                            e[j].th = plane<R>(p.planes, ld, AQUA_PLANE_THETA)[i];
+                            e[j].gx = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X)[i];
+                            e[j].gy = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y)[i];
+                            e[j].wx = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X)[i];
+                            e[j].wy = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y)[i];
+                            e[j].tw = ptw_[i];
                         }
                 }
-            }
-            __syncthreads();
-            const int nq = s_nq[qb];
-            if (threadIdx.x == 0) s_nq[qb ^ 1] = 0;
-            if (nq > 0) reset_queued<R>(p, tab, s_queue, nq, tile_base);
-            __syncthreads();
-            if (fw != 0u) {  // pick the fresh episode up from the planes
-#pragma unroll
-                for (int j = 0; j < V; ++j)
-                    if ((fw >> (8 * j)) & 1u) {
-                        const int64_t i = base + j;
-                        e[j].x = plane<R>(p.planes, ld, AQUA_PLANE_X)[i];
-                        e[j].y = plane<R>(p.planes, ld, AQUA_PLANE_Y)[i];
-                        e[j].th = plane<R>(p.planes, ld, AQUA_PLANE_THETA)[i];
-                        e[j].gx = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X)[i];
-                        e[j].gy = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y)[i];
-                        e[j].wx = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X)[i];
-                        e[j].wy = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y)[i];
-                        e[j].tw = ptw_[i];
-                    }
             }
         }
         if (nvalid > 0) {
@@ -488,6 +491,7 @@ __global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_co
             st_pack<uint32_t, V>(ptw_ + base, otw);
         }
     }
+    __syncthreads();
     flush_stats(st, s_stats, p.stats);
 }
 
@@ -532,7 +536,7 @@ __global__ void random_actions_kernel(const __grid_constant__ World w, int64_t n
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t env_id = (uint32_t)(w.env_id_base + (uint64_t)i);
-    const uint4 r = philox_env(w.keys, env_id, (uint32_t)step, (uint32_t)(step >> 32), kStreamAction);
+    const uint2 r = draw_action_words(w.keys, env_id, step);
     if constexpr (ACT == AQUA_ACT_F32X2) {
         reinterpret_cast<float2*>(actions)[i] = make_float2(draw_thrust(r.x), draw_thrust(r.y));
     } else {
@@ -707,6 +711,40 @@ cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n,
 cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s) {
     stats_reduce_kernel<<<1, 256, 0, s>>>(slots, out, clear);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// host-side key schedule of the draw streams
+// ------------------------------------------------------------------------------------------
+static void philox4x32_10_host(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void make_philox_keys(uint64_t seed, PhiloxKeys* out) {
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    for (int r = 0; r < 10; ++r) {
+        out->rk4[2 * r] = key[0] + (uint32_t)r * 0x9E3779B9u;
+        out->rk4[2 * r + 1] = key[1] + (uint32_t)r * 0xBB67AE85u;
+    }
+    uint32_t* streams[3] = {out->winit, out->noise, out->action};
+    const uint32_t tags[3] = {kStreamWaveInit, kStreamWaveNoise, kStreamAction};
+    for (int s = 0; s < 3; ++s) {
+        const uint32_t ctr[4] = {tags[s], 0u, 0u, 0u};
+        uint32_t o[4];
+        philox4x32_10_host(ctr, key, o);
+        for (int r = 0; r < 10; ++r) streams[s][r] = o[0] + (uint32_t)r * 0x9E3779B9u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -12,12 +12,19 @@ namespace aqua {
 constexpr int kMaxThreads = 256;   // threads per CTA upper bound (launch bounds)
 constexpr int kStatSlots = 1024;   // per-CTA statistics slots (CTA b adds into slot b % kStatSlots)
 
-// Philox4x32-10 round keys: rk[2r] = k0 + r*0x9E3779B9, rk[2r+1] = k1 + r*0xBB67AE85 with
-// (k0, k1) = (seed lo, seed hi).  Computed once on the host so that in the kernels they are
-// constant-bank operands of the rounds' XORs.
+// Round keys of the draw streams, computed once on the host so that in the kernels they are
+// constant-bank operands of the rounds' XORs:
+//   rk4[2r], rk4[2r+1] = k0 + r*0x9E3779B9, k1 + r*0xBB67AE85  (Philox4x32-10, key = seed:
+//                        RESET stream, 4 words per sampling try)
+//   noise/winit/action[r] = key32(tag) + r*0x9E3779B9          (Philox2x32-10, per-step streams;
+//                        key32(tag) = Philox4x32-10(counter (tag,0,0,0), key seed).x)
 struct PhiloxKeys {
-    uint32_t rk[20];
+    uint32_t rk4[20];
+    uint32_t noise[10];
+    uint32_t winit[10];
+    uint32_t action[10];
 };
+void make_philox_keys(uint64_t seed, PhiloxKeys* out);
 
 // Everything a kernel needs to know about the world; travels by value in the parameter block.
 struct World {

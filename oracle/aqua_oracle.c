@@ -57,6 +57,28 @@ void aqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
 
+/* Philox2x32-10 (same paper): the per-step draws need two words only */
+void aqo_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], k = key;
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p = (uint64_t)0xD256D193u * c0;
+        uint32_t n0 = (uint32_t)(p >> 32) ^ k ^ c1;
+        c1 = (uint32_t)p;
+        c0 = n0;
+        k += 0x9E3779B9u;
+    }
+    out[0] = c0; out[1] = c1;
+}
+
+/* 32-bit key of a per-step stream, derived from the 64-bit seed */
+uint32_t aqo_key32(uint64_t seed, uint32_t tag) {
+    uint32_t ctr[4] = {tag, 0u, 0u, 0u};
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    uint32_t out[4];
+    aqo_philox4x32_10(ctr, key, out);
+    return out[0];
+}
+
 /* 24 high bits -> float32 in [0, 1); exactly representable */
 float aqo_u01(uint32_t u) { return (float)(u >> 8) * 0x1p-24f; }
 
@@ -91,38 +113,64 @@ void aqo_draw_reset_sample(uint64_t seed, uint32_t env_id, uint32_t episode, uin
 }
 
 /* `wave_space.sample()` (aqua.py:124): U[-0.05, 0.05)^2 * has_waves */
-void aqo_draw_wave_init(uint64_t seed, uint32_t env_id, uint32_t episode, int waves,
-                        double out2[2]) {
-    if (!waves) { out2[0] = 0.0; out2[1] = 0.0; return; }
-    uint32_t r[4];
-    philox_env(seed, env_id, episode, 0u, AQO_STREAM_WAVE_INIT, r);
+static void wave_init_k(uint32_t key, uint32_t env_id, uint32_t episode, double out2[2]) {
+    uint32_t ctr[2] = {env_id, episode};
+    uint32_t r[2];
+    aqo_philox2x32_10(ctr, key, r);
     out2[0] = (double)fmaf(aqo_u01(r[0]), 0.1f, -0.05f);
     out2[1] = (double)fmaf(aqo_u01(r[1]), 0.1f, -0.05f);
 }
+void aqo_draw_wave_init(uint64_t seed, uint32_t env_id, uint32_t episode, int waves,
+                        double out2[2]) {
+    if (!waves) { out2[0] = 0.0; out2[1] = 0.0; return; }
+    wave_init_k(aqo_key32(seed, AQO_STREAM_WAVE_INIT), env_id, episode, out2);
+}
 
 /* `np.random.uniform(-var, var, 2)` (aqua.py:188); t = env time BEFORE the step's
- * increment (0 for the first step of an episode); one Philox call serves 2 steps */
+ * increment (0 for the first step of an episode): Philox2x32 keyed by the packed
+ * (episode << 11 | t) word */
+static void wave_noise_k(uint32_t key, uint32_t env_id, uint32_t episode, uint32_t t, double out2[2]) {
+    if (t > 2047u) t = 2047u;
+    uint32_t ctr[2] = {env_id, (episode << 11) | t};
+    uint32_t r[2];
+    aqo_philox2x32_10(ctr, key, r);
+    out2[0] = (double)fmaf(aqo_u01(r[0]), 0.002f, -0.001f);
+    out2[1] = (double)fmaf(aqo_u01(r[1]), 0.002f, -0.001f);
+}
 void aqo_draw_wave_noise(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t t, int waves,
                          double out2[2]) {
     if (!waves) { out2[0] = 0.0; out2[1] = 0.0; return; }
-    uint32_t r[4];
-    philox_env(seed, env_id, episode, t >> 1, AQO_STREAM_WAVE_NOISE, r);
-    uint32_t a = (t & 1u) ? r[2] : r[0], b = (t & 1u) ? r[3] : r[1];
-    out2[0] = (double)fmaf(aqo_u01(a), 0.002f, -0.001f);
-    out2[1] = (double)fmaf(aqo_u01(b), 0.002f, -0.001f);
+    wave_noise_k(aqo_key32(seed, AQO_STREAM_WAVE_NOISE), env_id, episode, t, out2);
+}
+
+/* derived keys of the per-step streams; call after setting w->seed */
+void aqo_world_init_keys(aqo_world* w) {
+    w->key_winit = aqo_key32(w->seed, AQO_STREAM_WAVE_INIT);
+    w->key_noise = aqo_key32(w->seed, AQO_STREAM_WAVE_NOISE);
+    w->key_action = aqo_key32(w->seed, AQO_STREAM_ACTION);
 }
 
 /* synthetic random policy: `action_space.sample()` stand-in (test_random.py:20) */
-uint32_t aqo_draw_action_discrete(uint64_t seed, uint32_t env_id, uint64_t step) {
-    uint32_t r[4];
-    philox_env(seed, env_id, (uint32_t)step, (uint32_t)(step >> 32), AQO_STREAM_ACTION, r);
+static void action_words_k(uint32_t key_action, uint32_t env_id, uint64_t step, uint32_t r[2]) {
+    uint32_t ctr[2] = {env_id, (uint32_t)step};
+    aqo_philox2x32_10(ctr, key_action + (uint32_t)(step >> 32), r);
+}
+static uint32_t action_discrete_k(uint32_t key_action, uint32_t env_id, uint64_t step) {
+    uint32_t r[2];
+    action_words_k(key_action, env_id, step, r);
     return (uint32_t)(((uint64_t)r[0] * 3u) >> 32);
 }
-void aqo_draw_action_continuous(uint64_t seed, uint32_t env_id, uint64_t step, float out2[2]) {
-    uint32_t r[4];
-    philox_env(seed, env_id, (uint32_t)step, (uint32_t)(step >> 32), AQO_STREAM_ACTION, r);
+static void action_continuous_k(uint32_t key_action, uint32_t env_id, uint64_t step, float out2[2]) {
+    uint32_t r[2];
+    action_words_k(key_action, env_id, step, r);
     out2[0] = fmaf(aqo_u01(r[0]), 0.3f, 0.2f);
     out2[1] = fmaf(aqo_u01(r[1]), 0.3f, 0.2f);
+}
+uint32_t aqo_draw_action_discrete(uint64_t seed, uint32_t env_id, uint64_t step) {
+    return action_discrete_k(aqo_key32(seed, AQO_STREAM_ACTION), env_id, step);
+}
+void aqo_draw_action_continuous(uint64_t seed, uint32_t env_id, uint64_t step, float out2[2]) {
+    action_continuous_k(aqo_key32(seed, AQO_STREAM_ACTION), env_id, step, out2);
 }
 
 /* ---------------- reference primitives ---------------- */
@@ -233,7 +281,8 @@ int aqo_reset_env(const aqo_world* w, aqo_state* s, int64_t i) {
     }
     /* velocities: aqua.py:120-125 */
     double wv[2];
-    aqo_draw_wave_init(w->seed, env_id, ep, w->waves, wv);
+    if (w->waves) wave_init_k(w->key_winit, env_id, ep, wv);
+    else { wv[0] = 0.0; wv[1] = 0.0; }
     s->wx[i] = wv[0];
     s->wy[i] = wv[1];
     s->time[i] = 0;
@@ -294,7 +343,8 @@ uint32_t aqo_step_env(const aqo_world* w, aqo_state* s, int64_t i, const double*
     /* waves: aqua.py:188-191 (after the move) */
     double nz[2];
     if (noise) { nz[0] = noise[0]; nz[1] = noise[1]; }
-    else aqo_draw_wave_noise(w->seed, env_id, s->episode[i], (uint32_t)t_before, w->waves, nz);
+    else if (!w->waves) { nz[0] = 0.0; nz[1] = 0.0; }
+    else wave_noise_k(w->key_noise, env_id, s->episode[i], (uint32_t)t_before, nz);
     (void)WAVE_SPEED_VARIANCE;
     double wmin = -WAVE_MAX_SPEED * has_waves, wmax = WAVE_MAX_SPEED * has_waves;
     s->wx[i] = clipd(s->wx[i] + nz[0], wmin, wmax);
@@ -427,11 +477,11 @@ static void rollout_range(void* p, int64_t lo, int64_t hi, int tid) {
             double act[2], rew;
             if (w->continuous) {
                 float t2[2];
-                aqo_draw_action_continuous(w->seed, env_id, a->step0 + (uint64_t)k, t2);
+                action_continuous_k(w->key_action, env_id, a->step0 + (uint64_t)k, t2);
                 act[0] = t2[0];
                 act[1] = t2[1];
             } else {
-                act[0] = (double)aqo_draw_action_discrete(w->seed, env_id, a->step0 + (uint64_t)k);
+                act[0] = (double)action_discrete_k(w->key_action, env_id, a->step0 + (uint64_t)k);
                 act[1] = 0.0;
             }
             uint32_t f = aqo_step_env(w, a->s, i, act, NULL, &rew, NULL);

@@ -36,9 +36,9 @@ extern "C" {
 
 /* Philox stream tags (counter word 3) */
 #define AQO_STREAM_RESET 1u      /* reset try n -> (x, y, theta | gx, gy) */
-#define AQO_STREAM_WAVE_INIT 2u  /* wave speed at reset */
-#define AQO_STREAM_WAVE_NOISE 3u /* wave-speed increment, two steps per call */
-#define AQO_STREAM_ACTION 4u     /* synthetic random actions (bench / rollout) */
+#define AQO_STREAM_WAVE_INIT 2u  /* wave speed at reset (Philox2x32) */
+#define AQO_STREAM_WAVE_NOISE 3u /* wave-speed increment of one step (Philox2x32) */
+#define AQO_STREAM_ACTION 4u     /* synthetic random actions (bench / rollout; Philox2x32) */
 
 #define AQO_RESET_MAX_TRIES 4096u
 /* the kernels pack (episode << 11 | time) in one 32-bit word: episode is 21 bits and
@@ -52,7 +52,9 @@ typedef struct {
     int32_t random_boat; /* aqua.py:16 */
     int32_t random_goal; /* aqua.py:17 */
     int32_t n_obstacles;
-    int32_t _pad;
+    uint32_t key_winit;  /* derived stream keys: aqo_world_init_keys() */
+    uint32_t key_noise;
+    uint32_t key_action;
     uint64_t seed;
     uint64_t env_id_base;
     /* obstacle k: {cx, cy, type (0 = circle, 1 = rectangle), a, b};
@@ -70,8 +72,13 @@ typedef struct {
     uint32_t *episode;     /* episode counter (key of the draw streams) */
 } aqo_state;
 
+/* fills key_noise / key_action from seed; call once after setting the fields */
+void aqo_world_init_keys(aqo_world* w);
+
 /* ---- draw streams (shared spec with the CUDA kernels) ---- */
 void aqo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+void aqo_philox2x32_10(const uint32_t ctr[2], uint32_t key, uint32_t out[2]);
+uint32_t aqo_key32(uint64_t seed, uint32_t tag);
 float aqo_u01(uint32_t u);
 void aqo_draw_reset_sample(uint64_t seed, uint32_t env_id, uint32_t episode, uint32_t n,
                            double out5[5]);

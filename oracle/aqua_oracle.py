@@ -20,8 +20,8 @@ EPISODE_NONE = 0x1FFFFF
 
 class _World(C.Structure):
     _fields_ = [("continuous", C.c_int32), ("waves", C.c_int32), ("random_boat", C.c_int32),
-                ("random_goal", C.c_int32), ("n_obstacles", C.c_int32), ("_pad", C.c_int32),
-                ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
+                ("random_goal", C.c_int32), ("n_obstacles", C.c_int32), ("key_winit", C.c_uint32),
+                ("key_noise", C.c_uint32), ("key_action", C.c_uint32), ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
                 ("obstacles", C.c_double * (MAX_OBSTACLES * 5))]
 
 
@@ -54,6 +54,10 @@ def lib():
         dp, u8p, i32p, f32p = (C.POINTER(C.c_double), C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                                C.POINTER(C.c_float))
         L.aqo_philox4x32_10.argtypes = [C.POINTER(C.c_uint32)] * 3
+        L.aqo_philox2x32_10.argtypes = [C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32)]
+        L.aqo_key32.restype = C.c_uint32
+        L.aqo_key32.argtypes = [C.c_uint64, C.c_uint32]
+        L.aqo_world_init_keys.argtypes = [C.POINTER(_World)]
         L.aqo_u01.restype = C.c_float
         L.aqo_u01.argtypes = [C.c_uint32]
         L.aqo_draw_reset_sample.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, dp]
@@ -114,6 +118,7 @@ class OracleVecEnv(object):
         w.random_boat, w.random_goal = int(random_boat), int(random_goal)
         w.n_obstacles = tab.shape[0]
         w.seed, w.env_id_base = int(seed), int(env_id_base)
+        self.L.aqo_world_init_keys(C.byref(w))
         for i, v in enumerate(tab.reshape(-1)):
             w.obstacles[i] = v
         self.world = w

@@ -5,12 +5,17 @@ generator (`gen_golden.py`) does not depend on the code it pins; the two are
 cross-checked in tests/test_philox.py.  The layout is specified in DESIGN.md
 section 4:
 
-    key     = (seed & 0xffffffff, seed >> 32)
-    counter = (global_env_id, c1, c2, stream_tag)
-      RESET      c1 = episode, c2 = try index n   -> one `observation_space.sample()`
-      WAVE_INIT  c1 = episode, c2 = 0             -> `wave_space.sample()`
-      WAVE_NOISE c1 = episode, c2 = t >> 1        -> two steps of `np.random.uniform(-var, var, 2)`
-      ACTION     c1 = step lo, c2 = step hi       -> synthetic random policy
+    Rare draws (4 words each): Philox4x32-10
+      key     = (seed & 0xffffffff, seed >> 32)
+      counter = (global_env_id, c1, c2, stream_tag)
+        RESET      c1 = episode, c2 = try index n   -> one `observation_space.sample()`
+    Per-step draws (2 words each): Philox2x32-10
+      key32(tag) = Philox4x32-10(counter = (tag, 0, 0, 0), key as above)[0]
+        WAVE_INIT  counter = (global_env_id, episode), key = key32(2)  -> `wave_space.sample()`
+        WAVE_NOISE counter = (global_env_id, (episode << 11) | t), key = key32(3)
+                   -> `np.random.uniform(-var, var, 2)` of the step taken at env time t
+        ACTION     counter = (global_env_id, step lo), key = key32(4) + step hi
+                   -> synthetic random policy
 
 All values are computed in float32 (single fused multiply-add where noted) and
 then widened to float64, so a float32 kernel, a float64 kernel and the float64
@@ -39,6 +44,27 @@ def philox4x32_10(ctr, key):
         k0 = (k0 + W0) & MASK32
         k1 = (k1 + W1) & MASK32
     return c0, c1, c2, c3
+
+
+M2 = 0xD256D193
+
+
+def philox2x32_10(ctr, key):
+    c0, c1 = (int(v) & MASK32 for v in ctr)
+    k = int(key) & MASK32
+    for _ in range(10):
+        p = M2 * c0
+        c0, c1 = ((p >> 32) ^ k ^ c1) & MASK32, p & MASK32
+        k = (k + W0) & MASK32
+    return c0, c1
+
+
+def key32(seed, tag):
+    """32-bit key of a per-step stream, derived from the 64-bit seed."""
+    return philox4x32_10((tag, 0, 0, 0), (seed & MASK32, (seed >> 32) & MASK32))[0]
+
+
+TIME_BITS = 11
 
 
 def _philox_env(seed, env_id, c1, c2, tag):
@@ -71,7 +97,7 @@ def reset_sample(seed, env_id, episode, n):
 def wave_init(seed, env_id, episode, waves=True):
     if not waves:
         return np.zeros(2)
-    r = _philox_env(seed, env_id, episode, 0, STREAM_WAVE_INIT)
+    r = philox2x32_10((env_id, episode), key32(seed, STREAM_WAVE_INIT))
     return np.array([_fmaf(u01(r[0]), 0.1, -0.05), _fmaf(u01(r[1]), 0.1, -0.05)],
                     dtype=np.float64)
 
@@ -80,17 +106,22 @@ def wave_noise(seed, env_id, episode, t, waves=True):
     """t = env time before the step's increment."""
     if not waves:
         return np.zeros(2)
-    r = _philox_env(seed, env_id, episode, t >> 1, STREAM_WAVE_NOISE)
-    a, b = (r[2], r[3]) if (t & 1) else (r[0], r[1])
+    tw = ((episode << TIME_BITS) | min(t, (1 << TIME_BITS) - 1)) & MASK32
+    a, b = philox2x32_10((env_id, tw), key32(seed, STREAM_WAVE_NOISE))
     return np.array([_fmaf(u01(a), 0.002, -0.001), _fmaf(u01(b), 0.002, -0.001)],
                     dtype=np.float64)
 
 
+def _action_words(seed, env_id, step):
+    key = (key32(seed, STREAM_ACTION) + ((step >> 32) & MASK32)) & MASK32
+    return philox2x32_10((env_id, step & MASK32), key)
+
+
 def action_discrete(seed, env_id, step):
-    r = _philox_env(seed, env_id, step & MASK32, (step >> 32) & MASK32, STREAM_ACTION)
+    r = _action_words(seed, env_id, step)
     return (r[0] * 3) >> 32
 
 
 def action_continuous(seed, env_id, step):
-    r = _philox_env(seed, env_id, step & MASK32, (step >> 32) & MASK32, STREAM_ACTION)
+    r = _action_words(seed, env_id, step)
     return np.array([_fmaf(u01(r[0]), 0.3, 0.2), _fmaf(u01(r[1]), 0.3, 0.2)], dtype=np.float32)

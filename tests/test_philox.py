@@ -15,6 +15,25 @@ KATS = [
 ]
 
 
+KATS_2X32 = [  # Random123 kat_vectors, philox2x32 10
+    ((0, 0), 0, (0xff1dae59, 0x6cd10df2)),
+    ((0xffffffff, 0xffffffff), 0xffffffff, (0x2c3f628b, 0xab4fd7ad)),
+    ((0x243f6a88, 0x85a308d3), 0x13198a2e, (0xdd7ce038, 0xf62a4c12)),
+]
+
+
+def test_philox2x32_kat():
+    L = ao.lib()
+    for ctr, key, want in KATS_2X32:
+        assert draws.philox2x32_10(ctr, key) == want
+        c = (C.c_uint32 * 2)(*ctr)
+        o = (C.c_uint32 * 2)()
+        L.aqo_philox2x32_10(c, key, o)
+        assert tuple(o) == want
+    for seed, tag in [(0, 3), (2 ** 63 + 12345, 4), (77, 3)]:
+        assert L.aqo_key32(seed, tag) == draws.key32(seed, tag)
+
+
 def _c_philox(ctr, key):
     c = (C.c_uint32 * 4)(*ctr)
     k = (C.c_uint32 * 2)(*key)
