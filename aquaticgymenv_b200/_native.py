@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libaquagym.so")
+# AQUAGYM_LIB selects another build of the same library (tuning variants, tools/tune.py)
+LIB_PATH = os.environ.get("AQUAGYM_LIB") or os.path.join(_HERE, "libaquagym.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aquagym.h")
 
 ABI_VERSION = 1

@@ -102,7 +102,7 @@ aqua::StepArgs base_args(const aqua_env* env) {
 // Launch geometry of the step kernel for `n` envs.  Small slabs use small CTAs so that every SM
 // gets work; large slabs use a persistent grid of (resident CTAs per SM) x (SM count) CTAs.
 int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aqua::LaunchGeom* g) {
-    const int V = env->cfg.precision == AQUA_F64 ? 2 : 4;
+    const int V = env->cfg.precision == AQUA_F64 ? 2 : aqua::envs_per_thread_f32();
     int threads = 256;
     while (threads > 64 && n < (int64_t)threads * V * env->sm_count * 2) threads >>= 1;
     const int ti = threads == 256 ? 2 : (threads == 128 ? 1 : 0);
@@ -255,6 +255,15 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.grid = nullptr;
     w.k_obst = cfg->n_obstacles;
     w.k_circ = k_circ;
+    {
+        double reach2 = 6.25;  // rectangles: (2.5)^2
+        for (int k = 0; k < cfg->n_obstacles; ++k)
+            if (cfg->obstacles[5 * k + 2] == 0.0) {
+                const double r = cfg->obstacles[5 * k + 3] + 2.5;
+                reach2 = std::max(reach2, r * r);
+            }
+        w.reset_band = (float)(1e-4 * reach2);
+    }
     w.waves = cfg->waves != 0;
     w.random_boat = cfg->random_boat != 0;
     w.random_goal = cfg->random_goal != 0;

@@ -101,9 +101,12 @@ __device__ __forceinline__ uint2 draw_action_words(const PhiloxKeys& keys, uint3
 // ------------------------------------------------------------------------------------------
 // precision traits
 // ------------------------------------------------------------------------------------------
+#ifndef AQUA_VF32
+#define AQUA_VF32 4
+#endif
 template <typename R> struct Prec;
 template <> struct Prec<float> {
-    static constexpr int V = 4;  // envs per thread: 16-byte plane loads
+    static constexpr int V = AQUA_VF32;  // envs per thread: 16-byte plane loads at V = 4
     // sin and cos of a heading: |a| <= pi + 0.06, so two quadrant-reduction terms suffice and no
     // large-argument path is needed.  Cephes single-precision minimax kernels on [-pi/4, pi/4]
     // (about 1 ulp); quadrant fix-up on the sign bits.
@@ -253,49 +256,33 @@ __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t e
 // a rejection loop run by the owning lane alone would serialise the whole warp behind it.  The
 // step kernels therefore queue finished envs per CTA and hand each one to a group of
 // kCoopLanes lanes that evaluates kCoopLanes consecutive tries of the reference's sampling
-// sequence at once: lane l of round q tests try n = 8q + l (one Philox call yields both the goal
+// sequence at once: lane l of round q tests try n = 4q + l (one Philox call yields both the goal
 // candidate, words z/w, and the boat candidate, words x/y/z of `observation_space.sample()`).
 // The accepted goal is the first passing try g, the accepted boat the first passing try > g
-// (aqua.py:102-115): exactly the sequential result, found in one round almost always.
+// (aqua.py:102-115): exactly the sequential result, found in the first round about 19 times in 20.
 //
 // Accept/reject decisions are those of float64 arithmetic on the float32 draws: the float table
 // is used with a guard band and anything inside the band is re-evaluated in float64.
 // ------------------------------------------------------------------------------------------
-constexpr int kCoopLanes = 8;
+constexpr int kCoopLanes = 4;
 
 __device__ __forceinline__ bool outside_border_f(float x, float y) {
     // (double)x - 2.5 and (double)x + 2.5 are exact for a float x in [0, 128): same predicate
     return !((x >= 2.5f) & (x <= 97.5f) & (y >= 2.5f) & (y <= 97.5f));
 }
 
+// `band` = guard band of the float32 clearance (1e-4 x the largest squared reach of the table,
+// far above its rounding error): outside the band the float32 sign is the float64 sign.
 template <typename R>
 __device__ __forceinline__ bool reset_blocked(const ObstacleTable<R>& tab, const double* __restrict__ tab64,
-                                              int k_circ, int k_obst, float x, float y) {
-    if constexpr (sizeof(R) == 8) {
-        const double px[1] = {(double)x}, py[1] = {(double)y};
-        double clr[1] = {(double)kClearFar};
-        obstacle_clearance<double, 1>(tab, k_circ, k_obst, px, py, clr);
-        return clr[0] <= 0.0;
-    } else {
-        bool hit = false, unsure = false;
-        for (int k = 0; k < k_circ; ++k) {
-            const ObstacleBox<float> o = tab.box[k];
-            const float ddx = x - o.cx, ddy = y - o.cy;
-            const float sd = fmaf(ddx, ddx, ddy * ddy) - o.a;
-            hit |= sd <= 0.f;
-            unsure |= fabsf(sd) <= 1e-4f * o.a;
-        }
-        for (int k = k_circ; k < k_obst; ++k) {
-            const ObstacleBox<float> o = tab.box[k];
-            const float ddx = fmaxf(fabsf(x - o.cx) - o.a, 0.f);
-            const float ddy = fmaxf(fabsf(y - o.cy) - o.b, 0.f);
-            const float sd = fmaf(ddx, ddx, ddy * ddy) - (float)kRectR2;
-            hit |= sd <= 0.f;
-            unsure |= fabsf(sd) <= 1e-4f * (float)kRectR2;
-        }
-        if (unsure) hit = hits_obstacle_g(tab64, k_obst, (double)x, (double)y);
-        return hit;
+                                              int k_circ, int k_obst, float band, float x, float y) {
+    const R px[1] = {(R)x}, py[1] = {(R)y};
+    R clr[1] = {R(kClearFar)};
+    obstacle_clearance<R, 1>(tab, k_circ, k_obst, px, py, clr);
+    if constexpr (sizeof(R) == 4) {
+        if (fabsf(clr[0]) <= band) return hits_obstacle_g(tab64, k_obst, (double)x, (double)y);
     }
+    return clr[0] <= R(0);
 }
 
 // aqua.py:421-422 at reset: goal and boat radius 2.5 each
@@ -314,12 +301,13 @@ struct CoopResetResult {
 };
 
 // Must be called by all 32 lanes of a warp (it uses full-mask ballots and shuffles).  Lanes
-// [8s, 8s+8) serve one env: `valid`, `env_id`, `ep` (the NEW episode index) are group-uniform.
+// [4s, 4s+4) serve one env: `valid`, `env_id`, `ep` (the NEW episode index) are group-uniform.
 // The result is returned to every lane of the group.
 template <typename R>
 __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, const ObstacleTable<R>& tab,
                                                       const double* __restrict__ tab64, int k_circ, int k_obst,
-                                                      WorldFlags wf, bool valid, uint32_t env_id, uint32_t ep) {
+                                                      float band, WorldFlags wf, bool valid, uint32_t env_id,
+                                                      uint32_t ep) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned sub = lane & ~(unsigned)(kCoopLanes - 1);  // first lane of this group
@@ -338,7 +326,7 @@ __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, co
         const float cgx = draw_pos(r.z), cgy = draw_pos(r.w);
         bool ok_g = false;
         if (!goal_done)
-            ok_g = force || !(outside_border_f(cgx, cgy) || reset_blocked<R>(tab, tab64, k_circ, k_obst, cgx, cgy));
+            ok_g = force || !(outside_border_f(cgx, cgy) || reset_blocked<R>(tab, tab64, k_circ, k_obst, band, cgx, cgy));
         const unsigned mg = (__ballot_sync(full, ok_g) >> sub) & ((1u << kCoopLanes) - 1u);
         unsigned first_boat = goal_done ? 0u : (unsigned)kCoopLanes;  // first lane whose try follows the goal's
         const unsigned lg = mg ? (unsigned)(__ffs(mg) - 1) : 0u;
@@ -354,7 +342,7 @@ __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, co
         bool ok_b = false;
         if (goal_done && !boat_done && l >= first_boat)
             ok_b = force || !(reset_reached<R>(o.gx, o.gy, cbx, cby) || outside_border_f(cbx, cby) ||
-                              reset_blocked<R>(tab, tab64, k_circ, k_obst, cbx, cby));
+                              reset_blocked<R>(tab, tab64, k_circ, k_obst, band, cbx, cby));
         const unsigned mb = (__ballot_sync(full, ok_b) >> sub) & ((1u << kCoopLanes) - 1u);
         const unsigned lb = mb ? (unsigned)(__ffs(mb) - 1) : 0u;
         const float sbx = __shfl_sync(full, cbx, sub + lb), sby = __shfl_sync(full, cby, sub + lb);

@@ -199,41 +199,55 @@ __device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g
 }
 
 // ------------------------------------------------------------------------------------------
-// Phase B of a step, per warp: the warp resets the envs its lanes finished in this tile,
-// kCoopLanes lanes per env (no CTA barrier).  `fw` holds the flags of the lane's V envs, one
-// byte each (0 for padding / inactive lanes); the owner has already stored the terminal time
-// word, the fresh episode goes straight to the state planes (aqua.py:100-126).
-// Must be called by all 32 lanes.
+// Phase B of a step, per warp: the warp resets the envs its lanes finished, kCoopLanes lanes
+// per env, 32 / kCoopLanes envs per pass (no CTA barrier).  Finished envs are first queued per
+// warp (env index relative to env_begin); the step kernel drains the queue only in full passes
+// and flushes the remainder before it exits, so that every pass runs with all groups busy.
+// The owner has already stored the terminal state and time word; the fresh episode goes
+// straight to the state planes (aqua.py:100-126).  Both functions are warp-collective.
 // ------------------------------------------------------------------------------------------
-template <typename R, int V>
-__device__ __forceinline__ void warp_reset(const StepArgs& p, const ObstacleTable<R>& tab, uint8_t* wq,
-                                           uint32_t fw, int64_t warp_base) {
-    constexpr int kGroups = 32 / kCoopLanes;
+constexpr int kResetGroups = 32 / kCoopLanes;
+template <int V> struct WarpResetQueue {
+    uint32_t rel[32 * V + kResetGroups];
+};
+
+// fw: flags of the lane's V envs, one byte each (0 for padding / inactive lanes); rel_base: index
+// of the lane's first env relative to env_begin.  Returns the new queue length.
+template <int V>
+__device__ __forceinline__ int reset_queue_push(uint32_t* wq, int n, uint32_t fw, uint32_t rel_base) {
     const unsigned full = 0xffffffffu;
-    const unsigned lane = threadIdx.x & 31u;
-    const unsigned lt = (1u << lane) - 1u;
-    // enumerate the finished envs of the warp into its queue (tile-local index lane * V + j)
-    int n = 0;
+    const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const bool d = ((fw >> (8 * j)) & 1u) != 0u;
         const unsigned mj = __ballot_sync(full, d);
-        if (d) wq[n + __popc(mj & lt)] = (uint8_t)(lane * V + j);
+        if (d) wq[n + __popc(mj & lt)] = rel_base + (uint32_t)j;
         n += __popc(mj);
     }
-    __syncwarp();
+    return n;
+}
+
+// Resets queued envs in passes of kResetGroups, from the tail, while at least `min_batch` are
+// queued (min_batch = kResetGroups: full passes only; 1: flush).  Returns the new queue length.
+template <typename R>
+__device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const ObstacleTable<R>& tab,
+                                                 const uint32_t* wq, int n, int min_batch) {
+    const unsigned lane = threadIdx.x & 31u;
     const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
     uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
     const int grp = (int)(lane / kCoopLanes);
     const bool leader = (lane % kCoopLanes) == 0u;
-    for (int q0 = 0; q0 < n; q0 += kGroups) {
-        const int q = q0 + grp;
-        const bool valid = q < n;
-        const int64_t i = warp_base + (valid ? (int64_t)wq[q] : 0);
+    __syncwarp();  // queue entries and the owners' stores are visible to the whole warp
+    while (n >= min_batch && n > 0) {
+        const int take = min(n, kResetGroups);
+        const int first = n - take;
+        const bool valid = grp < take;
+        const int64_t i = p.env_begin + (int64_t)(valid ? wq[first + grp] : 0u);
         const uint32_t tw = valid ? ptw[i] : 0u;
         const uint32_t ep = ((tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
         const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
-        const CoopResetResult rr = coop_reset<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst, wf, valid, env_id, ep);
+        const CoopResetResult rr = coop_reset<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
+                                                 p.w.reset_band, wf, valid, env_id, ep);
         if (valid && leader) {
             plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
             plane<R>(p.planes, p.ld, AQUA_PLANE_Y)[i] = (R)rr.y;
@@ -244,8 +258,10 @@ __device__ __forceinline__ void warp_reset(const StepArgs& p, const ObstacleTabl
             plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_Y)[i] = (R)rr.wy;
             ptw[i] = ep << AQUA_TIME_BITS;
         }
+        n = first;
     }
     __syncwarp();
+    return n;
 }
 
 template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8_t, V>& f, int nvalid) {
@@ -260,11 +276,11 @@ template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8
 // env finishes and autoreset is on)
 // ------------------------------------------------------------------------------------------
 template <typename R, int ACT, bool INJECT>
-__global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_constant__ StepArgs p) {
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
     constexpr int V = Prec<R>::V;
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
-    __shared__ uint8_t s_wq[kMaxThreads / 32][32 * V];
+    __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     stage_table<R>(tab, p.w.tab, p.w.k_obst);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
@@ -285,6 +301,8 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
     const int64_t warp_off = (int64_t)(threadIdx.x & ~31u) * V;  // first env of this warp within the tile
 
     ThreadStats st;
+    uint32_t* const wq = s_wq[threadIdx.x >> 5].rel;
+    int n_queued = 0;  // warp-uniform
     // the loop is uniform over each warp (phase B is warp-collective)
     for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base + warp_off < p.env_end;
          tile_base += (int64_t)gridDim.x * tile_envs) {
@@ -361,9 +379,12 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
                     if (j < nvalid) { rew[j] = vrew.v[j]; fl[j] = vfl.v[j]; }
             }
         }
-        if (autoreset && __any_sync(0xffffffffu, fw != 0u))
-            warp_reset<R, V>(p, tab, s_wq[threadIdx.x >> 5], fw, tile_base + warp_off);
+        if (autoreset && __any_sync(0xffffffffu, fw != 0u)) {
+            n_queued = reset_queue_push<V>(wq, n_queued, fw, (uint32_t)(base - p.env_begin));
+            if (n_queued >= kResetGroups) n_queued = reset_queue_drain<R>(p, tab, wq, n_queued, kResetGroups);
+        }
     }
+    if (autoreset) reset_queue_drain<R>(p, tab, wq, n_queued, 1);  // flush the remainder
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
 }
@@ -373,11 +394,11 @@ __global__ void __launch_bounds__(kMaxThreads, 2) step_kernel(const __grid_const
 // state stays in registers between steps, per-step reward/flags are folded into the statistics
 // ------------------------------------------------------------------------------------------
 template <typename R, bool CONTINUOUS>
-__global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_constant__ StepArgs p) {
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const __grid_constant__ StepArgs p) {
     constexpr int V = Prec<R>::V;
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
-    __shared__ uint8_t s_wq[kMaxThreads / 32][32 * V];
+    __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     stage_table<R>(tab, p.w.tab, p.w.k_obst);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
@@ -454,7 +475,9 @@ __global__ void __launch_bounds__(kMaxThreads, 2) rollout_kernel(const __grid_co
                 }
             }
             if (__any_sync(0xffffffffu, fw != 0u)) {
-                warp_reset<R, V>(p, tab, s_wq[threadIdx.x >> 5], fw, tile_base + warp_off);
+                uint32_t* const wq = s_wq[threadIdx.x >> 5].rel;
+                const int n_queued = reset_queue_push<V>(wq, 0, fw, (uint32_t)(base - p.env_begin));
+                reset_queue_drain<R>(p, tab, wq, n_queued, 1);  // the next step needs the fresh state
                 if (fw != 0u) {  // pick the fresh episode up from the planes
 #pragma unroll
                     for (int j = 0; j < V; ++j)
@@ -750,6 +773,8 @@ void make_philox_keys(uint64_t seed, PhiloxKeys* out) {
 // ------------------------------------------------------------------------------------------
 // host-side obstacle tables (aqua.py:56-68, 373-390)
 // ------------------------------------------------------------------------------------------
+int envs_per_thread_f32() { return Prec<float>::V; }
+
 size_t obstacle_table_bytes(int precision) {
     return precision == AQUA_F64 ? sizeof(ObstacleTable<double>) : sizeof(ObstacleTable<float>);
 }

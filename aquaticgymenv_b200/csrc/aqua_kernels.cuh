@@ -10,6 +10,10 @@
 namespace aqua {
 
 constexpr int kMaxThreads = 256;   // threads per CTA upper bound (launch bounds)
+#ifndef AQUA_MIN_BLOCKS
+#define AQUA_MIN_BLOCKS 2
+#endif
+constexpr int kMinBlocks = AQUA_MIN_BLOCKS;  // resident CTAs per SM the kernels are compiled for
 constexpr int kStatSlots = 1024;   // per-CTA statistics slots (CTA b adds into slot b % kStatSlots)
 
 // Round keys of the draw streams, computed once on the host so that in the kernels they are
@@ -35,6 +39,7 @@ struct World {
     const uint32_t* grid;   // device uint32[kGridCells][2]: per-cell obstacle bit masks (or NULL)
     int32_t k_obst;
     int32_t k_circ;         // obstacles [0, k_circ) are circles, [k_circ, k_obst) rectangles
+    float reset_band;       // guard band of the float32 reset test, see reset_blocked()
     uint8_t waves, random_boat, random_goal, autoreset;
 };
 
@@ -74,6 +79,8 @@ cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int cle
 // occupancy of the step kernel for (precision, action dtype) at `threads` per CTA
 cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm);
 cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* blocks_per_sm);
+
+int envs_per_thread_f32();
 
 // host-side construction of the device obstacle tables; `out` sized for the precision
 size_t obstacle_table_bytes(int precision);

@@ -317,29 +317,31 @@ def run_b200(args):
     value = total_steps / elapsed_max
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory both ways) ----
+    e2e_value = None
     np_real = np.float32 if args.precision == "float32" else np.float64
     es = np.dtype(np_real).itemsize
-    h_act = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
-    h_act.copy_(pool[0].cpu())
-    h_obs = torch.empty(5, n_local, dtype=getattr(torch, args.precision), pin_memory=True)
-    h_rew = torch.empty(n_local, dtype=getattr(torch, args.precision), pin_memory=True)
-    h_flg = torch.empty(n_local, dtype=torch.uint8, pin_memory=True)
-    a_np, o_np, r_np, f_np = h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_flg.numpy()
-    for _ in range(3):
-        env.step_host(a_np, o_np, r_np, f_np)
-    torch.cuda.synchronize()
-    if dist_on:
-        dist.barrier()
-    te0 = time.perf_counter()
-    for _ in range(args.e2e_steps):
-        env.step_host(a_np, o_np, r_np, f_np)
-    torch.cuda.synchronize()
-    e2e_dt = time.perf_counter() - te0
-    ed = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
-    if dist_on:
-        dist.all_reduce(ed, op=dist.ReduceOp.MAX)
-    e2e_value = n_local * world * args.e2e_steps / float(ed.item())
-    assert int(f_np.max()) <= 9 and np.isfinite(r_np).all()
+    if args.e2e_steps > 0:
+        h_act = torch.empty(n_local, dtype=torch.int32, pin_memory=True)
+        h_act.copy_(pool[0].cpu())
+        h_obs = torch.empty(5, n_local, dtype=getattr(torch, args.precision), pin_memory=True)
+        h_rew = torch.empty(n_local, dtype=getattr(torch, args.precision), pin_memory=True)
+        h_flg = torch.empty(n_local, dtype=torch.uint8, pin_memory=True)
+        a_np, o_np, r_np, f_np = h_act.numpy(), h_obs.numpy(), h_rew.numpy(), h_flg.numpy()
+        for _ in range(3):
+            env.step_host(a_np, o_np, r_np, f_np)
+        torch.cuda.synchronize()
+        if dist_on:
+            dist.barrier()
+        te0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            env.step_host(a_np, o_np, r_np, f_np)
+        torch.cuda.synchronize()
+        e2e_dt = time.perf_counter() - te0
+        ed = torch.tensor([e2e_dt], dtype=torch.float64, device="cuda")
+        if dist_on:
+            dist.all_reduce(ed, op=dist.ReduceOp.MAX)
+        e2e_value = n_local * world * args.e2e_steps / float(ed.item())
+        assert int(f_np.max()) <= 9 and np.isfinite(r_np).all()
 
     peak_gbs, peak_src = peaks()
     bpe = BYTES_PER_STEP["discrete_i32"]
