@@ -269,6 +269,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.random_goal = cfg->random_goal != 0;
     w.autoreset = cfg->autoreset != 0;
 
+    AQ_CREATE(aqua::configure_kernels(cfg->precision));
     for (int ti = 0; ti < 3; ++ti) {
         const int threads = 64 << ti;
         for (int act = 0; act < 4; ++act) {

@@ -59,9 +59,15 @@ template <typename R> __device__ __forceinline__ uint32_t* plane_tw(void* planes
 // ------------------------------------------------------------------------------------------
 // action decode for V envs starting at absolute env index `base`
 // ------------------------------------------------------------------------------------------
-// discrete indices as 32-bit words; an int64 index outside 32 bits maps to 0xffffffff (invalid)
+// The actions of a thread's V envs as 32-bit words: discrete indices (an int64 index outside 32
+// bits maps to 0xffffffff, i.e. invalid) or the 2 V thrust floats.
+template <int ACT, int V> struct ActVals {
+    static constexpr int N = (ACT == AQUA_ACT_F32X2) ? 2 * V : V;
+    uint32_t w[N];
+};
+
 template <typename T, int V>
-__device__ __forceinline__ void load_discrete(const void* actions, int64_t base, int nvalid, uint32_t (&a)[V]) {
+__device__ __forceinline__ void fetch_discrete(const void* actions, int64_t base, int nvalid, uint32_t (&a)[V]) {
     const T* src = reinterpret_cast<const T*>(actions) + base;
     T raw[V];
     if (nvalid == V) {
@@ -83,43 +89,76 @@ __device__ __forceinline__ void load_discrete(const void* actions, int64_t base,
     }
 }
 
-template <typename R, int ACT, int V>
-__device__ __forceinline__ void load_thrusts(const void* actions, int64_t base, int nvalid, R (&tl)[V],
-                                             R (&tr)[V], uint32_t& bad) {
+// loads the actions of V envs starting at absolute env index `base` (padding lanes: valid values)
+template <int ACT, int V>
+__device__ __forceinline__ ActVals<ACT, V> fetch_actions(const void* actions, int64_t base, int nvalid) {
+    ActVals<ACT, V> out;
     if constexpr (ACT == AQUA_ACT_F32X2) {
-        float a[2 * V];
         const float* src = reinterpret_cast<const float*>(actions) + 2 * base;
         if (nvalid == V) {
             const Pack<float, 2 * V> pk = ldg_pack<float, 2 * V>(src);
 #pragma unroll
-            for (int j = 0; j < 2 * V; ++j) a[j] = pk.v[j];
+            for (int j = 0; j < 2 * V; ++j) out.w[j] = __float_as_uint(pk.v[j]);
         } else {
 #pragma unroll
-            for (int j = 0; j < 2 * V; ++j) a[j] = (j < 2 * nvalid) ? __ldg(src + j) : 0.5f;
+            for (int j = 0; j < 2 * V; ++j) out.w[j] = __float_as_uint((j < 2 * nvalid) ? __ldg(src + j) : 0.5f);
         }
+    } else if constexpr (ACT == AQUA_ACT_I32) {
+        fetch_discrete<int32_t, V>(actions, base, nvalid, out.w);
+    } else if constexpr (ACT == AQUA_ACT_I64) {
+        fetch_discrete<long long, V>(actions, base, nvalid, out.w);
+    } else {
+        fetch_discrete<uint8_t, V>(actions, base, nvalid, out.w);
+    }
+    return out;
+}
+
+template <typename R, int ACT, int V>
+__device__ __forceinline__ void decode_thrusts(const ActVals<ACT, V>& a, R (&tl)[V], R (&tr)[V], uint32_t& bad) {
+    if constexpr (ACT == AQUA_ACT_F32X2) {
 #pragma unroll
         for (int j = 0; j < V; ++j) {
             uint32_t b = 0;
-            decode_continuous<R>(a[2 * j], a[2 * j + 1], tl[j], tr[j], b);
+            decode_continuous<R>(__uint_as_float(a.w[2 * j]), __uint_as_float(a.w[2 * j + 1]), tl[j], tr[j], b);
             bad += b;  // padding lanes hold 0.5: never counted
         }
     } else {
-        uint32_t a[V];
-        if constexpr (ACT == AQUA_ACT_I32) load_discrete<int32_t, V>(actions, base, nvalid, a);
-        else if constexpr (ACT == AQUA_ACT_I64) load_discrete<long long, V>(actions, base, nvalid, a);
-        else load_discrete<uint8_t, V>(actions, base, nvalid, a);
         uint32_t worst = 0u;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            decode_discrete<R>(a[j], tl[j], tr[j]);
-            worst = max(worst, a[j]);
+            decode_discrete<R>(a.w[j], tl[j], tr[j]);
+            worst = max(worst, a.w[j]);
         }
         if (worst > 2u) {  // rare: an index outside {0, 1, 2} (padding lanes hold 2)
 #pragma unroll
-            for (int j = 0; j < V; ++j) bad += (a[j] > 2u) ? 1u : 0u;
+            for (int j = 0; j < V; ++j) bad += (a.w[j] > 2u) ? 1u : 0u;
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// asynchronous global -> shared copies (LDGSTS): each thread stages the 8 plane slices of ITS
+// next tile in its own shared-memory slots while it computes the current tile, so no barrier is
+// involved and the memory pipe stays busy through the compute phase
+// ------------------------------------------------------------------------------------------
+template <int BYTES> __device__ __forceinline__ void cp_async(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+    else {
+        static_assert(BYTES == 4, "cp.async moves 4, 8 or 16 bytes");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+    }
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+constexpr int kStageSlot = 16;                              // bytes per thread per plane per stage
+constexpr int kStages = 2;
+constexpr int kStageBytesPerThread = kStages * AQUA_N_PLANES * kStageSlot;  // 256
 
 // ------------------------------------------------------------------------------------------
 // per-thread episode statistics and their reduction
@@ -275,6 +314,8 @@ template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8
 // K1: env.step(action) for a range of envs -- aqua.py:135-213 (+ reset aqua.py:100-126 when an
 // env finishes and autoreset is on)
 // ------------------------------------------------------------------------------------------
+extern __shared__ __align__(16) unsigned char s_stage[];
+
 template <typename R, int ACT, bool INJECT>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
     constexpr int V = Prec<R>::V;
@@ -286,38 +327,82 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
     __syncthreads();
 
     const int64_t ld = p.ld;
-    R* const px_ = plane<R>(p.planes, ld, AQUA_PLANE_X);
-    R* const py_ = plane<R>(p.planes, ld, AQUA_PLANE_Y);
-    R* const pth_ = plane<R>(p.planes, ld, AQUA_PLANE_THETA);
-    R* const pwx_ = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X);
-    R* const pwy_ = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y);
-    R* const pgx_ = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X);
-    R* const pgy_ = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y);
+    R* const pl0 = reinterpret_cast<R*>(p.planes);
     uint32_t* const ptw_ = plane_tw<R>(p.planes, ld);
     const bool waves = p.w.waves != 0;
     const bool autoreset = p.w.autoreset != 0;
     const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
     const int64_t tile_envs = (int64_t)blockDim.x * V;
+    const int64_t stride = (int64_t)gridDim.x * tile_envs;
     const int64_t warp_off = (int64_t)(threadIdx.x & ~31u) * V;  // first env of this warp within the tile
+
+    // this thread's staging slots: [stage][plane][thread] x 16 bytes (conflict-free 16-byte LDS)
+    unsigned char* const my_stage = s_stage + (size_t)threadIdx.x * kStageSlot;
+    const size_t plane_pitch = (size_t)blockDim.x * kStageSlot;
+    auto slot = [&](int stage, int pl) { return my_stage + (size_t)(stage * AQUA_N_PLANES + pl) * plane_pitch; };
+    auto prefetch = [&](int stage, int64_t b) {  // the 8 plane slices of the V envs starting at b
+#pragma unroll
+        for (int pl = 0; pl < 7; ++pl) cp_async<(int)sizeof(R) * V>(slot(stage, pl), pl0 + (int64_t)pl * ld + b);
+        cp_async<4 * V>(slot(stage, AQUA_PLANE_TIME), ptw_ + b);
+    };
 
     ThreadStats st;
     uint32_t* const wq = s_wq[threadIdx.x >> 5].rel;
     int n_queued = 0;  // warp-uniform
+
+    int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs;
+    // prologue: stage the first tile (full threads only; a partial tail thread loads directly)
+    bool staged = false;
+    ActVals<ACT, V> act_next;
+    {
+        const int64_t b0 = tile_base + (int64_t)threadIdx.x * V;
+        if (b0 + V <= p.env_end) {
+            prefetch(0, b0);
+            act_next = fetch_actions<ACT, V>(p.actions, b0, V);
+            staged = true;
+        }
+        cp_async_commit();
+    }
     // the loop is uniform over each warp (phase B is warp-collective)
-    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base + warp_off < p.env_end;
-         tile_base += (int64_t)gridDim.x * tile_envs) {
+    for (int it = 0; tile_base + warp_off < p.env_end; tile_base += stride, ++it) {
         const int64_t base = tile_base + (int64_t)threadIdx.x * V;
         const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
+        // ---- stage the next tile of this thread while this one is computed ----
+        const int64_t next_base = base + stride;
+        const bool next_staged = next_base + V <= p.env_end;
+        const ActVals<ACT, V> act_cur = staged ? act_next : fetch_actions<ACT, V>(p.actions, base, nvalid);
+        if (next_staged) {
+            prefetch((it + 1) & 1, next_base);
+            act_next = fetch_actions<ACT, V>(p.actions, next_base, V);
+        }
+        cp_async_commit();
+        cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
         uint32_t fw = 0u;
         if (nvalid > 0) {
-            // ---- loads: one 16-byte access per plane (the planes are padded to AQUA_TILE) ----
-            const Pack<R, V> vx = ld_pack<R, V>(px_ + base), vy = ld_pack<R, V>(py_ + base);
-            const Pack<R, V> vth = ld_pack<R, V>(pth_ + base);
-            const Pack<R, V> vwx = ld_pack<R, V>(pwx_ + base), vwy = ld_pack<R, V>(pwy_ + base);
-            const Pack<R, V> vgx = ld_pack<R, V>(pgx_ + base), vgy = ld_pack<R, V>(pgy_ + base);
-            const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(ptw_ + base);
+            Pack<R, V> vx, vy, vth, vgx, vgy, vwx, vwy;
+            Pack<uint32_t, V> vtw;
+            if (staged) {
+                const int sg = it & 1;
+                vx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_X));
+                vy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_Y));
+                vth = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_THETA));
+                vgx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_GOAL_X));
+                vgy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_GOAL_Y));
+                vwx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_WAVE_X));
+                vwy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_WAVE_Y));
+                vtw = *reinterpret_cast<const Pack<uint32_t, V>*>(slot(sg, AQUA_PLANE_TIME));
+            } else {  // partial tail: the planes are padded to AQUA_TILE, full-width loads are in bounds
+                vx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_X * ld + base);
+                vy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_Y * ld + base);
+                vth = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_THETA * ld + base);
+                vgx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_GOAL_X * ld + base);
+                vgy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_GOAL_Y * ld + base);
+                vwx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_X * ld + base);
+                vwy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_Y * ld + base);
+                vtw = ld_pack<uint32_t, V>(ptw_ + base);
+            }
             R tl[V], tr[V];
-            load_thrusts<R, ACT, V>(p.actions, base, nvalid, tl, tr, st.bad);
+            decode_thrusts<R, ACT, V>(act_cur, tl, tr, st.bad);
 
             EnvState<R> e[V];
             MoveTmp<R> m[V];
@@ -362,11 +447,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
             st.add_flags(fw, nvalid);
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
-            st_pack<R, V>(px_ + base, ox);
-            st_pack<R, V>(py_ + base, oy);
-            st_pack<R, V>(pth_ + base, oth);
-            st_pack<R, V>(pwx_ + base, owx);
-            st_pack<R, V>(pwy_ + base, owy);
+            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_X * ld + base, ox);
+            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_Y * ld + base, oy);
+            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_THETA * ld + base, oth);
+            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_X * ld + base, owx);
+            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_Y * ld + base, owy);
             st_pack<uint32_t, V>(ptw_ + base, otw);
             R* const rew = reinterpret_cast<R*>(p.reward) + base;
             uint8_t* const fl = p.flags + base;
@@ -379,11 +464,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
                     if (j < nvalid) { rew[j] = vrew.v[j]; fl[j] = vfl.v[j]; }
             }
         }
+        staged = next_staged;
         if (autoreset && __any_sync(0xffffffffu, fw != 0u)) {
             n_queued = reset_queue_push<V>(wq, n_queued, fw, (uint32_t)(base - p.env_begin));
             if (n_queued >= kResetGroups) n_queued = reset_queue_drain<R>(p, tab, wq, n_queued, kResetGroups);
         }
     }
+    cp_async_wait<0>();
     if (autoreset) reset_queue_drain<R>(p, tab, wq, n_queued, 1);  // flush the remainder
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
@@ -626,8 +713,9 @@ __global__ void stats_reduce_kernel(unsigned long long* slots, int64_t* out, int
 // ------------------------------------------------------------------------------------------
 template <typename R, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    if (a.noise_x != nullptr) step_kernel<R, ACT, true><<<g.blocks, g.threads, 0, s>>>(a);
-    else step_kernel<R, ACT, false><<<g.blocks, g.threads, 0, s>>>(a);
+    const size_t smem = (size_t)g.threads * kStageBytesPerThread;
+    if (a.noise_x != nullptr) step_kernel<R, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
+    else step_kernel<R, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
     return cudaGetLastError();
 }
 template <typename R>
@@ -645,6 +733,30 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
                                  : launch_step_r<float>(action_dtype, a, g, s);
 }
 
+template <typename R, int ACT> static cudaError_t configure_step_t() {
+    const int bytes = kMaxThreads * kStageBytesPerThread;  // 64 KiB: above the 48 KiB default limit
+    cudaError_t e = cudaFuncSetAttribute(step_kernel<R, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(step_kernel<R, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(step_kernel<R, ACT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(step_kernel<R, ACT, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+    return e;
+}
+template <typename R> static cudaError_t configure_step_r() {
+    cudaError_t e = configure_step_t<R, AQUA_ACT_I32>();
+    if (e == cudaSuccess) e = configure_step_t<R, AQUA_ACT_I64>();
+    if (e == cudaSuccess) e = configure_step_t<R, AQUA_ACT_U8>();
+    if (e == cudaSuccess) e = configure_step_t<R, AQUA_ACT_F32X2>();
+    return e;
+}
+cudaError_t configure_kernels(int precision) {
+    return precision == AQUA_F64 ? configure_step_r<double>() : configure_step_r<float>();
+}
+
 template <typename R, int ACT> static const void* step_fn() {
     return reinterpret_cast<const void*>(&step_kernel<R, ACT, false>);
 }
@@ -660,7 +772,8 @@ template <typename R> static const void* step_fn_r(int act) {
 cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm) {
     const void* fn = precision == AQUA_F64 ? step_fn_r<double>(action_dtype) : step_fn_r<float>(action_dtype);
     if (fn == nullptr) return cudaErrorInvalidValue;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads,
+                                                         (size_t)threads * kStageBytesPerThread);
 }
 
 cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s) {

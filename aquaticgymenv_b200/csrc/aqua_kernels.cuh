@@ -76,6 +76,8 @@ cudaError_t launch_get_state(int precision, const void* planes, int64_t ld, int6
 cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n, const double* in,
                              cudaStream_t s);
 cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s);
+// per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
+cudaError_t configure_kernels(int precision);
 // occupancy of the step kernel for (precision, action dtype) at `threads` per CTA
 cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm);
 cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* blocks_per_sm);
