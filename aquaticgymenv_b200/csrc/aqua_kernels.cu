@@ -66,12 +66,18 @@ template <int ACT, int V> struct ActVals {
     uint32_t w[N];
 };
 
-template <typename T, int V>
-__device__ __forceinline__ void fetch_discrete(const void* actions, int64_t base, int nvalid, uint32_t (&a)[V]) {
-    const T* src = reinterpret_cast<const T*>(actions) + base;
+template <bool SMEM, typename T, int V> __device__ __forceinline__ Pack<T, V> act_pack(const T* src) {
+    if constexpr (SMEM) return *reinterpret_cast<const Pack<T, V>*>(src);
+    else return ldg_pack<T, V>(src);
+}
+
+// `src` points at the thread's V actions (global memory, or its staging slot when SMEM)
+template <bool SMEM, typename T, int V>
+__device__ __forceinline__ void fetch_discrete(const void* src_, int nvalid, uint32_t (&a)[V]) {
+    const T* src = reinterpret_cast<const T*>(src_);
     T raw[V];
     if (nvalid == V) {
-        const Pack<T, V> pk = ldg_pack<T, V>(src);
+        const Pack<T, V> pk = act_pack<SMEM, T, V>(src);
 #pragma unroll
         for (int j = 0; j < V; ++j) raw[j] = pk.v[j];
     } else {
@@ -89,26 +95,33 @@ __device__ __forceinline__ void fetch_discrete(const void* actions, int64_t base
     }
 }
 
-// loads the actions of V envs starting at absolute env index `base` (padding lanes: valid values)
-template <int ACT, int V>
-__device__ __forceinline__ ActVals<ACT, V> fetch_actions(const void* actions, int64_t base, int nvalid) {
+template <int ACT> struct ActElem { using T = int32_t; static constexpr int kPerEnv = 1; };
+template <> struct ActElem<AQUA_ACT_I64> { using T = long long; static constexpr int kPerEnv = 1; };
+template <> struct ActElem<AQUA_ACT_U8> { using T = uint8_t; static constexpr int kPerEnv = 1; };
+template <> struct ActElem<AQUA_ACT_F32X2> { using T = float; static constexpr int kPerEnv = 2; };
+template <int ACT, int V> constexpr int act_bytes() { return (int)sizeof(typename ActElem<ACT>::T) * ActElem<ACT>::kPerEnv * V; }
+
+// address of the actions of the V envs starting at absolute env index `base`
+template <int ACT> __device__ __forceinline__ const void* act_ptr(const void* actions, int64_t base) {
+    return reinterpret_cast<const typename ActElem<ACT>::T*>(actions) + base * ActElem<ACT>::kPerEnv;
+}
+
+// loads the actions of V envs from `src` (padding lanes: valid values)
+template <int ACT, int V, bool SMEM = false>
+__device__ __forceinline__ ActVals<ACT, V> fetch_actions(const void* src_, int nvalid) {
     ActVals<ACT, V> out;
     if constexpr (ACT == AQUA_ACT_F32X2) {
-        const float* src = reinterpret_cast<const float*>(actions) + 2 * base;
+        const float* src = reinterpret_cast<const float*>(src_);
         if (nvalid == V) {
-            const Pack<float, 2 * V> pk = ldg_pack<float, 2 * V>(src);
+            const Pack<float, 2 * V> pk = act_pack<SMEM, float, 2 * V>(src);
 #pragma unroll
             for (int j = 0; j < 2 * V; ++j) out.w[j] = __float_as_uint(pk.v[j]);
         } else {
 #pragma unroll
             for (int j = 0; j < 2 * V; ++j) out.w[j] = __float_as_uint((j < 2 * nvalid) ? __ldg(src + j) : 0.5f);
         }
-    } else if constexpr (ACT == AQUA_ACT_I32) {
-        fetch_discrete<int32_t, V>(actions, base, nvalid, out.w);
-    } else if constexpr (ACT == AQUA_ACT_I64) {
-        fetch_discrete<long long, V>(actions, base, nvalid, out.w);
     } else {
-        fetch_discrete<uint8_t, V>(actions, base, nvalid, out.w);
+        fetch_discrete<SMEM, typename ActElem<ACT>::T, V>(src_, nvalid, out.w);
     }
     return out;
 }
@@ -156,9 +169,10 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-constexpr int kStageSlot = 16;                              // bytes per thread per plane per stage
+constexpr int kStageSlot = 16;                              // bytes per thread per slot per stage
 constexpr int kStages = 2;
-constexpr int kStageBytesPerThread = kStages * AQUA_N_PLANES * kStageSlot;  // 256
+constexpr int kStageSlots = AQUA_N_PLANES + 2;              // 8 state planes + up to 32 bytes of actions
+constexpr int kStageBytesPerThread = kStages * kStageSlots * kStageSlot;  // 320
 
 // ------------------------------------------------------------------------------------------
 // per-thread episode statistics and their reduction
@@ -303,10 +317,10 @@ __device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const Obstac
     return n;
 }
 
-template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8_t, V>& f, int nvalid) {
+// the V flag bytes as one word (byte j = env j)
+template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8_t, V>& f) {
     uint32_t w = 0;
-#pragma unroll
-    for (int j = 0; j < V; ++j) w |= (j < nvalid ? (uint32_t)f.v[j] : 0u) << (8 * j);
+    memcpy(&w, &f, V);
     return w;
 }
 
@@ -339,11 +353,43 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
     // this thread's staging slots: [stage][plane][thread] x 16 bytes (conflict-free 16-byte LDS)
     unsigned char* const my_stage = s_stage + (size_t)threadIdx.x * kStageSlot;
     const size_t plane_pitch = (size_t)blockDim.x * kStageSlot;
-    auto slot = [&](int stage, int pl) { return my_stage + (size_t)(stage * AQUA_N_PLANES + pl) * plane_pitch; };
-    auto prefetch = [&](int stage, int64_t b) {  // the 8 plane slices of the V envs starting at b
+    auto slot = [&](int stage, int pl) { return my_stage + (size_t)(stage * kStageSlots + pl) * plane_pitch; };
+    // actions ride along when their per-thread footprint is a legal cp.async size
+    constexpr int kActBytes = act_bytes<ACT, V>();
+    constexpr bool kActStaged = kActBytes == 4 || kActBytes == 8 || kActBytes == 16 || kActBytes == 32;
+    auto prefetch = [&](int stage, int64_t b) {  // the 8 plane slices + actions of the V envs starting at b
 #pragma unroll
         for (int pl = 0; pl < 7; ++pl) cp_async<(int)sizeof(R) * V>(slot(stage, pl), pl0 + (int64_t)pl * ld + b);
         cp_async<4 * V>(slot(stage, AQUA_PLANE_TIME), ptw_ + b);
+        if constexpr (kActStaged) {
+            const char* a = reinterpret_cast<const char*>(act_ptr<ACT>(p.actions, b));
+            if constexpr (kActBytes == 32) {
+                cp_async<16>(slot(stage, AQUA_N_PLANES), a);
+                cp_async<16>(slot(stage, AQUA_N_PLANES + 1), a + 16);
+            } else {
+                cp_async<kActBytes>(slot(stage, AQUA_N_PLANES), a);
+            }
+        }
+    };
+    auto staged_actions = [&](int stage) {
+        if constexpr (kActBytes == 32) {  // the two halves sit in different slots
+            ActVals<ACT, V> out;
+            const Pack<uint32_t, 4> lo = *reinterpret_cast<const Pack<uint32_t, 4>*>(slot(stage, AQUA_N_PLANES));
+            const Pack<uint32_t, 4> hi = *reinterpret_cast<const Pack<uint32_t, 4>*>(slot(stage, AQUA_N_PLANES + 1));
+            uint32_t raw[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { raw[j] = lo.v[j]; raw[4 + j] = hi.v[j]; }
+            if constexpr (ACT == AQUA_ACT_F32X2) {
+#pragma unroll
+                for (int j = 0; j < 2 * V; ++j) out.w[j] = raw[j];
+            } else {  // int64 x 4: (lo, hi) word pairs
+#pragma unroll
+                for (int j = 0; j < V; ++j) out.w[j] = raw[2 * j + 1] ? 0xffffffffu : raw[2 * j];
+            }
+            return out;
+        } else {
+            return fetch_actions<ACT, V, true>(slot(stage, AQUA_N_PLANES), V);
+        }
     };
 
     ThreadStats st;
@@ -353,12 +399,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
     int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs;
     // prologue: stage the first tile (full threads only; a partial tail thread loads directly)
     bool staged = false;
-    ActVals<ACT, V> act_next;
+    ActVals<ACT, V> act_next;  // only used when the actions cannot be staged (2-byte footprint)
     {
         const int64_t b0 = tile_base + (int64_t)threadIdx.x * V;
         if (b0 + V <= p.env_end) {
             prefetch(0, b0);
-            act_next = fetch_actions<ACT, V>(p.actions, b0, V);
+            if constexpr (!kActStaged) act_next = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, b0), V);
             staged = true;
         }
         cp_async_commit();
@@ -370,13 +416,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
         // ---- stage the next tile of this thread while this one is computed ----
         const int64_t next_base = base + stride;
         const bool next_staged = next_base + V <= p.env_end;
-        const ActVals<ACT, V> act_cur = staged ? act_next : fetch_actions<ACT, V>(p.actions, base, nvalid);
+        ActVals<ACT, V> act_cur;
+        if constexpr (!kActStaged) act_cur = act_next;
         if (next_staged) {
             prefetch((it + 1) & 1, next_base);
-            act_next = fetch_actions<ACT, V>(p.actions, next_base, V);
+            if constexpr (!kActStaged) act_next = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, next_base), V);
         }
         cp_async_commit();
         cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
+        if (staged) {
+            if constexpr (kActStaged) act_cur = staged_actions(it & 1);
+        } else {
+            act_cur = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, base), nvalid);
+        }
         uint32_t fw = 0u;
         if (nvalid > 0) {
             Pack<R, V> vx, vy, vth, vgx, vgy, vwx, vwy;
@@ -439,12 +491,18 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
                 const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
                 vrew.v[j] = reward;
                 vfl.v[j] = (uint8_t)f;
-                if (j < nvalid) st.add_env<R>(f, e[j].tw & kTimeMask, reward);
                 ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
                 owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
             }
-            fw = flags_word<V>(vfl, nvalid);
+            if (nvalid != V) {  // the one partial thread of a launch: padding envs count for nothing
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (j >= nvalid) { vfl.v[j] = 0; vrew.v[j] = R(0); }
+            }
+            fw = flags_word<V>(vfl);
             st.add_flags(fw, nvalid);
+#pragma unroll
+            for (int j = 0; j < V; ++j) st.add_env<R>(vfl.v[j], otw.v[j] & kTimeMask, vrew.v[j]);
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
             st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_X * ld + base, ox);
@@ -550,10 +608,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const 
                 for (int j = 0; j < V; ++j) {
                     R reward;
                     const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
-                    vfl.v[j] = (uint8_t)f;
-                    if (j < nvalid) st.add_env<R>(f, e[j].tw & kTimeMask, reward);
+                    vfl.v[j] = (uint8_t)((j < nvalid) ? f : 0u);
+                    st.add_env<R>(vfl.v[j], e[j].tw & kTimeMask, (j < nvalid) ? reward : R(0));
                 }
-                fw = flags_word<V>(vfl, nvalid);
+                fw = flags_word<V>(vfl);
                 st.add_flags(fw, nvalid);
                 if (fw != 0u) {  // rare: publish the terminal time word for phase B
 #pragma unroll
