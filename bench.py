@@ -255,6 +255,35 @@ def graph_rate(torch, n, seed, precision, steps_per_graph=50, replays=6):
     return n * steps_per_graph * replays / dt
 
 
+def step_rate(torch, env_id, n, seed, precision, obstacles=None, steps=100):
+    """Other BASELINE configs, same method as the headline (single-step launches, resident actions)."""
+    from aquaticgymenv_b200 import gym_aqua
+    kw = {}
+    if obstacles == "dense64":
+        kw["obstacles"] = np.load(os.path.join(ROOT, "tests", "golden", "dense64_table.npy"))
+    env = gym_aqua.make(env_id, num_envs=n, seed=seed, precision=precision, **kw)
+    env.reset()
+    pool = [env.random_actions(k) for k in range(4)]
+    for k in range(10):
+        env.step_flags(pool[k % 4])
+    torch.cuda.synchronize()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    start.record()
+    for k in range(steps):
+        env.step_flags(pool[k % 4])
+    end.record()
+    torch.cuda.synchronize()
+    dt = start.elapsed_time(end) * 1e-3
+    env.close()
+    cont = "Continuous" in env_id
+    es = 4 if precision == "float32" else 8
+    bpe = (7 * es + 4) + (8 if cont else 4) + (5 * es + 4) + es + 1
+    peak_gbs, _ = peaks()
+    return {"env": env_id + ("+dense64" if obstacles else ""), "envs": n, "precision": precision,
+            "env_steps_per_s": n * steps / dt, "bytes_per_env_step": bpe,
+            "hbm_frac": bpe * n * steps / dt / 1e9 / peak_gbs}
+
+
 def rollout_rate(torch, n, seed, precision, steps=100):
     from aquaticgymenv_b200 import gym_aqua
     env = gym_aqua.make(WORKLOAD_ENV, num_envs=n, seed=seed, precision=precision)
@@ -381,13 +410,18 @@ def run_b200(args):
                 for n in (65536, 1 << 20)]
             extras["rollout_kernel_env_steps_per_s"] = {
                 str(n): rollout_rate(torch, n, args.seed, args.precision) for n in (65536, 1 << 20, n_local)}
+            extras["other_configs"] = [
+                step_rate(torch, "AquaContinuousEnv-v1", 1 << 24, args.seed, "float32"),
+                step_rate(torch, "AquaEnv-v1", 1 << 23, args.seed, "float64"),
+                step_rate(torch, "AquaEnv-v0", 1 << 22, args.seed, "float32", obstacles="dense64"),
+            ]
         except Exception as e:  # extras must never cost the headline
             extras["error"] = repr(e)
         line["extras"] = extras
         cores = host_cores()
-        n_cpu = 1 << 18
-        per_step = n_cpu / (6e6 * cores)  # ~6 M env-steps/s per host thread (measured, oracle port)
-        cpu_steps = int(max(5, min(400, args.cpu_seconds / max(per_step, 1e-6))))
+        n_cpu = 1 << 20
+        probe, _ = cpu_step_rate(n_cpu, 3, 1, args.seed, cores)     # calibrate the bounded sample
+        cpu_steps = int(max(5, min(4000, args.cpu_seconds * probe / n_cpu)))
         v, dt = cpu_step_rate(n_cpu, cpu_steps, 2, args.seed, cores)
         line["cpu_baseline"] = {
             "value": v, "unit": "env-steps/s", "cores": cores, "kind": "port",
