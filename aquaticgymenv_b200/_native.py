@@ -63,6 +63,7 @@ SIGNATURES = {
     "aqua_random_actions": (_int, [_vp, _vp, _u64, _vp, _int]),
     "aqua_rollout_random": (_int, [_vp, _vp, _i64, _u64]),
     "aqua_step_host": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "aqua_observe": (_int, [_vp, _vp, _vp, _int]),
     "aqua_get_state": (_int, [_vp, _vp, _vp]),
     "aqua_set_state": (_int, [_vp, _vp, _vp]),
     "aqua_stats_reduce": (_int, [_vp, _vp, _vp, _int]),

@@ -252,7 +252,6 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.env_id_base = cfg->env_id_base;
     w.tab = env->d_tab;
     w.tab64 = env->d_tab64;
-    w.grid = nullptr;
     w.k_obst = cfg->n_obstacles;
     w.k_circ = k_circ;
     {
@@ -440,6 +439,15 @@ int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_
                                         (size_t)len * es, cudaMemcpyDeviceToHost, s));
     }
     for (int i = 0; i < kHostStreams; ++i) AQ_CUDA(cudaStreamSynchronize(env->hs[i]));
+    return AQUA_OK;
+}
+
+int aqua_observe(aqua_env* env, void* stream, float* out, int normalized) {
+    if (int rc = check_env(env)) return rc;
+    if (out == nullptr) return fail(AQUA_ERR_INVALID, "out is NULL");
+    DeviceGuard guard(env->device);
+    AQ_CUDA(aqua::launch_observe(env->cfg.precision, env->state, env->ld, env->cfg.n_envs, out, normalized,
+                                 static_cast<cudaStream_t>(stream)));
     return AQUA_OK;
 }
 

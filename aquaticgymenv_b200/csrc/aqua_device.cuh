@@ -147,8 +147,16 @@ template <> struct Prec<double> {
 template <typename R> struct alignas(16) ObstacleBox {
     R cx, cy, a, b;
 };
+// Dense maps (more than kGridMinObstacles obstacles) are culled through a uniform grid over the
+// world: cell[c] is the bit mask of the obstacles whose clearance region (obstacle inflated by
+// the radius 2.5, plus a safety margin) touches cell c, so only those few are tested exactly.
+// Culling is conservative, hence the collision decision is unchanged.
+constexpr int kGridDim = 16;                          // 16 x 16 cells of 6.25 px
+constexpr int kGridCells = kGridDim * kGridDim;
+constexpr int kGridMinObstacles = 12;
 template <typename R> struct ObstacleTable {
     ObstacleBox<R> box[AQUA_MAX_OBSTACLES];
+    unsigned long long cell[kGridCells];
 };
 constexpr double kRectR2 = 6.25;  // (boat or goal radius 2.5)^2, aqua.py:72,75
 
@@ -177,6 +185,37 @@ __device__ __forceinline__ void obstacle_clearance(const ObstacleTable<R>& tab, 
     }
 }
 constexpr float kClearFar = 1e30f;  // initial clearance: "no obstacle near"
+
+// same result (sign of the minimum clearance) through the culling grid
+template <typename R, int V>
+__device__ __forceinline__ void obstacle_clearance_grid(const ObstacleTable<R>& tab, int k_circ,
+                                                        const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const int cx = min(max((int)((float)px[j] * (kGridDim / 100.0f)), 0), kGridDim - 1);
+        const int cy = min(max((int)((float)py[j] * (kGridDim / 100.0f)), 0), kGridDim - 1);
+        unsigned long long mask = tab.cell[cy * kGridDim + cx];
+        while (mask != 0ull) {
+            const int k = __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            const ObstacleBox<R> o = tab.box[k];
+            const bool circle = k < k_circ;
+            const R hx = circle ? R(0) : o.a, hy = circle ? R(0) : o.b;
+            const R r2 = circle ? o.a : R(kRectR2);
+            const R ddx = fmax(fabs(px[j] - o.cx) - hx, R(0));
+            const R ddy = fmax(fabs(py[j] - o.cy) - hy, R(0));
+            clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, -r2)));
+        }
+    }
+}
+
+// brute force for the small tables of the reference, grid for dense maps
+template <typename R, int V>
+__device__ __forceinline__ void obstacle_clearance_any(const ObstacleTable<R>& tab, int k_circ, int k_obst,
+                                                       const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
+    if (k_obst > kGridMinObstacles) obstacle_clearance_grid<R, V>(tab, k_circ, px, py, clr);
+    else obstacle_clearance<R, V>(tab, k_circ, k_obst, px, py, clr);
+}
 
 // same test against the float64 table in global memory (reset path: rare, always float64 so
 // that accept/reject decisions are those of the float64 reference)
@@ -278,7 +317,7 @@ __device__ __forceinline__ bool reset_blocked(const ObstacleTable<R>& tab, const
                                               int k_circ, int k_obst, float band, float x, float y) {
     const R px[1] = {(R)x}, py[1] = {(R)y};
     R clr[1] = {R(kClearFar)};
-    obstacle_clearance<R, 1>(tab, k_circ, k_obst, px, py, clr);
+    obstacle_clearance_any<R, 1>(tab, k_circ, k_obst, px, py, clr);
     if constexpr (sizeof(R) == 4) {
         if (fabsf(clr[0]) <= band) return hits_obstacle_g(tab64, k_obst, (double)x, (double)y);
     }

@@ -8,6 +8,7 @@
 // bandwidth (65 B per discrete env-step).
 #include "aqua_device.cuh"
 
+#include <algorithm>
 #include <cstring>
 
 namespace aqua {
@@ -249,6 +250,10 @@ __device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g
     uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
     constexpr int kWordsPerBox = sizeof(ObstacleBox<R>) / 4;
     for (int i = threadIdx.x; i < k_obst * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
+    if (k_obst > kGridMinObstacles) {  // dense map: the culling grid as well
+        constexpr int kCellOff = sizeof(ObstacleBox<R>) * AQUA_MAX_OBSTACLES / 4;
+        for (int i = threadIdx.x; i < kGridCells * 2; i += blockDim.x) dst[kCellOff + i] = __ldg(src + kCellOff + i);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -480,7 +485,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
                 pyn[j] = e[j].y;
                 clr[j] = R(kClearFar);
             }
-            obstacle_clearance<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
+            obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
 
             Pack<R, V> vrew, ox, oy, oth, owx, owy;
             Pack<uint8_t, V> vfl;
@@ -602,7 +607,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const 
                     pyn[j] = e[j].y;
                     clr[j] = R(kClearFar);
                 }
-                obstacle_clearance<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
+                obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
                 Pack<uint8_t, V> vfl;
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -739,6 +744,30 @@ __global__ void set_state_kernel(void* planes, int64_t ld, int64_t n, const doub
     const uint32_t t = min((uint32_t)in[(int64_t)7 * n + i], kTimeMask);
     const uint32_t ep = (uint32_t)in[(int64_t)8 * n + i] & kEpisodeMask;
     plane_tw<R>(planes, ld)[i] = (ep << AQUA_TIME_BITS) | t;
+}
+
+// Observation rows [n][5] float32 for a policy network, optionally scaled like
+// AquaStateNormalizer (main/impl/utils.py:15-27): obs / (high - low) with the bounds of
+// aqua.py:46-49, angle shifted by +0.5.  One thread per env; a warp reads 5 coalesced plane
+// segments and writes 640 contiguous bytes.
+template <typename R>
+__global__ void observe_kernel(const void* planes, int64_t ld, int64_t n, float* __restrict__ out, int normalized) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    void* pl = const_cast<void*>(planes);
+    float v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) v[k] = (float)plane<R>(pl, ld, k)[i];  // planes 0..4 = x, y, theta, gx, gy
+    if (normalized) {
+        const float inv_pos = 1.0f / 100.0f, inv_ang = 1.0f / (2.0f * 3.14159265358979323846f);
+        v[0] *= inv_pos;
+        v[1] *= inv_pos;
+        v[2] = fmaf(v[2], inv_ang, 0.5f);
+        v[3] *= inv_pos;
+        v[4] *= inv_pos;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) out[i * 5 + k] = v[k];
 }
 
 // K3: fold the per-CTA slots into int64[AQUA_N_STATS]
@@ -902,6 +931,14 @@ cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n,
     return cudaGetLastError();
 }
 
+cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_t n, float* out, int normalized,
+                           cudaStream_t s) {
+    const int threads = 256;
+    if (precision == AQUA_F64) observe_kernel<double><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, out, normalized);
+    else observe_kernel<float><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, out, normalized);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s) {
     stats_reduce_kernel<<<1, 256, 0, s>>>(slots, out, clear);
     return cudaGetLastError();
@@ -964,8 +1001,29 @@ static int sorted_rows(int k, const double* rows5, double* out5) {
     return k_circ;
 }
 
+// obstacles whose clearance region (inflated by the radius 2.5 and a 0.05 px safety margin that
+// also covers the rounding of the cell index) touches the cell
+static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy) {
+    const double cw = 100.0 / kGridDim;
+    const double x0 = cx * cw, x1 = x0 + cw, y0 = cy * cw, y1 = y0 + cw;
+    unsigned long long m = 0ull;
+    for (int i = 0; i < k; ++i) {
+        const double* o = rows5 + 5 * i;
+        const bool circle = o[2] == 0.0;
+        const double hx = circle ? 0.0 : o[3] / 2, hy = circle ? 0.0 : o[4] / 2;
+        const double reach = (circle ? o[3] + 2.5 : 2.5) + 0.05;
+        // distance between the obstacle's box and the cell rectangle
+        const double dx = std::max(std::max(x0 - (o[0] + hx), (o[0] - hx) - x1), 0.0);
+        const double dy = std::max(std::max(y0 - (o[1] + hy), (o[1] - hy) - y1), 0.0);
+        if (dx * dx + dy * dy <= reach * reach) m |= 1ull << i;
+    }
+    return m;
+}
+
 template <typename R> static void fill_table(int k, const double* rows5, ObstacleTable<R>* t) {
     memset(t, 0, sizeof(*t));
+    for (int cy = 0; cy < kGridDim; ++cy)
+        for (int cx = 0; cx < kGridDim; ++cx) t->cell[cy * kGridDim + cx] = cell_mask(k, rows5, cx, cy);
     for (int i = 0; i < k; ++i) {
         const double* o = rows5 + 5 * i;
         const bool circle = o[2] == 0.0;

@@ -36,7 +36,6 @@ struct World {
     uint64_t env_id_base;   // global id of env 0 of this slab
     const void* tab;        // device ObstacleTable<R> (R = float or double per precision)
     const double* tab64;    // device double[K][5] = {cx, cy, hx, hy, r2}: float64 table (reset path)
-    const uint32_t* grid;   // device uint32[kGridCells][2]: per-cell obstacle bit masks (or NULL)
     int32_t k_obst;
     int32_t k_circ;         // obstacles [0, k_circ) are circles, [k_circ, k_obst) rectangles
     float reset_band;       // guard band of the float32 reset test, see reset_blocked()
@@ -75,6 +74,8 @@ cudaError_t launch_get_state(int precision, const void* planes, int64_t ld, int6
                              cudaStream_t s);
 cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n, const double* in,
                              cudaStream_t s);
+cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_t n, float* out, int normalized,
+                           cudaStream_t s);
 cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s);
 // per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
 cudaError_t configure_kernels(int precision);

@@ -296,6 +296,18 @@ class AquaVecEnv(object):
         N.check(self.lib.aqua_rollout_random(self._h, self._stream(), int(steps), int(first_step_index)))
         self._step_index = int(first_step_index) + int(steps)
 
+    def observe(self, normalized=False, out=None):
+        """Observation rows ``[N, 5]`` float32, contiguous (network input).  ``normalized`` applies
+        ``AquaStateNormalizer.__call__`` (main/impl/utils.py:23-27) in the same kernel."""
+        self._check_open()
+        if out is None:
+            out = torch.empty(self.num_envs, 5, dtype=torch.float32, device=self.device)
+        elif out.shape != (self.num_envs, 5) or out.dtype != torch.float32 or not out.is_contiguous():
+            raise ValueError("out must be a contiguous float32 [%d, 5] tensor" % self.num_envs)
+        N.check(self.lib.aqua_observe(self._h, self._stream(), C.c_void_p(out.data_ptr()),
+                                      int(bool(normalized))))
+        return out
+
     # ---------------------------------------------------------------- state / statistics
     def get_state(self):
         """Canonical float64 ``[9, N]`` device tensor: x, y, theta, wave_x, wave_y, goal_x, goal_y,

@@ -172,6 +172,12 @@ int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t fir
 int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
                    void* reward, uint8_t* flags);
 
+/* Observation rows for a policy network: device float[N][5] = (x, y, angle, goal_x, goal_y)
+ * gathered from the state planes (aqua.py:126,213).  normalized != 0 applies the scaling of
+ * AquaStateNormalizer.__call__ (main/impl/utils.py:23-27): obs / (high - low), angle + 0.5, so
+ * that every component lies in [0, 1].  Always float32, whatever the env precision. */
+int aqua_observe(aqua_env* env, void* stream, float* out, int normalized);
+
 /* ---- state access (parity teacher-forcing, checkpoint/restore) ------------------------ */
 /* canonical DEVICE double[9][N]: x, y, theta, wave_x, wave_y, goal_x, goal_y, time, episode */
 int aqua_get_state(aqua_env* env, void* stream, double* out);

@@ -1,0 +1,129 @@
+"""CPU checks of the host-side agent code (the "next" rows of SURVEY.md section 8f): normaliser,
+bearing controller and the batched DQN loop against a tiny fake vector env (no GPU needed)."""
+import math
+import os
+
+import numpy as np
+import torch
+
+from aquaticgymenv_b200 import dqn, policies, spaces, utils
+
+
+def _ref_optimal_action(state):
+    """main/testing/test_optimal.py:10-28, restated with NumPy scalars."""
+    norm = lambda a: (a + 2 * np.pi) % (2 * np.pi)
+    boat, goal = state[:2], state[3:]
+    boat_angle_wrt_zero = norm(state[2] + np.pi / 2)
+    goal_angle_wrt_boat = norm(np.arctan2(*(goal - boat)[::-1]))
+    angle_diff = goal_angle_wrt_boat - boat_angle_wrt_zero
+    if 8 / 180 * np.pi < abs(angle_diff):
+        return 0 if angle_diff > 0 else 1
+    return 2
+
+
+def test_optimal_policy_matches_reference_rule():
+    rs = np.random.RandomState(0)
+    st = np.stack([rs.uniform(0, 100, 500), rs.uniform(0, 100, 500), rs.uniform(-np.pi, np.pi, 500),
+                   rs.uniform(0, 100, 500), rs.uniform(0, 100, 500)], axis=1)
+    got = policies.OptimalAquaPolicy().get_action(torch.as_tensor(st)).numpy()
+    want = np.array([_ref_optimal_action(s) for s in st])
+    assert (got == want).mean() > 0.995  # float64 both sides; ties at the threshold aside
+    assert set(got.tolist()) == {0, 1, 2}
+
+
+class _Env:
+    observation_space = spaces.Box(np.array([0, 0, -np.pi, 0, 0]), np.array([100, 100, np.pi, 100, 100]),
+                                   dtype=np.float64)
+
+
+def test_state_normalizer_matches_reference_formula():
+    nz = utils.AquaStateNormalizer(_Env())
+    s = np.array([50.0, 25.0, -np.pi / 2, 100.0, 0.0])
+    out = nz(s)
+    assert out.shape == (1, 5)
+    assert np.allclose(out[0], [0.5, 0.25, 0.25, 1.0, 0.0])     # utils.py:23-27
+    assert np.allclose(nz.inverse(out), s)
+    assert s[2] == -np.pi / 2                                    # the input is not modified
+    assert "REACHED GOAL" in utils.aqua_term_string({'Termination.time': False, 'Termination.collided': False}, 12.5, 40)
+    assert "collided" in utils.aqua_term_string({'Termination.time': False, 'Termination.collided': True}, -3.0, 7)
+
+
+class FakeVecEnv(object):
+    """1-D corridor: action 2 moves right, reaching x >= 1 is a success; 20-step time limit."""
+    continuous = False
+    autoreset = True
+
+    def __init__(self, n):
+        self.num_envs, self.device = n, torch.device("cpu")
+        self.x = torch.zeros(n)
+        self.t = torch.zeros(n, dtype=torch.int64)
+        self.reward = torch.zeros(n)
+
+    def reset(self):
+        self.x.zero_()
+        self.t.zero_()
+
+    def observe(self, normalized=True):
+        o = torch.zeros(self.num_envs, 5)
+        o[:, 0] = self.x
+        return o
+
+    def step_flags(self, a):
+        self.x += torch.where(a == 2, 0.25, -0.05)
+        self.t += 1
+        succ, tout = self.x >= 1.0, self.t >= 20
+        flags = torch.where(succ, 9, torch.where(tout, 5, 0)).to(torch.uint8)
+        self.reward = torch.where(succ, 10.0, torch.where(tout, -10.0, 0.1))
+        done = flags != 0
+        self.x[done] = 0.0
+        self.t[done] = 0
+        return flags
+
+
+def test_batched_dqn_loop_learns_the_corridor(tmp_path):
+    env = FakeVecEnv(32)
+    agent = dqn.BatchedDQN(env, save_directory=str(tmp_path), save_freq=50,
+                           hyperparams={"EPSILON_DECAY": 200, "BUFFER_SIZE": 4000, "MINIBATCH_SIZE": 64})
+    rewards, success = agent.train(episodes=700)
+    assert len(rewards) >= 700 and len(rewards) == len(success)
+    assert np.mean(success[-200:]) > 0.8                          # it learns to go right
+    assert agent.learner_steps > 0 and agent.env_steps == agent.learner_steps * 32
+    r = np.loadtxt(os.path.join(str(tmp_path), "rewards.txt"))    # dqn.py:316-321 artifacts
+    s = np.loadtxt(os.path.join(str(tmp_path), "success.txt"))
+    assert r.shape == s.shape and set(np.unique(s)) <= {0.0, 1.0}
+    assert any(f.startswith("model-") for f in os.listdir(os.path.join(str(tmp_path), "models")))
+
+
+def test_dqn_targets_and_quirk_options():
+    torch.manual_seed(0)
+    env = FakeVecEnv(4)
+    for strategy in ("double", "fixed", "standard"):
+        a = dqn.BatchedDQN(env, hyperparams={"LOSS_STRATEGY": strategy})
+        s, s2 = torch.rand(8, 5), torch.rand(8, 5)
+        r, d = torch.rand(8), torch.tensor([True, False] * 4)
+        t = a._targets(s, r, s2, d)
+        assert torch.allclose(t[d], r[d])                         # terminal: no bootstrap
+        assert t.shape == (8,)
+    a = dqn.BatchedDQN(env, reference_double=True, reference_broadcast_loss=True)
+    a.exp_buffer.push(torch.rand(16, 5), torch.randint(0, 3, (16,)), torch.rand(16), torch.rand(16, 5),
+                      torch.zeros(16, dtype=torch.bool))
+    assert torch.isfinite(a._improve_network_gradient())
+    w0 = [p.clone() for p in a.q_function_target.parameters()]
+    a._improve_target_network()
+    assert any(not torch.equal(x, y) for x, y in zip(w0, a.q_function_target.parameters()))
+    try:
+        dqn.BatchedDQN(env, hyperparams={"LOSS_STRATEGY": "nope"})
+        raise AssertionError("bad strategy accepted")
+    except NotImplementedError:
+        pass
+
+
+def test_replay_buffer_ring():
+    b = dqn.ReplayBuffer(10, 5, "cpu")
+    for k in range(4):
+        b.push(torch.full((4, 5), float(k)), torch.zeros(4), torch.full((4,), float(k)), torch.zeros(4, 5),
+               torch.zeros(4, dtype=torch.bool))
+    assert b.size == 10 and b.head == 6
+    assert sorted(set(b.r.tolist())) == [1.0, 2.0, 3.0]           # the oldest rows were overwritten
+    b.push(torch.ones(25, 5), torch.zeros(25), torch.arange(25.0), torch.zeros(25, 5), torch.zeros(25, dtype=torch.bool))
+    assert b.size == 10 and sorted(b.r.tolist()) == list(map(float, range(15, 25)))
