@@ -131,11 +131,17 @@ template <> struct Prec<float> {
         asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
         return r;
     }
+    static __device__ __forceinline__ float rcp_(float v) {
+        float r;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+        return r;
+    }
 };
 template <> struct Prec<double> {
     static constexpr int V = 2;
     static __device__ __forceinline__ void sincos_(double a, double* s, double* c) { sincos(a, s, c); }
     static __device__ __forceinline__ double sqrt_(double v) { return sqrt(v); }
+    static __device__ __forceinline__ double rcp_(double v) { return 1.0 / v; }
 };
 
 // Obstacle table in shared memory (aqua.py:56-68, 373-390).  Circles come first (k < k_circ):
@@ -432,29 +438,53 @@ template <typename R> struct MoveTmp {
     R px, py, dx, dy;  // position before the move, displacement
 };
 
-// Phase 1 of step(): thrusts -> new pose, wave update, time.  (tl, tr) are the thrusts after
-// clamping, (nx, ny) the wave increment of this step.
-template <typename R>
-__device__ __forceinline__ void move_env(EnvState<R>& e, R tl, R tr, R nx, R ny, bool waves,
-                                         MoveTmp<R>& m) {
-    using P = Prec<R>;
-    constexpr bool kF64 = sizeof(R) == 8;
+// The part of the move that depends on the thrusts only: turn angle phi = w * tau, half angle h
+// and chord length v * tau * sin(h)/h of the arc (aqua.py:159-170 in closed form).
+template <typename R> struct Drive {
+    R phi, h, chord;
+};
 
-    // ---- differential drive, aqua.py:159-183 in closed form ----
+template <typename R> __device__ __forceinline__ Drive<R> drive_from_thrusts(R tl, R tr) {
+    constexpr bool kF64 = sizeof(R) == 8;
     R d = tr - tl;
     if (fabs(d) < R(1e-8)) d = copysign(R(1e-8), d);  // aqua.py:159-160 (epsilon sentinel)
-    R phi, sinc;                                      // phi = w * tau, aqua.py:168
-    if constexpr (kF64) phi = d / R(2.5);
-    else phi = d * R(0.4);
+    Drive<R> o;
+    R sinc;
+    if constexpr (kF64) o.phi = d / R(2.5);           // aqua.py:168
+    else o.phi = d * R(0.4);
     const R v = (tr + tl) * R(0.5);                   // |w * r|,  aqua.py:166-170
-    const R h = phi * R(0.5);
-    const R h2 = h * h;
+    o.h = o.phi * R(0.5);
+    const R h2 = o.h * o.h;
     // sin(h)/h for |h| <= 0.06
     if constexpr (kF64)
         sinc = fma(h2, fma(h2, fma(h2, fma(h2, R(1.0 / 362880), R(-1.0 / 5040)), R(1.0 / 120)), R(-1.0 / 6)), R(1));
     else
         sinc = fma(h2, fma(h2, R(1.0 / 120), R(-1.0 / 6)), R(1));
-    const R chord = v * sinc;
+    o.chord = v * sinc;
+    return o;
+}
+
+// Discrete table aqua.py:33-42: 0 -> (0.2, 0.5) rotate left, 1 -> (0.5, 0.2) rotate right (the
+// exact mirror image of action 0: same chord, opposite angles), 2 -> (0.5, 0.5) full throttle.
+// The three drives are compile-time constants of the same arithmetic as drive_from_thrusts().
+// An index outside {0,1,2} selects full throttle (and is counted by the caller).
+template <typename R> __device__ __forceinline__ Drive<R> drive_from_index(uint32_t a) {
+    const Drive<R> turn = drive_from_thrusts<R>(R(0.2), R(0.5));
+    const Drive<R> ahead = drive_from_thrusts<R>(R(0.5), R(0.5));
+    Drive<R> o;
+    o.phi = (a == 0u) ? turn.phi : ((a == 1u) ? -turn.phi : ahead.phi);
+    o.h = (a == 0u) ? turn.h : ((a == 1u) ? -turn.h : ahead.h);
+    o.chord = (a < 2u) ? turn.chord : ahead.chord;
+    return o;
+}
+
+// Phase 1 of step(): drive -> new pose, wave update, time.  (nx, ny) is the wave increment of
+// this step.
+template <typename R>
+__device__ __forceinline__ void move_env(EnvState<R>& e, const Drive<R>& dr, R nx, R ny, bool waves,
+                                         MoveTmp<R>& m) {
+    using P = Prec<R>;
+    const R phi = dr.phi, h = dr.h, chord = dr.chord;
     R sn, cs;
     P::sincos_(e.th + h, &sn, &cs);
     m.dx = fma(-chord, sn, e.wx);  // heading 0 = +y; aqua.py:173-181, tau = 1
@@ -510,7 +540,7 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
         reached = dc2 <= R(25);
         const R num = -fma(m.dx, fma(R(2), gpx, m.dx), m.dy * fma(R(2), gpy, m.dy));
         const R den = P::sqrt_(dp2) + P::sqrt_(dc2);
-        step_reward = R(0.7) * __fdividef(num, den);
+        step_reward = (R(0.7) * num) * P::rcp_(den);
     }
     const uint32_t tn = e.tw & kTimeMask;
     uint32_t flags;
@@ -531,19 +561,14 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
 }
 
 // action decode ---------------------------------------------------------------------------
-// discrete table aqua.py:33-42: 0 -> (0.2, 0.5) rotate left, 1 -> (0.5, 0.2) rotate right,
-// 2 -> (0.5, 0.5) full throttle.  An index outside {0,1,2} selects full throttle and is counted.
-template <typename R> __device__ __forceinline__ void decode_discrete(uint32_t a, R& tl, R& tr) {
-    tl = (a == 0u) ? R(0.2) : R(0.5);
-    tr = (a == 1u) ? R(0.2) : R(0.5);
-}
 // continuous aqua.py:143-151: values outside [0.2, 0.5] are clipped (and counted)
 template <typename R>
-__device__ __forceinline__ void decode_continuous(float al, float ar, R& tl, R& tr, uint32_t& bad) {
+__device__ __forceinline__ Drive<R> drive_continuous(float al, float ar, uint32_t& bad) {
     const R l = (R)al, r = (R)ar;
-    tl = fmin(fmax(l, R(0.2)), R(0.5));
-    tr = fmin(fmax(r, R(0.2)), R(0.5));
+    const R tl = fmin(fmax(l, R(0.2)), R(0.5));
+    const R tr = fmin(fmax(r, R(0.2)), R(0.5));
     bad += (tl != l || tr != r) ? 1u : 0u;
+    return drive_from_thrusts<R>(tl, tr);
 }
 
 }  // namespace aqua

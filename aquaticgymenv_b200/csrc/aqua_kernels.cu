@@ -128,19 +128,16 @@ __device__ __forceinline__ ActVals<ACT, V> fetch_actions(const void* src_, int n
 }
 
 template <typename R, int ACT, int V>
-__device__ __forceinline__ void decode_thrusts(const ActVals<ACT, V>& a, R (&tl)[V], R (&tr)[V], uint32_t& bad) {
+__device__ __forceinline__ void decode_drives(const ActVals<ACT, V>& a, Drive<R> (&dr)[V], uint32_t& bad) {
     if constexpr (ACT == AQUA_ACT_F32X2) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            uint32_t b = 0;
-            decode_continuous<R>(__uint_as_float(a.w[2 * j]), __uint_as_float(a.w[2 * j + 1]), tl[j], tr[j], b);
-            bad += b;  // padding lanes hold 0.5: never counted
-        }
+        for (int j = 0; j < V; ++j)  // padding lanes hold 0.5: never counted
+            dr[j] = drive_continuous<R>(__uint_as_float(a.w[2 * j]), __uint_as_float(a.w[2 * j + 1]), bad);
     } else {
         uint32_t worst = 0u;
 #pragma unroll
         for (int j = 0; j < V; ++j) {
-            decode_discrete<R>(a.w[j], tl[j], tr[j]);
+            dr[j] = drive_from_index<R>(a.w[j]);
             worst = max(worst, a.w[j]);
         }
         if (worst > 2u) {  // rare: an index outside {0, 1, 2} (padding lanes hold 2)
@@ -173,7 +170,9 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
 constexpr int kStageSlot = 16;                              // bytes per thread per slot per stage
 constexpr int kStages = 2;
 constexpr int kStageSlots = AQUA_N_PLANES + 2;              // 8 state planes + up to 32 bytes of actions
-constexpr int kStageBytesPerThread = kStages * kStageSlots * kStageSlot;  // 320
+constexpr int kStagePitch = kMaxThreads * kStageSlot;       // bytes between slots: independent of blockDim,
+                                                            // so that every slot offset is an immediate
+constexpr int kStageBytes = kStages * kStageSlots * kStagePitch;  // 80 KiB of dynamic shared memory
 
 // ------------------------------------------------------------------------------------------
 // per-thread episode statistics and their reduction
@@ -203,8 +202,12 @@ struct ThreadStats {
         steps += (uint32_t)nvalid;
         if (++pk_n == 255u) widen();
     }
-    template <typename R> __device__ __forceinline__ void add_env(uint32_t flags, uint32_t time_after, R reward) {
+    // without auto-reset the episode length is taken here; with it, phase B adds it (the reset
+    // pass reads the terminal time word anyway)
+    __device__ __forceinline__ void add_length(uint32_t flags, uint32_t time_after) {
         length += (flags & 1u) ? time_after : 0u;
+    }
+    template <typename R> __device__ __forceinline__ void add_env(R reward) {
         int fx;
         if constexpr (sizeof(R) == 8) fx = __double2int_rn(reward * R(AQUA_REWARD_FIXED_POINT));
         else fx = __float2int_rn(reward * R(AQUA_REWARD_FIXED_POINT));
@@ -289,7 +292,7 @@ __device__ __forceinline__ int reset_queue_push(uint32_t* wq, int n, uint32_t fw
 // queued (min_batch = kResetGroups: full passes only; 1: flush).  Returns the new queue length.
 template <typename R>
 __device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const ObstacleTable<R>& tab,
-                                                 const uint32_t* wq, int n, int min_batch) {
+                                                 const uint32_t* wq, int n, int min_batch, uint32_t& length_sum) {
     const unsigned lane = threadIdx.x & 31u;
     const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
     uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
@@ -307,6 +310,7 @@ __device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const Obstac
         const CoopResetResult rr = coop_reset<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
                                                  p.w.reset_band, wf, valid, env_id, ep);
         if (valid && leader) {
+            length_sum += tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
             plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
             plane<R>(p.planes, p.ld, AQUA_PLANE_Y)[i] = (R)rr.y;
             plane<R>(p.planes, p.ld, AQUA_PLANE_THETA)[i] = (R)rr.th;
@@ -357,15 +361,15 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
 
     // this thread's staging slots: [stage][plane][thread] x 16 bytes (conflict-free 16-byte LDS)
     unsigned char* const my_stage = s_stage + (size_t)threadIdx.x * kStageSlot;
-    const size_t plane_pitch = (size_t)blockDim.x * kStageSlot;
-    auto slot = [&](int stage, int pl) { return my_stage + (size_t)(stage * kStageSlots + pl) * plane_pitch; };
+    auto slot = [&](int stage, int pl) { return my_stage + (size_t)stage * (kStageSlots * kStagePitch) + pl * kStagePitch; };
     // actions ride along when their per-thread footprint is a legal cp.async size
     constexpr int kActBytes = act_bytes<ACT, V>();
     constexpr bool kActStaged = kActBytes == 4 || kActBytes == 8 || kActBytes == 16 || kActBytes == 32;
     auto prefetch = [&](int stage, int64_t b) {  // the 8 plane slices + actions of the V envs starting at b
+        const R* g = pl0 + b;  // running pointer: one 64-bit add per plane
 #pragma unroll
-        for (int pl = 0; pl < 7; ++pl) cp_async<(int)sizeof(R) * V>(slot(stage, pl), pl0 + (int64_t)pl * ld + b);
-        cp_async<4 * V>(slot(stage, AQUA_PLANE_TIME), ptw_ + b);
+        for (int pl = 0; pl < 7; ++pl, g += ld) cp_async<(int)sizeof(R) * V>(slot(stage, pl), g);
+        cp_async<4 * V>(slot(stage, AQUA_PLANE_TIME), ptw_ + b);  // uint32 plane: its own index scale
         if constexpr (kActStaged) {
             const char* a = reinterpret_cast<const char*>(act_ptr<ACT>(p.actions, b));
             if constexpr (kActBytes == 32) {
@@ -458,8 +462,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
                 vwy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_Y * ld + base);
                 vtw = ld_pack<uint32_t, V>(ptw_ + base);
             }
-            R tl[V], tr[V];
-            decode_thrusts<R, ACT, V>(act_cur, tl, tr, st.bad);
+            Drive<R> dr[V];
+            decode_drives<R, ACT, V>(act_cur, dr, st.bad);
 
             EnvState<R> e[V];
             MoveTmp<R> m[V];
@@ -480,7 +484,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
                     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
                     if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx, ny);
                 }
-                move_env<R>(e[j], tl[j], tr[j], (R)nx, (R)ny, waves, m[j]);
+                move_env<R>(e[j], dr[j], (R)nx, (R)ny, waves, m[j]);
                 pxn[j] = e[j].x;
                 pyn[j] = e[j].y;
                 clr[j] = R(kClearFar);
@@ -507,14 +511,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
             fw = flags_word<V>(vfl);
             st.add_flags(fw, nvalid);
 #pragma unroll
-            for (int j = 0; j < V; ++j) st.add_env<R>(vfl.v[j], otw.v[j] & kTimeMask, vrew.v[j]);
+            for (int j = 0; j < V; ++j) st.add_env<R>(vrew.v[j]);
+            if (!autoreset) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) st.add_length(vfl.v[j], otw.v[j] & kTimeMask);
+            }
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
-            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_X * ld + base, ox);
-            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_Y * ld + base, oy);
-            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_THETA * ld + base, oth);
-            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_X * ld + base, owx);
-            st_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_Y * ld + base, owy);
+            R* g = pl0 + base;  // plane x; running pointer
+            st_pack<R, V>(g, ox);
+            st_pack<R, V>(g += ld, oy);
+            st_pack<R, V>(g += ld, oth);
+            st_pack<R, V>(g += 3 * ld, owx);  // skip the two goal planes
+            st_pack<R, V>(g += ld, owy);
             st_pack<uint32_t, V>(ptw_ + base, otw);
             R* const rew = reinterpret_cast<R*>(p.reward) + base;
             uint8_t* const fl = p.flags + base;
@@ -530,11 +539,12 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
         staged = next_staged;
         if (autoreset && __any_sync(0xffffffffu, fw != 0u)) {
             n_queued = reset_queue_push<V>(wq, n_queued, fw, (uint32_t)(base - p.env_begin));
-            if (n_queued >= kResetGroups) n_queued = reset_queue_drain<R>(p, tab, wq, n_queued, kResetGroups);
+            if (n_queued >= kResetGroups)
+                n_queued = reset_queue_drain<R>(p, tab, wq, n_queued, kResetGroups, st.length);
         }
     }
     cp_async_wait<0>();
-    if (autoreset) reset_queue_drain<R>(p, tab, wq, n_queued, 1);  // flush the remainder
+    if (autoreset) reset_queue_drain<R>(p, tab, wq, n_queued, 1, st.length);  // flush the remainder
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
 }
@@ -593,16 +603,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const 
                 for (int j = 0; j < V; ++j) {
                     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
                     const uint2 ra = draw_action_words(p.w.keys, env_id, step);
-                    R tl, tr;
+                    Drive<R> dr;
                     if constexpr (CONTINUOUS) {
                         uint32_t bad = 0;
-                        decode_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), tl, tr, bad);
+                        dr = drive_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), bad);
                     } else {
-                        decode_discrete<R>(__umulhi(ra.x, 3u), tl, tr);
+                        dr = drive_from_index<R>(__umulhi(ra.x, 3u));
                     }
                     float nx = 0.f, ny = 0.f;
                     if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx, ny);
-                    move_env<R>(e[j], tl, tr, (R)nx, (R)ny, waves, m[j]);
+                    move_env<R>(e[j], dr, (R)nx, (R)ny, waves, m[j]);
                     pxn[j] = e[j].x;
                     pyn[j] = e[j].y;
                     clr[j] = R(kClearFar);
@@ -614,7 +624,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const 
                     R reward;
                     const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
                     vfl.v[j] = (uint8_t)((j < nvalid) ? f : 0u);
-                    st.add_env<R>(vfl.v[j], e[j].tw & kTimeMask, (j < nvalid) ? reward : R(0));
+                    st.add_env<R>((j < nvalid) ? reward : R(0));
                 }
                 fw = flags_word<V>(vfl);
                 st.add_flags(fw, nvalid);
@@ -627,7 +637,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const 
             if (__any_sync(0xffffffffu, fw != 0u)) {
                 uint32_t* const wq = s_wq[threadIdx.x >> 5].rel;
                 const int n_queued = reset_queue_push<V>(wq, 0, fw, (uint32_t)(base - p.env_begin));
-                reset_queue_drain<R>(p, tab, wq, n_queued, 1);  // the next step needs the fresh state
+                reset_queue_drain<R>(p, tab, wq, n_queued, 1, st.length);  // the next step needs the fresh state
                 if (fw != 0u) {  // pick the fresh episode up from the planes
 #pragma unroll
                     for (int j = 0; j < V; ++j)
@@ -800,7 +810,7 @@ __global__ void stats_reduce_kernel(unsigned long long* slots, int64_t* out, int
 // ------------------------------------------------------------------------------------------
 template <typename R, int ACT>
 static cudaError_t launch_step_t(const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    const size_t smem = (size_t)g.threads * kStageBytesPerThread;
+    const size_t smem = kStageBytes;
     if (a.noise_x != nullptr) step_kernel<R, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
     else step_kernel<R, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
     return cudaGetLastError();
@@ -821,7 +831,7 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 }
 
 template <typename R, int ACT> static cudaError_t configure_step_t() {
-    const int bytes = kMaxThreads * kStageBytesPerThread;  // 64 KiB: above the 48 KiB default limit
+    const int bytes = kStageBytes;  // 80 KiB: above the 48 KiB default limit
     cudaError_t e = cudaFuncSetAttribute(step_kernel<R, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(step_kernel<R, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -859,8 +869,7 @@ template <typename R> static const void* step_fn_r(int act) {
 cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm) {
     const void* fn = precision == AQUA_F64 ? step_fn_r<double>(action_dtype) : step_fn_r<float>(action_dtype);
     if (fn == nullptr) return cudaErrorInvalidValue;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads,
-                                                         (size_t)threads * kStageBytesPerThread);
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, kStageBytes);
 }
 
 cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
