@@ -168,7 +168,10 @@ template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 constexpr int kStageSlot = 16;                              // bytes per thread per slot per stage
-constexpr int kStages = 2;
+#ifndef AQUA_STAGES
+#define AQUA_STAGES 2
+#endif
+constexpr int kStages = AQUA_STAGES;                        // 2: double buffer; 1: refill after the reads
 constexpr int kStageSlots = AQUA_N_PLANES + 2;              // 8 state planes + up to 32 bytes of actions
 constexpr int kStagePitch = kMaxThreads * kStageSlot;       // bytes between slots: independent of blockDim,
                                                             // so that every slot offset is an immediate
@@ -427,41 +430,52 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
         const bool next_staged = next_base + V <= p.env_end;
         ActVals<ACT, V> act_cur;
         if constexpr (!kActStaged) act_cur = act_next;
-        if (next_staged) {
-            prefetch((it + 1) & 1, next_base);
-            if constexpr (!kActStaged) act_next = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, next_base), V);
+        const int sg = (kStages == 2) ? (it & 1) : 0;      // the stage holding this tile
+        if constexpr (kStages == 2) {
+            if (next_staged) {
+                prefetch((it + 1) & 1, next_base);
+                if constexpr (!kActStaged) act_next = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, next_base), V);
+            }
+            cp_async_commit();
+            cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
+        } else {
+            cp_async_wait<0>();
         }
-        cp_async_commit();
-        cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
         if (staged) {
-            if constexpr (kActStaged) act_cur = staged_actions(it & 1);
+            if constexpr (kActStaged) act_cur = staged_actions(sg);
         } else {
             act_cur = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, base), nvalid);
         }
         uint32_t fw = 0u;
-        if (nvalid > 0) {
-            Pack<R, V> vx, vy, vth, vgx, vgy, vwx, vwy;
-            Pack<uint32_t, V> vtw;
-            if (staged) {
-                const int sg = it & 1;
-                vx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_X));
-                vy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_Y));
-                vth = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_THETA));
-                vgx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_GOAL_X));
-                vgy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_GOAL_Y));
-                vwx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_WAVE_X));
-                vwy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_WAVE_Y));
-                vtw = *reinterpret_cast<const Pack<uint32_t, V>*>(slot(sg, AQUA_PLANE_TIME));
-            } else {  // partial tail: the planes are padded to AQUA_TILE, full-width loads are in bounds
-                vx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_X * ld + base);
-                vy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_Y * ld + base);
-                vth = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_THETA * ld + base);
-                vgx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_GOAL_X * ld + base);
-                vgy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_GOAL_Y * ld + base);
-                vwx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_X * ld + base);
-                vwy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_Y * ld + base);
-                vtw = ld_pack<uint32_t, V>(ptw_ + base);
+        Pack<R, V> vx, vy, vth, vgx, vgy, vwx, vwy;
+        Pack<uint32_t, V> vtw;
+        if (staged) {
+            vx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_X));
+            vy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_Y));
+            vth = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_THETA));
+            vgx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_GOAL_X));
+            vgy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_GOAL_Y));
+            vwx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_WAVE_X));
+            vwy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_WAVE_Y));
+            vtw = *reinterpret_cast<const Pack<uint32_t, V>*>(slot(sg, AQUA_PLANE_TIME));
+        } else if (nvalid > 0) {  // partial tail: the planes are padded to AQUA_TILE, full-width loads are in bounds
+            vx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_X * ld + base);
+            vy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_Y * ld + base);
+            vth = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_THETA * ld + base);
+            vgx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_GOAL_X * ld + base);
+            vgy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_GOAL_Y * ld + base);
+            vwx = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_X * ld + base);
+            vwy = ld_pack<R, V>(pl0 + (int64_t)AQUA_PLANE_WAVE_Y * ld + base);
+            vtw = ld_pack<uint32_t, V>(ptw_ + base);
+        }
+        if constexpr (kStages == 1) {  // single buffer: refill it once this tile's slices are in registers
+            if (next_staged) {
+                prefetch(0, next_base);
+                if constexpr (!kActStaged) act_next = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, next_base), V);
             }
+            cp_async_commit();
+        }
+        if (nvalid > 0) {
             Drive<R> dr[V];
             decode_drives<R, ACT, V>(act_cur, dr, st.bad);
 
