@@ -15,6 +15,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aquagym.h")
 ABI_VERSION = 1
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
+GEOM_AUTO, GEOM_WIDE, GEOM_NARROW = 0, 1, 2
 ACT_I32, ACT_I64, ACT_U8, ACT_F32X2 = 0, 1, 2, 3
 FLAG_DONE, FLAG_COLLIDED, FLAG_TIME, FLAG_SUCCESS = 1, 2, 4, 8
 MAX_OBSTACLES = 64
@@ -39,7 +40,7 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("device", C.c_int32), ("n_envs", C.c_int64),
         ("continuous", C.c_int32), ("waves", C.c_int32), ("random_boat", C.c_int32),
         ("random_goal", C.c_int32), ("precision", C.c_int32), ("autoreset", C.c_int32),
-        ("n_obstacles", C.c_int32), ("_reserved", C.c_int32),
+        ("n_obstacles", C.c_int32), ("geometry", C.c_int32),
         ("obstacles", C.POINTER(C.c_double)), ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
         ("state", C.c_void_p), ("ld", C.c_int64)]
 

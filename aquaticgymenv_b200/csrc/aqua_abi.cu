@@ -72,9 +72,10 @@ struct aqua_env {
     unsigned long long* d_slots = nullptr;
     int64_t* d_stats_out = nullptr;
     aqua::World world;
-    // resident CTAs per SM, queried once at create: [action dtype][64 / 128 / 256 threads]
-    int occ_step[4][3] = {};
-    int occ_rollout[3] = {};
+    // resident CTAs per SM, queried once at create: [action dtype][narrow (V = 1, 128 threads) /
+    // wide (256 threads)]
+    int occ_step[4][2] = {};
+    int occ_rollout[2] = {};
     // host-step pipeline (lazily created)
     cudaStream_t hs[kHostStreams] = {};
     cudaEvent_t ev_in = nullptr;
@@ -99,17 +100,22 @@ aqua::StepArgs base_args(const aqua_env* env) {
     return a;
 }
 
-// Launch geometry of the step kernel for `n` envs.  Small slabs use small CTAs so that every SM
-// gets work; large slabs use a persistent grid of (resident CTAs per SM) x (SM count) CTAs.
+// Launch geometry for `n` envs.  Large slabs: wide threads (16-byte plane accesses), 256-thread
+// CTAs, a persistent grid of (resident CTAs per SM) x (SM count).  Slabs too small to give every
+// SM two wide tiles are latency-bound: they use narrow threads (one env each) in 128-thread CTAs,
+// which quarters the dependent work per thread and spreads the slab over all SMs.
 int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aqua::LaunchGeom* g) {
-    const int V = env->cfg.precision == AQUA_F64 ? 2 : aqua::envs_per_thread_f32();
-    int threads = 256;
-    while (threads > 64 && n < (int64_t)threads * V * env->sm_count * 2) threads >>= 1;
-    const int ti = threads == 256 ? 2 : (threads == 128 ? 1 : 0);
+    const int wide = aqua::envs_per_thread(env->cfg.precision);
+    const bool narrow = env->cfg.geometry == AQUA_GEOM_NARROW ||
+                        (env->cfg.geometry == AQUA_GEOM_AUTO && n < (int64_t)256 * wide * env->sm_count * 2);
+    const int V = narrow ? 1 : wide;
+    const int threads = narrow ? 128 : 256;
+    const int ti = narrow ? 0 : 1;
     const int per_sm = rollout ? env->occ_rollout[ti] : env->occ_step[action_dtype][ti];
     const int64_t tiles = (n + (int64_t)threads * V - 1) / ((int64_t)threads * V);
     const int64_t resident = (int64_t)per_sm * env->sm_count;
     g->threads = threads;
+    g->v = V;
     g->blocks = (int)std::max<int64_t>(1, std::min(tiles, resident));
     return AQUA_OK;
 }
@@ -165,6 +171,8 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     if (cfg->n_envs < 1) return fail(AQUA_ERR_INVALID, "n_envs must be >= 1, got %lld", (long long)cfg->n_envs);
     if (cfg->precision != AQUA_F32 && cfg->precision != AQUA_F64)
         return fail(AQUA_ERR_INVALID, "precision must be AQUA_F32 or AQUA_F64, got %d", cfg->precision);
+    if (cfg->geometry < AQUA_GEOM_AUTO || cfg->geometry > AQUA_GEOM_NARROW)
+        return fail(AQUA_ERR_INVALID, "geometry must be AQUA_GEOM_AUTO, _WIDE or _NARROW, got %d", cfg->geometry);
     if (cfg->n_obstacles < 0 || cfg->n_obstacles > AQUA_MAX_OBSTACLES)
         return fail(AQUA_ERR_INVALID, "n_obstacles must be in [0, %d], got %d", AQUA_MAX_OBSTACLES, cfg->n_obstacles);
     if (cfg->n_obstacles > 0 && cfg->obstacles == nullptr)
@@ -269,13 +277,14 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.autoreset = cfg->autoreset != 0;
 
     AQ_CREATE(aqua::configure_kernels(cfg->precision));
-    for (int ti = 0; ti < 3; ++ti) {
-        const int threads = 64 << ti;
+    for (int ti = 0; ti < 2; ++ti) {
+        const int threads = ti == 0 ? 128 : 256;
+        const int v = ti == 0 ? 1 : aqua::envs_per_thread(cfg->precision);
         for (int act = 0; act < 4; ++act) {
-            AQ_CREATE(aqua::step_occupancy(cfg->precision, act, threads, &env->occ_step[act][ti]));
+            AQ_CREATE(aqua::step_occupancy(cfg->precision, v, act, threads, &env->occ_step[act][ti]));
             env->occ_step[act][ti] = std::max(env->occ_step[act][ti], 1);
         }
-        AQ_CREATE(aqua::rollout_occupancy(cfg->precision, cfg->continuous, threads, &env->occ_rollout[ti]));
+        AQ_CREATE(aqua::rollout_occupancy(cfg->precision, v, cfg->continuous, threads, &env->occ_rollout[ti]));
         env->occ_rollout[ti] = std::max(env->occ_rollout[ti], 1);
     }
     AQ_CREATE(aqua::launch_init_state(cfg->precision, env->state, ld, nullptr));

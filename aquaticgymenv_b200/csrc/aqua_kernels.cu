@@ -42,10 +42,13 @@ template <typename T, int V> __device__ __forceinline__ Pack<T, V> ldg_pack(cons
     } else if constexpr (sizeof(T) * V == 4) {
         const uint32_t r = __ldg(reinterpret_cast<const uint32_t*>(p));
         memcpy(&out, &r, 4);
-    } else {
-        static_assert(sizeof(T) * V == 2, "unsupported pack");
+    } else if constexpr (sizeof(T) * V == 2) {
         const unsigned short r = __ldg(reinterpret_cast<const unsigned short*>(p));
         memcpy(&out, &r, 2);
+    } else {
+        static_assert(sizeof(T) * V == 1, "unsupported pack");
+        const unsigned char r = __ldg(reinterpret_cast<const unsigned char*>(p));
+        memcpy(&out, &r, 1);
     }
     return out;
 }
@@ -342,9 +345,8 @@ template <int V> __device__ __forceinline__ uint32_t flags_word(const Pack<uint8
 // ------------------------------------------------------------------------------------------
 extern __shared__ __align__(16) unsigned char s_stage[];
 
-template <typename R, int ACT, bool INJECT>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
-    constexpr int V = Prec<R>::V;
+template <typename R, int V, int ACT, bool INJECT>
+__global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
@@ -368,6 +370,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
     // actions ride along when their per-thread footprint is a legal cp.async size
     constexpr int kActBytes = act_bytes<ACT, V>();
     constexpr bool kActStaged = kActBytes == 4 || kActBytes == 8 || kActBytes == 16 || kActBytes == 32;
+    // narrow threads (V = 1) serve small, latency-bound slabs with one tile per thread: nothing to
+    // pipeline, so they load directly and the kernel is launched without the staging buffer
+    constexpr bool kStaging = V > 1;
     auto prefetch = [&](int stage, int64_t b) {  // the 8 plane slices + actions of the V envs starting at b
         const R* g = pl0 + b;  // running pointer: one 64-bit add per plane
 #pragma unroll
@@ -414,7 +419,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
     ActVals<ACT, V> act_next;  // only used when the actions cannot be staged (2-byte footprint)
     {
         const int64_t b0 = tile_base + (int64_t)threadIdx.x * V;
-        if (b0 + V <= p.env_end) {
+        if (kStaging && b0 + V <= p.env_end) {
             prefetch(0, b0);
             if constexpr (!kActStaged) act_next = fetch_actions<ACT, V>(act_ptr<ACT>(p.actions, b0), V);
             staged = true;
@@ -427,7 +432,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
         const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
         // ---- stage the next tile of this thread while this one is computed ----
         const int64_t next_base = base + stride;
-        const bool next_staged = next_base + V <= p.env_end;
+        const bool next_staged = kStaging && next_base + V <= p.env_end;
         ActVals<ACT, V> act_cur;
         if constexpr (!kActStaged) act_cur = act_next;
         const int sg = (kStages == 2) ? (it & 1) : 0;      // the stage holding this tile
@@ -567,9 +572,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_kernel(const __g
 // K1r: `steps` env-steps per launch under the synthetic random policy (ACTION stream); the
 // state stays in registers between steps, per-step reward/flags are folded into the statistics
 // ------------------------------------------------------------------------------------------
-template <typename R, bool CONTINUOUS>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) rollout_kernel(const __grid_constant__ StepArgs p) {
-    constexpr int V = Prec<R>::V;
+template <typename R, int V, bool CONTINUOUS>
+__global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) rollout_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleTable<R> tab;
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
@@ -820,91 +824,107 @@ __global__ void stats_reduce_kernel(unsigned long long* slots, int64_t* out, int
 }
 
 // ------------------------------------------------------------------------------------------
-// launchers
+// launchers.  Every step / rollout kernel exists for V = Prec<R>::V envs per thread (wide: 16-byte
+// plane accesses, the bandwidth layout) and for V = 1 (narrow: four times the threads and a
+// quarter of the per-thread latency, for slabs too small to fill the GPU with wide threads).
 // ------------------------------------------------------------------------------------------
-template <typename R, int ACT>
-static cudaError_t launch_step_t(const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    const size_t smem = kStageBytes;
-    if (a.noise_x != nullptr) step_kernel<R, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
-    else step_kernel<R, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
-    return cudaGetLastError();
-}
-template <typename R>
-static cudaError_t launch_step_r(int act, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+template <typename R, int V, typename Op> static cudaError_t dispatch_act(int act, const Op& op) {
     switch (act) {
-        case AQUA_ACT_I32: return launch_step_t<R, AQUA_ACT_I32>(a, g, s);
-        case AQUA_ACT_I64: return launch_step_t<R, AQUA_ACT_I64>(a, g, s);
-        case AQUA_ACT_U8: return launch_step_t<R, AQUA_ACT_U8>(a, g, s);
-        case AQUA_ACT_F32X2: return launch_step_t<R, AQUA_ACT_F32X2>(a, g, s);
+        case AQUA_ACT_I32: return op.template run<R, V, AQUA_ACT_I32>();
+        case AQUA_ACT_I64: return op.template run<R, V, AQUA_ACT_I64>();
+        case AQUA_ACT_U8: return op.template run<R, V, AQUA_ACT_U8>();
+        case AQUA_ACT_F32X2: return op.template run<R, V, AQUA_ACT_F32X2>();
         default: return cudaErrorInvalidValue;
     }
 }
-cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    return precision == AQUA_F64 ? launch_step_r<double>(action_dtype, a, g, s)
-                                 : launch_step_r<float>(action_dtype, a, g, s);
-}
-
-template <typename R, int ACT> static cudaError_t configure_step_t() {
-    const int bytes = kStageBytes;  // 80 KiB: above the 48 KiB default limit
-    cudaError_t e = cudaFuncSetAttribute(step_kernel<R, ACT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(step_kernel<R, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(step_kernel<R, ACT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(step_kernel<R, ACT, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                 cudaSharedmemCarveoutMaxShared);
-    return e;
-}
-template <typename R> static cudaError_t configure_step_r() {
-    cudaError_t e = configure_step_t<R, AQUA_ACT_I32>();
-    if (e == cudaSuccess) e = configure_step_t<R, AQUA_ACT_I64>();
-    if (e == cudaSuccess) e = configure_step_t<R, AQUA_ACT_U8>();
-    if (e == cudaSuccess) e = configure_step_t<R, AQUA_ACT_F32X2>();
-    return e;
-}
-cudaError_t configure_kernels(int precision) {
-    return precision == AQUA_F64 ? configure_step_r<double>() : configure_step_r<float>();
-}
-
-template <typename R, int ACT> static const void* step_fn() {
-    return reinterpret_cast<const void*>(&step_kernel<R, ACT, false>);
-}
-template <typename R> static const void* step_fn_r(int act) {
-    switch (act) {
-        case AQUA_ACT_I32: return step_fn<R, AQUA_ACT_I32>();
-        case AQUA_ACT_I64: return step_fn<R, AQUA_ACT_I64>();
-        case AQUA_ACT_U8: return step_fn<R, AQUA_ACT_U8>();
-        case AQUA_ACT_F32X2: return step_fn<R, AQUA_ACT_F32X2>();
-        default: return nullptr;
-    }
-}
-cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm) {
-    const void* fn = precision == AQUA_F64 ? step_fn_r<double>(action_dtype) : step_fn_r<float>(action_dtype);
-    if (fn == nullptr) return cudaErrorInvalidValue;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, kStageBytes);
-}
-
-cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    if (precision == AQUA_F64) {
-        if (continuous) rollout_kernel<double, true><<<g.blocks, g.threads, 0, s>>>(a);
-        else rollout_kernel<double, false><<<g.blocks, g.threads, 0, s>>>(a);
-    } else {
-        if (continuous) rollout_kernel<float, true><<<g.blocks, g.threads, 0, s>>>(a);
-        else rollout_kernel<float, false><<<g.blocks, g.threads, 0, s>>>(a);
-    }
-    return cudaGetLastError();
-}
-cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* blocks_per_sm) {
-    const void* fn;
+template <typename Op> static cudaError_t dispatch_step(int precision, int v, int act, const Op& op) {
     if (precision == AQUA_F64)
-        fn = continuous ? reinterpret_cast<const void*>(&rollout_kernel<double, true>)
-                        : reinterpret_cast<const void*>(&rollout_kernel<double, false>);
-    else
-        fn = continuous ? reinterpret_cast<const void*>(&rollout_kernel<float, true>)
-                        : reinterpret_cast<const void*>(&rollout_kernel<float, false>);
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, threads, 0);
+        return v == 1 ? dispatch_act<double, 1>(act, op) : dispatch_act<double, Prec<double>::V>(act, op);
+    return v == 1 ? dispatch_act<float, 1>(act, op) : dispatch_act<float, Prec<float>::V>(act, op);
+}
+template <typename Op> static cudaError_t dispatch_rollout(int precision, int v, int continuous, const Op& op) {
+    if (precision == AQUA_F64) {
+        if (v == 1) return continuous ? op.template run<double, 1, true>() : op.template run<double, 1, false>();
+        return continuous ? op.template run<double, Prec<double>::V, true>() : op.template run<double, Prec<double>::V, false>();
+    }
+    if (v == 1) return continuous ? op.template run<float, 1, true>() : op.template run<float, 1, false>();
+    return continuous ? op.template run<float, Prec<float>::V, true>() : op.template run<float, Prec<float>::V, false>();
+}
+
+struct StepLaunchOp {
+    const StepArgs& a;
+    LaunchGeom g;
+    cudaStream_t s;
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        const size_t smem = V > 1 ? kStageBytes : 0;
+        if (a.noise_x != nullptr) step_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
+        else step_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
+        return cudaGetLastError();
+    }
+};
+cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+    return dispatch_step(precision, g.v, action_dtype, StepLaunchOp{a, g, s});
+}
+
+struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limit needs an opt-in
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        cudaError_t e = cudaFuncSetAttribute(step_kernel<R, V, ACT, false>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(step_kernel<R, V, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     kStageBytes);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(step_kernel<R, V, ACT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(step_kernel<R, V, ACT, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared);
+        return e;
+    }
+};
+cudaError_t configure_kernels(int precision) {
+    const int wide = precision == AQUA_F64 ? Prec<double>::V : Prec<float>::V;
+    for (int v : {wide, 1})
+        for (int act = 0; act < 4; ++act) {
+            const cudaError_t e = dispatch_step(precision, v, act, StepConfigureOp{});
+            if (e != cudaSuccess) return e;
+        }
+    return cudaSuccess;
+}
+
+struct StepOccupancyOp {
+    int threads;
+    int* out;
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_kernel<R, V, ACT, false>, threads,
+                                                             V > 1 ? kStageBytes : 0);
+    }
+};
+cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm) {
+    return dispatch_step(precision, v, action_dtype, StepOccupancyOp{threads, blocks_per_sm});
+}
+
+struct RolloutLaunchOp {
+    const StepArgs& a;
+    LaunchGeom g;
+    cudaStream_t s;
+    template <typename R, int V, bool CONT> cudaError_t run() const {
+        rollout_kernel<R, V, CONT><<<g.blocks, g.threads, 0, s>>>(a);
+        return cudaGetLastError();
+    }
+};
+cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
+    return dispatch_rollout(precision, g.v, continuous, RolloutLaunchOp{a, g, s});
+}
+struct RolloutOccupancyOp {
+    int threads;
+    int* out;
+    template <typename R, int V, bool CONT> cudaError_t run() const {
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, rollout_kernel<R, V, CONT>, threads, 0);
+    }
+};
+cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int* blocks_per_sm) {
+    return dispatch_rollout(precision, v, continuous, RolloutOccupancyOp{threads, blocks_per_sm});
 }
 
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -1004,7 +1024,7 @@ void make_philox_keys(uint64_t seed, PhiloxKeys* out) {
 // ------------------------------------------------------------------------------------------
 // host-side obstacle tables (aqua.py:56-68, 373-390)
 // ------------------------------------------------------------------------------------------
-int envs_per_thread_f32() { return Prec<float>::V; }
+int envs_per_thread(int precision) { return precision == AQUA_F64 ? Prec<double>::V : Prec<float>::V; }
 
 size_t obstacle_table_bytes(int precision) {
     return precision == AQUA_F64 ? sizeof(ObstacleTable<double>) : sizeof(ObstacleTable<float>);

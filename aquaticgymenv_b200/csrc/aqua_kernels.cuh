@@ -61,6 +61,7 @@ struct StepArgs {
 struct LaunchGeom {
     int threads;  // per CTA
     int blocks;
+    int v;        // envs per thread: envs_per_thread(precision) (wide) or 1 (narrow, small slabs)
 };
 
 // every launcher returns the cudaError_t of the launch (cudaGetLastError)
@@ -80,10 +81,10 @@ cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int cle
 // per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
 cudaError_t configure_kernels(int precision);
 // occupancy of the step kernel for (precision, action dtype) at `threads` per CTA
-cudaError_t step_occupancy(int precision, int action_dtype, int threads, int* blocks_per_sm);
-cudaError_t rollout_occupancy(int precision, int continuous, int threads, int* blocks_per_sm);
+cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm);
+cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int* blocks_per_sm);
 
-int envs_per_thread_f32();
+int envs_per_thread(int precision);
 
 // host-side construction of the device obstacle tables; `out` sized for the precision
 size_t obstacle_table_bytes(int precision);

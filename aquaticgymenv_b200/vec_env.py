@@ -93,12 +93,14 @@ class AquaVecEnv(object):
       that a slab of a sharded job reproduces the same per-env trajectories as a single-GPU job;
     * ``precision``: ``"float32"`` (throughput layout, 65 B per env-step) or ``"float64"``
       (parity-grade pose);
-    * ``autoreset``: finished envs are reset inside the step kernel (vector-env semantics).
+    * ``autoreset``: finished envs are reset inside the step kernel (vector-env semantics);
+    * ``geometry``: ``"auto"`` (default), or force the ``"wide"`` / ``"narrow"`` kernel family
+      (tests and tuning; results are identical).
     """
 
     def __init__(self, num_envs, continuous=False, obstacles=False, waves=True, random_boat=True,
                  random_goal=True, seed=0, env_id_base=0, device=None, precision="float32",
-                 autoreset=True):
+                 autoreset=True, geometry="auto"):
         self._h = None
         self.lib = N.load()
         if device is None:
@@ -133,6 +135,7 @@ class AquaVecEnv(object):
         cfg.random_boat, cfg.random_goal = int(self.random_boat), int(self.random_goal)
         cfg.precision, cfg.autoreset = self.precision, int(self.autoreset)
         cfg.n_obstacles = self.table.shape[0]
+        cfg.geometry = {"auto": N.GEOM_AUTO, "wide": N.GEOM_WIDE, "narrow": N.GEOM_NARROW}[geometry]
         tab = np.ascontiguousarray(self.table)
         cfg.obstacles = tab.ctypes.data_as(C.POINTER(C.c_double)) if tab.size else None
         cfg.seed, cfg.env_id_base = self.seed, self.env_id_base

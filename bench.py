@@ -404,10 +404,16 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_extras:
         extras = {}
         try:
-            extras["sweep_cuda_graph"] = [
-                {"envs": n, "env_steps_per_s": graph_rate(torch, n, args.seed, args.precision),
-                 "note": "L2-resident, launch-bound; 50 step launches per CUDA graph"}
-                for n in (65536, 1 << 20)]
+            # envs/GPU sweep: 50 step launches per CUDA graph, replayed.
+            # Up to ~2^20 envs the slab (41 B/env of state+outputs) is L2-resident and the step is
+            # launch/latency-bound; from 2^22 it streams from HBM.
+            extras["sweep_cuda_graph"] = []
+            for n in (1 << 16, 1 << 18, 1 << 20, 1 << 22, 1 << 24):
+                r = graph_rate(torch, n, args.seed, args.precision)
+                extras["sweep_cuda_graph"].append({
+                    "envs": n, "env_steps_per_s": r, "us_per_step": 1e6 * n / r,
+                    "hbm_frac_algorithmic": r * BYTES_PER_STEP["discrete_i32"] / 1e9 / peaks()[0],
+                    "regime": "launch/latency-bound, L2-resident" if n <= (1 << 20) else "HBM-streaming"})
             extras["rollout_kernel_env_steps_per_s"] = {
                 str(n): rollout_rate(torch, n, args.seed, args.precision) for n in (65536, 1 << 20, n_local)}
             extras["other_configs"] = [

@@ -46,6 +46,11 @@ typedef enum {
 
 enum { AQUA_F32 = 0, AQUA_F64 = 1 };
 
+/* Kernel family: wide threads own 4 (float) / 2 (double) consecutive envs (16-byte plane accesses,
+ * the bandwidth layout); narrow threads own one env (small, latency-bound slabs).  AUTO picks
+ * narrow below about 300k envs per launch.  Results are identical either way. */
+enum { AQUA_GEOM_AUTO = 0, AQUA_GEOM_WIDE = 1, AQUA_GEOM_NARROW = 2 };
+
 /* element type of the `actions` buffer of aqua_step */
 enum {
     AQUA_ACT_I32 = 0,   /* discrete: int32[N]  action index, aqua.py:33-43,154 */
@@ -100,7 +105,7 @@ typedef struct {
                               hold the first observation of the next episode); 0: the terminal
                               state stays until aqua_reset (the reference's single-env flow) */
     int32_t n_obstacles;   /* 0..AQUA_MAX_OBSTACLES */
-    int32_t _reserved;
+    int32_t geometry;      /* AQUA_GEOM_AUTO (0), or force one kernel family (tests, tuning) */
     /* HOST array [n_obstacles][5] = {cx, cy, type (0 circle / 1 rectangle), a, b}: circle
      * a = radius; rectangle a = width, b = height, centre anchored (aqua.py:56-68,373-390) */
     const double* obstacles;

@@ -29,9 +29,9 @@ def _torch():
     return torch
 
 
-def _make_gpu(g, n, precision, autoreset, base=None):
+def _make_gpu(g, n, precision, autoreset, base=None, geometry="auto"):
     from aquaticgymenv_b200 import AquaVecEnv
-    return AquaVecEnv(n, continuous=bool(g["continuous"]), obstacles=np.asarray(g["table"], np.float64),
+    return AquaVecEnv(n, geometry=geometry, continuous=bool(g["continuous"]), obstacles=np.asarray(g["table"], np.float64),
                       waves=bool(g["waves"]), random_boat=bool(g.get("random_boat", True)),
                       random_goal=bool(g.get("random_goal", True)), seed=int(g.get("seed", 0)),
                       env_id_base=int(g.get("env_id_base", 0)) if base is None else base,
@@ -60,13 +60,17 @@ def _state_err(got, ref):
 
 
 # ------------------------------------------------------------------ single-step goldens
+GEOMETRIES = ["wide", "narrow"]  # both kernel families must pass every parity test
+
+
+@pytest.mark.parametrize("geometry", GEOMETRIES)
 @pytest.mark.parametrize("precision,tol", [("float64", TOL_F64), ("float32", TOL_F32)])
 @pytest.mark.parametrize("name", golden_names(GOLDEN, "step_"))
-def test_single_step_golden(name, precision, tol):
+def test_single_step_golden(name, precision, tol, geometry):
     torch = _torch()
     g = load_golden(GOLDEN, name)
     n = g["state_in"].shape[0]
-    env = _make_gpu(g, n, precision, autoreset=False)
+    env = _make_gpu(g, n, precision, autoreset=False, geometry=geometry)
     st = np.zeros((9, n))
     st[:8] = g["state_in"].T
     env.set_state(st)
@@ -92,13 +96,14 @@ def test_single_step_golden(name, precision, tol):
 
 
 # ------------------------------------------------------------------ golden rollouts, float64
+@pytest.mark.parametrize("geometry", GEOMETRIES)
 @pytest.mark.parametrize("name", golden_names(GOLDEN, "roll_"))
-def test_rollout_golden_f64_free_running(name):
+def test_rollout_golden_f64_free_running(name, geometry):
     """1000-step lock-step with the reference's recorded rollout, resets included: the GPU env
     draws its own noise and reset samples from the Philox streams; nothing is teacher-forced."""
     g = load_golden(GOLDEN, name)
     T, n = g["flags"].shape
-    env = _make_gpu(g, n, "float64", autoreset=False)
+    env = _make_gpu(g, n, "float64", autoreset=False, geometry=geometry)
     env.reset()
     assert np.array_equal(env.get_state().cpu().numpy(), g["init_state"])
     resets = {(int(r[0]), int(r[1])): r for r in g["resets"]}
@@ -148,10 +153,10 @@ def _cfg(name, seed=5, base=0):
     return c
 
 
-def _lockstep(cfg, n, steps, precision, autoreset=True, ragged_check=False):
+def _lockstep(cfg, n, steps, precision, autoreset=True, geometry="auto"):
     """Random-policy lock-step GPU vs oracle with the float32 margin policy; returns counters."""
     torch = _torch()
-    env = _make_gpu(cfg, n, precision, autoreset=autoreset)
+    env = _make_gpu(cfg, n, precision, autoreset=autoreset, geometry=geometry)
     ref = _make_oracle(cfg, n)
     env.reset()
     ref.reset()
@@ -184,28 +189,50 @@ def _lockstep(cfg, n, steps, precision, autoreset=True, ragged_check=False):
     return flips, worst
 
 
+@pytest.mark.parametrize("geometry", GEOMETRIES)
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_lockstep_oracle_f64(name):
-    flips, worst = _lockstep(_cfg(name), 4096, 300, "float64")
+def test_lockstep_oracle_f64(name, geometry):
+    flips, worst = _lockstep(_cfg(name), 4096, 300, "float64", geometry=geometry)
     assert flips == 0
 
 
+@pytest.mark.parametrize("geometry", GEOMETRIES)
 @pytest.mark.parametrize("name", sorted(CONFIGS))
-def test_lockstep_oracle_f32(name):
+def test_lockstep_oracle_f32(name, geometry):
     n, steps = 4096, 300
-    flips, worst = _lockstep(_cfg(name), n, steps, "float32")
+    flips, worst = _lockstep(_cfg(name), n, steps, "float32", geometry=geometry)
     # measured flip rate of the float32 layout: a handful per million env-steps
     assert flips <= max(3, int(2e-5 * n * steps)), flips
 
 
+@pytest.mark.parametrize("geometry", GEOMETRIES)
 @pytest.mark.parametrize("precision", ["float64", "float32"])
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 1023, 1025, 4099])
-def test_ragged_sizes(n, precision):
+def test_ragged_sizes(n, precision, geometry):
     """N not a multiple of the vector width / tile: tails handled, nothing out of bounds."""
-    flips, _ = _lockstep(_cfg("v1_discrete", seed=9, base=77), n, 40, precision)
+    flips, _ = _lockstep(_cfg("v1_discrete", seed=9, base=77), n, 40, precision, geometry=geometry)
     assert flips <= 1
-    flips, _ = _lockstep(_cfg("v2_continuous", seed=9, base=77), n, 40, precision)
+    flips, _ = _lockstep(_cfg("v2_continuous", seed=9, base=77), n, 40, precision, geometry=geometry)
     assert flips <= 1
+
+
+def test_wide_and_narrow_kernels_agree_bitwise():
+    """The two kernel families run the same arithmetic: identical state, rewards and statistics,
+    also across the auto-selection threshold (a ragged slab large enough for the wide path)."""
+    cfg = _cfg("v1_discrete", seed=12, base=5)
+    n = 400003
+    outs = []
+    for geometry in ("wide", "narrow", "auto"):
+        env = _make_gpu(cfg, n, "float32", autoreset=True, geometry=geometry)
+        env.reset()
+        for t in range(30):
+            env.step_flags(env.random_actions(t))
+        outs.append((env.get_state().cpu().numpy(), env.reward.cpu().numpy().copy(), env.flags.cpu().numpy().copy(),
+                     env.stats()))
+        env.close()
+    for o in outs[1:]:
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert np.array_equal(o[2], outs[0][2]) and o[3] == outs[0][3]
 
 
 def test_no_autoreset_terminal_state_stays():
@@ -247,13 +274,14 @@ def test_statistics_match_oracle_counts():
     env.close()
 
 
-def test_action_dtypes_agree():
+@pytest.mark.parametrize("geometry", GEOMETRIES)
+def test_action_dtypes_agree(geometry):
     torch = _torch()
     cfg = _cfg("v1_discrete", seed=4)
     n = 5000
     outs = []
     for dt in (torch.int32, torch.int64, torch.uint8):
-        env = _make_gpu(cfg, n, "float32", autoreset=True)
+        env = _make_gpu(cfg, n, "float32", autoreset=True, geometry=geometry)
         env.reset()
         for t in range(50):
             act = env.random_actions(t).to(dt)
@@ -304,14 +332,15 @@ def test_random_actions_follow_the_oracle_stream():
     cenv.close()
 
 
+@pytest.mark.parametrize("geometry", GEOMETRIES)
 @pytest.mark.parametrize("precision", ["float64", "float32"])
 @pytest.mark.parametrize("name", ["v1_discrete", "dense64_continuous"])
-def test_rollout_kernel_equals_stepwise(name, precision):
+def test_rollout_kernel_equals_stepwise(name, precision, geometry):
     """K steps fused in one launch == K single-step launches fed by random_actions: bitwise."""
     cfg = _cfg(name, seed=31, base=1000)
     n, K = 10000, 150
-    a = _make_gpu(cfg, n, precision, autoreset=True)
-    b = _make_gpu(cfg, n, precision, autoreset=True)
+    a = _make_gpu(cfg, n, precision, autoreset=True, geometry=geometry)
+    b = _make_gpu(cfg, n, precision, autoreset=True, geometry=geometry)
     a.reset()
     b.reset()
     for t in range(K):
