@@ -130,6 +130,23 @@ __device__ __forceinline__ ActVals<ACT, V> fetch_actions(const void* src_, int n
     return out;
 }
 
+// the same from the raw bytes of the thread's actions (as staged in shared memory)
+template <int ACT, int V, int NW>
+__device__ __forceinline__ ActVals<ACT, V> actions_from_raw(const uint32_t (&raw)[NW]) {
+    ActVals<ACT, V> out;
+    if constexpr (ACT == AQUA_ACT_F32X2 || ACT == AQUA_ACT_I32) {
+#pragma unroll
+        for (int j = 0; j < ActVals<ACT, V>::N; ++j) out.w[j] = raw[j];
+    } else if constexpr (ACT == AQUA_ACT_I64) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) out.w[j] = raw[2 * j + 1] ? 0xffffffffu : raw[2 * j];
+    } else {
+#pragma unroll
+        for (int j = 0; j < V; ++j) out.w[j] = (raw[0] >> (8 * j)) & 0xffu;
+    }
+    return out;
+}
+
 template <typename R, int ACT, int V>
 __device__ __forceinline__ void decode_drives(const ActVals<ACT, V>& a, Drive<R> (&dr)[V], uint32_t& bad) {
     if constexpr (ACT == AQUA_ACT_F32X2) {
@@ -170,15 +187,16 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N> __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
-constexpr int kStageSlot = 16;                              // bytes per thread per slot per stage
 #ifndef AQUA_STAGES
 #define AQUA_STAGES 2
 #endif
 constexpr int kStages = AQUA_STAGES;                        // 2: double buffer; 1: refill after the reads
-constexpr int kStageSlots = AQUA_N_PLANES + 2;              // 8 state planes + up to 32 bytes of actions
-constexpr int kStagePitch = kMaxThreads * kStageSlot;       // bytes between slots: independent of blockDim,
-                                                            // so that every slot offset is an immediate
-constexpr int kStageBytes = kStages * kStageSlots * kStagePitch;  // 80 KiB of dynamic shared memory
+constexpr int kStageSlots = AQUA_N_PLANES + 2;              // 8 state planes + up to two slots of actions
+// one slot = the bytes one thread moves per plane (16 at V = 4 float / V = 2 double); slots are
+// kMaxThreads apart whatever blockDim is, so that every slot offset is an immediate
+template <typename R, int V> constexpr int stage_slot() { return (int)sizeof(R) * V; }
+template <typename R, int V> constexpr int stage_pitch() { return kMaxThreads * stage_slot<R, V>(); }
+template <typename R, int V> constexpr int stage_bytes() { return V > 1 ? kStages * kStageSlots * stage_pitch<R, V>() : 0; }
 
 // ------------------------------------------------------------------------------------------
 // per-thread episode statistics and their reduction
@@ -365,48 +383,41 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
     const int64_t warp_off = (int64_t)(threadIdx.x & ~31u) * V;  // first env of this warp within the tile
 
     // this thread's staging slots: [stage][plane][thread] x 16 bytes (conflict-free 16-byte LDS)
-    unsigned char* const my_stage = s_stage + (size_t)threadIdx.x * kStageSlot;
-    auto slot = [&](int stage, int pl) { return my_stage + (size_t)stage * (kStageSlots * kStagePitch) + pl * kStagePitch; };
+    constexpr int kSlot = stage_slot<R, V>(), kPitch = stage_pitch<R, V>();
+    unsigned char* const my_stage = s_stage + (size_t)threadIdx.x * kSlot;
+    auto slot = [&](int stage, int pl) { return my_stage + (size_t)stage * (kStageSlots * kPitch) + pl * kPitch; };
     // actions ride along when their per-thread footprint is a legal cp.async size
     constexpr int kActBytes = act_bytes<ACT, V>();
-    constexpr bool kActStaged = kActBytes == 4 || kActBytes == 8 || kActBytes == 16 || kActBytes == 32;
+    constexpr bool kActStaged = kActBytes >= 4;                       // 4, 8, 16 or 32
+    constexpr int kActPiece = kActBytes < kSlot ? kActBytes : kSlot;  // bytes per action slot
+    constexpr int kActPieces = kActBytes >= 4 ? kActBytes / kActPiece : 0;
+    static_assert(kActPieces <= 2, "the actions fit two slots");
     // narrow threads (V = 1) serve small, latency-bound slabs with one tile per thread: nothing to
     // pipeline, so they load directly and the kernel is launched without the staging buffer
     constexpr bool kStaging = V > 1;
     auto prefetch = [&](int stage, int64_t b) {  // the 8 plane slices + actions of the V envs starting at b
         const R* g = pl0 + b;  // running pointer: one 64-bit add per plane
 #pragma unroll
-        for (int pl = 0; pl < 7; ++pl, g += ld) cp_async<(int)sizeof(R) * V>(slot(stage, pl), g);
+        for (int pl = 0; pl < 7; ++pl, g += ld) cp_async<kSlot>(slot(stage, pl), g);
         cp_async<4 * V>(slot(stage, AQUA_PLANE_TIME), ptw_ + b);  // uint32 plane: its own index scale
         if constexpr (kActStaged) {
             const char* a = reinterpret_cast<const char*>(act_ptr<ACT>(p.actions, b));
-            if constexpr (kActBytes == 32) {
-                cp_async<16>(slot(stage, AQUA_N_PLANES), a);
-                cp_async<16>(slot(stage, AQUA_N_PLANES + 1), a + 16);
-            } else {
-                cp_async<kActBytes>(slot(stage, AQUA_N_PLANES), a);
-            }
+#pragma unroll
+            for (int q = 0; q < kActPieces; ++q) cp_async<kActPiece>(slot(stage, AQUA_N_PLANES + q), a + q * kActPiece);
         }
     };
     auto staged_actions = [&](int stage) {
-        if constexpr (kActBytes == 32) {  // the two halves sit in different slots
-            ActVals<ACT, V> out;
-            const Pack<uint32_t, 4> lo = *reinterpret_cast<const Pack<uint32_t, 4>*>(slot(stage, AQUA_N_PLANES));
-            const Pack<uint32_t, 4> hi = *reinterpret_cast<const Pack<uint32_t, 4>*>(slot(stage, AQUA_N_PLANES + 1));
-            uint32_t raw[8];
+        constexpr int kWords = kActBytes >= 4 ? kActBytes / 4 : 1;
+        constexpr int kPieceWords = kActPiece >= 4 ? kActPiece / 4 : 1;
+        uint32_t raw[kWords] = {};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { raw[j] = lo.v[j]; raw[4 + j] = hi.v[j]; }
-            if constexpr (ACT == AQUA_ACT_F32X2) {
+        for (int q = 0; q < kActPieces; ++q) {
+            const Pack<uint32_t, kPieceWords> pk =
+                *reinterpret_cast<const Pack<uint32_t, kPieceWords>*>(slot(stage, AQUA_N_PLANES + q));
 #pragma unroll
-                for (int j = 0; j < 2 * V; ++j) out.w[j] = raw[j];
-            } else {  // int64 x 4: (lo, hi) word pairs
-#pragma unroll
-                for (int j = 0; j < V; ++j) out.w[j] = raw[2 * j + 1] ? 0xffffffffu : raw[2 * j];
-            }
-            return out;
-        } else {
-            return fetch_actions<ACT, V, true>(slot(stage, AQUA_N_PLANES), V);
+            for (int i = 0; i < kPieceWords; ++i) raw[q * kPieceWords + i] = pk.v[i];
         }
+        return actions_from_raw<ACT, V, kWords>(raw);
     };
 
     ThreadStats st;
@@ -856,7 +867,7 @@ struct StepLaunchOp {
     LaunchGeom g;
     cudaStream_t s;
     template <typename R, int V, int ACT> cudaError_t run() const {
-        const size_t smem = V > 1 ? kStageBytes : 0;
+        const size_t smem = stage_bytes<R, V>();
         if (a.noise_x != nullptr) step_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
         else step_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
         return cudaGetLastError();
@@ -869,10 +880,10 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limit needs an opt-in
     template <typename R, int V, int ACT> cudaError_t run() const {
         cudaError_t e = cudaFuncSetAttribute(step_kernel<R, V, ACT, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kStageBytes);
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes<R, V>());
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(step_kernel<R, V, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     kStageBytes);
+                                     stage_bytes<R, V>());
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(step_kernel<R, V, ACT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
@@ -897,7 +908,7 @@ struct StepOccupancyOp {
     int* out;
     template <typename R, int V, int ACT> cudaError_t run() const {
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_kernel<R, V, ACT, false>, threads,
-                                                             V > 1 ? kStageBytes : 0);
+                                                             stage_bytes<R, V>());
     }
 };
 cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm) {
