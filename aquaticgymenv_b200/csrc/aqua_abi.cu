@@ -44,6 +44,7 @@ struct DeviceGuard {
 };
 
 constexpr int kHostStreams = 4;       // host-step pipeline depth
+constexpr int kTileCounters = 64;     // launches that may be in flight at once on one handle
 constexpr int64_t kHostChunkMin = 64 * 1024;
 
 size_t elem_size(int precision) { return precision == AQUA_F64 ? 8 : 4; }
@@ -71,6 +72,8 @@ struct aqua_env {
     double* d_tab64 = nullptr;
     unsigned long long* d_slots = nullptr;
     int64_t* d_stats_out = nullptr;
+    uint32_t* d_tile_ctr = nullptr;  // kTileCounters pairs, handed out round robin per launch
+    unsigned launch_seq = 0;
     aqua::World world;
     // resident CTAs per SM, queried once at create: [action dtype][narrow (V = 1, 128 threads) /
     // wide (256 threads)]
@@ -88,9 +91,10 @@ struct aqua_env {
 
 namespace {
 
-aqua::StepArgs base_args(const aqua_env* env) {
+aqua::StepArgs base_args(aqua_env* env) {
     aqua::StepArgs a;
     memset(&a, 0, sizeof a);
+    a.tile_ctr = env->d_tile_ctr + 2 * (env->launch_seq++ % kTileCounters);
     a.w = env->world;
     a.planes = env->state;
     a.ld = env->ld;
@@ -253,6 +257,8 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     AQ_CREATE(cudaMalloc(&env->d_slots, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
     AQ_CREATE(cudaMemset(env->d_slots, 0, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
     AQ_CREATE(cudaMalloc(&env->d_stats_out, sizeof(int64_t) * AQUA_N_STATS));
+    AQ_CREATE(cudaMalloc(&env->d_tile_ctr, sizeof(uint32_t) * 2 * kTileCounters));
+    AQ_CREATE(cudaMemset(env->d_tile_ctr, 0, sizeof(uint32_t) * 2 * kTileCounters));
 
     aqua::World& w = env->world;
     memset(&w, 0, sizeof w);
@@ -283,6 +289,11 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
         for (int act = 0; act < 4; ++act) {
             AQ_CREATE(aqua::step_occupancy(cfg->precision, v, act, threads, &env->occ_step[act][ti]));
             env->occ_step[act][ti] = std::max(env->occ_step[act][ti], 1);
+            if (ti == 1) {  // wide slabs run the streaming kernel where there is one: size the grid for it
+                int occ = 0;
+                AQ_CREATE(aqua::stream_occupancy(cfg->precision, act, cfg->waves != 0, threads, &occ));
+                if (occ > 0) env->occ_step[act][ti] = occ;
+            }
         }
         AQ_CREATE(aqua::rollout_occupancy(cfg->precision, v, cfg->continuous, threads, &env->occ_rollout[ti]));
         env->occ_rollout[ti] = std::max(env->occ_rollout[ti], 1);
@@ -317,6 +328,7 @@ int aqua_destroy(aqua_env* env) {
     if (env->d_tab64) keep(cudaFree(env->d_tab64));
     if (env->d_slots) keep(cudaFree(env->d_slots));
     if (env->d_stats_out) keep(cudaFree(env->d_stats_out));
+    if (env->d_tile_ctr) keep(cudaFree(env->d_tile_ctr));
     delete env;
     if (first != cudaSuccess) return fail(AQUA_ERR_CUDA, "aqua_destroy: %s", cudaGetErrorString(first));
     return AQUA_OK;

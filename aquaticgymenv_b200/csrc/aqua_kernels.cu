@@ -293,20 +293,27 @@ __device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g
 // ------------------------------------------------------------------------------------------
 constexpr int kResetGroups = 32 / kCoopLanes;
 template <int V> struct WarpResetQueue {
-    uint32_t rel[32 * V + kResetGroups];
+    uint32_t rel[32 * V + kResetGroups];  // env index relative to env_begin
+    uint32_t tw[32 * V + kResetGroups];   // its terminal time word (episode, length)
 };
 
 // fw: flags of the lane's V envs, one byte each (0 for padding / inactive lanes); rel_base: index
-// of the lane's first env relative to env_begin.  Returns the new queue length.
+// of the lane's first env relative to env_begin; tw: the envs' time words after the step.
+// Returns the new queue length.
 template <int V>
-__device__ __forceinline__ int reset_queue_push(uint32_t* wq, int n, uint32_t fw, uint32_t rel_base) {
+__device__ __forceinline__ int reset_queue_push(WarpResetQueue<V>& wq, int n, uint32_t fw, uint32_t rel_base,
+                                                const uint32_t (&tw)[V]) {
     const unsigned full = 0xffffffffu;
     const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const bool d = ((fw >> (8 * j)) & 1u) != 0u;
         const unsigned mj = __ballot_sync(full, d);
-        if (d) wq[n + __popc(mj & lt)] = rel_base + (uint32_t)j;
+        if (d) {
+            const int at = n + __popc(mj & lt);
+            wq.rel[at] = rel_base + (uint32_t)j;
+            wq.tw[at] = tw[j];
+        }
         n += __popc(mj);
     }
     return n;
@@ -314,21 +321,21 @@ __device__ __forceinline__ int reset_queue_push(uint32_t* wq, int n, uint32_t fw
 
 // Resets queued envs in passes of kResetGroups, from the tail, while at least `min_batch` are
 // queued (min_batch = kResetGroups: full passes only; 1: flush).  Returns the new queue length.
-template <typename R>
+template <typename R, int V>
 __device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const ObstacleTable<R>& tab,
-                                                 const uint32_t* wq, int n, int min_batch, uint32_t& length_sum) {
+                                                 const WarpResetQueue<V>& wq, int n, int min_batch, uint32_t& length_sum) {
     const unsigned lane = threadIdx.x & 31u;
     const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
     uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
     const int grp = (int)(lane / kCoopLanes);
     const bool leader = (lane % kCoopLanes) == 0u;
-    __syncwarp();  // queue entries and the owners' stores are visible to the whole warp
+    __syncwarp();  // queue entries are visible to the whole warp
     while (n >= min_batch && n > 0) {
         const int take = min(n, kResetGroups);
         const int first = n - take;
         const bool valid = grp < take;
-        const int64_t i = p.env_begin + (int64_t)(valid ? wq[first + grp] : 0u);
-        const uint32_t tw = valid ? ptw[i] : 0u;
+        const int64_t i = p.env_begin + (int64_t)(valid ? wq.rel[first + grp] : 0u);
+        const uint32_t tw = valid ? wq.tw[first + grp] : 0u;
         const uint32_t ep = ((tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
         const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
         const CoopResetResult rr = coop_reset<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
@@ -421,7 +428,7 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
     };
 
     ThreadStats st;
-    uint32_t* const wq = s_wq[threadIdx.x >> 5].rel;
+    WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
     int n_queued = 0;  // warp-uniform
 
     int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs;
@@ -464,7 +471,7 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
         }
         uint32_t fw = 0u;
         Pack<R, V> vx, vy, vth, vgx, vgy, vwx, vwy;
-        Pack<uint32_t, V> vtw;
+        Pack<uint32_t, V> vtw, otw;
         if (staged) {
             vx = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_X));
             vy = *reinterpret_cast<const Pack<R, V>*>(slot(sg, AQUA_PLANE_Y));
@@ -523,7 +530,6 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
 
             Pack<R, V> vrew, ox, oy, oth, owx, owy;
             Pack<uint8_t, V> vfl;
-            Pack<uint32_t, V> otw;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 R reward;
@@ -568,13 +574,13 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
         }
         staged = next_staged;
         if (autoreset && __any_sync(0xffffffffu, fw != 0u)) {
-            n_queued = reset_queue_push<V>(wq, n_queued, fw, (uint32_t)(base - p.env_begin));
+            n_queued = reset_queue_push<V>(wq, n_queued, fw, (uint32_t)(base - p.env_begin), otw.v);
             if (n_queued >= kResetGroups)
-                n_queued = reset_queue_drain<R>(p, tab, wq, n_queued, kResetGroups, st.length);
+                n_queued = reset_queue_drain<R, V>(p, tab, wq, n_queued, kResetGroups, st.length);
         }
     }
     cp_async_wait<0>();
-    if (autoreset) reset_queue_drain<R>(p, tab, wq, n_queued, 1, st.length);  // flush the remainder
+    if (autoreset) reset_queue_drain<R, V>(p, tab, wq, n_queued, 1, st.length);  // flush the remainder
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
 }
@@ -657,16 +663,14 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) rollout_
                 }
                 fw = flags_word<V>(vfl);
                 st.add_flags(fw, nvalid);
-                if (fw != 0u) {  // rare: publish the terminal time word for phase B
-#pragma unroll
-                    for (int j = 0; j < V; ++j)
-                        if ((fw >> (8 * j)) & 1u) ptw_[base + j] = e[j].tw;
-                }
             }
             if (__any_sync(0xffffffffu, fw != 0u)) {
-                uint32_t* const wq = s_wq[threadIdx.x >> 5].rel;
-                const int n_queued = reset_queue_push<V>(wq, 0, fw, (uint32_t)(base - p.env_begin));
-                reset_queue_drain<R>(p, tab, wq, n_queued, 1, st.length);  // the next step needs the fresh state
+                WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
+                uint32_t tws[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) tws[j] = (nvalid > 0) ? e[j].tw : 0u;
+                const int n_queued = reset_queue_push<V>(wq, 0, fw, (uint32_t)(base - p.env_begin), tws);
+                reset_queue_drain<R, V>(p, tab, wq, n_queued, 1, st.length);  // the next step needs the fresh state
                 if (fw != 0u) {  // pick the fresh episode up from the planes
 #pragma unroll
                     for (int j = 0; j < V; ++j)
@@ -705,6 +709,277 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) rollout_
     }
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1s: the streaming form of K1 -- what large slabs run.  Same arithmetic as step_kernel (it
+// inlines the same move_env / finish_env / obstacle_clearance, hence the same results bit for
+// bit), without everything a full warp of full threads does not need:
+//   * the launch covers whole warps only (n_stream is a multiple of 32 V; launch_step() gives the
+//     few remaining envs to step_kernel), so there are no tail guards;
+//   * one 32-bit env index, base pointers of the planes in the constant bank (one IMAD.WIDE per
+//     address), 32-bit shared-memory addresses for the staging slots;
+//   * `waves` is a template parameter, and the Philox2x32 chains of the thread's V envs are
+//     advanced round by round side by side (V independent multiply chains in flight);
+//   * the discrete drive is one 16-byte shared-memory read of a 3-entry table.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <int BYTES> __device__ __forceinline__ void cp_async_s(uint32_t d, const void* gsrc) {
+    if constexpr (BYTES == 16)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+    else if constexpr (BYTES == 8)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc) : "memory");
+    else {
+        static_assert(BYTES == 4, "cp.async moves 4, 8 or 16 bytes");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(gsrc) : "memory");
+    }
+}
+template <int BYTES> __device__ __forceinline__ void lds_words(uint32_t a, uint32_t (&w)[BYTES / 4]) {
+    if constexpr (BYTES == 16)
+        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];\n" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "r"(a));
+    else if constexpr (BYTES == 8)
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];\n" : "=r"(w[0]), "=r"(w[1]) : "r"(a));
+    else {
+        static_assert(BYTES == 4, "staging slots hold 4, 8 or 16 bytes");
+        asm volatile("ld.shared.u32 %0, [%1];\n" : "=r"(w[0]) : "r"(a));
+    }
+}
+template <typename T, int V> __device__ __forceinline__ Pack<T, V> lds_pack(uint32_t a) {
+    uint32_t w[sizeof(T) * V / 4];
+    lds_words<(int)sizeof(T) * V>(a, w);
+    Pack<T, V> out;
+    memcpy(&out, w, sizeof(T) * V);
+    return out;
+}
+
+// wave increments of V consecutive envs (ids env_id .. env_id + V - 1): draw_wave_noise() for
+// each, the ten rounds of the V counters interleaved
+template <int V>
+__device__ __forceinline__ void draw_wave_noise_v(const PhiloxKeys& keys, uint32_t env_id, const uint32_t (&tw)[V],
+                                                  float (&nx)[V], float (&ny)[V]) {
+    uint32_t c0[V], c1[V];
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        c0[j] = env_id + (uint32_t)j;
+        c1[j] = tw[j];
+    }
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const unsigned long long pr = (unsigned long long)0xD256D193u * c0[j];
+            const uint32_t n0 = (uint32_t)(pr >> 32) ^ c1[j] ^ keys.noise[r];
+            c1[j] = (uint32_t)pr;
+            c0[j] = n0;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        nx[j] = draw_noise(c0[j]);
+        ny[j] = draw_noise(c1[j]);
+    }
+}
+
+template <typename R> struct alignas(16) DriveSlot {
+    R phi, h, chord, pad;
+};
+
+template <int ACT, int V> constexpr bool stream_supported() {
+    constexpr int b = act_bytes<ACT, V>();
+    return V > 1 && (b == 4 || b == 8 || b == 16 || b == 32);
+}
+
+template <typename R, int V, int ACT, bool WAVES>
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(const __grid_constant__ StepArgs p) {
+    __shared__ ObstacleTable<R> tab;
+    __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
+    __shared__ DriveSlot<R> s_drive[3];
+    stage_table<R>(tab, p.w.tab, p.w.k_obst);
+    if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
+        const Drive<R> d = drive_from_index<R>(threadIdx.x);
+        s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
+    }
+    __syncthreads();
+
+    constexpr int kSlot = stage_slot<R, V>(), kPitch = stage_pitch<R, V>();
+    constexpr int kStage = kStageSlots * kPitch;
+    constexpr int kActBytes = act_bytes<ACT, V>();
+    constexpr int kActPiece = kActBytes < 16 ? kActBytes : 16;
+    constexpr int kActPieces = kActBytes / kActPiece;
+    constexpr int kActWords = kActBytes / 4;
+    static_assert(stream_supported<ACT, V>() && kSlot == 16 && kStages == 2, "streaming kernel layout");
+
+    const uint32_t n = p.n_stream;
+    const bool autoreset = p.w.autoreset != 0;
+    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
+    uint32_t s_cur = smem_u32(s_stage) + threadIdx.x * kSlot, s_nxt = s_cur + kStage;
+
+    // the 8 plane slices + actions of the V envs starting at (relative) env index i
+    auto prefetch = [&](uint32_t s, uint32_t i) {
+#pragma unroll
+        for (int pl = 0; pl < 7; ++pl) cp_async_s<kSlot>(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R));
+        cp_async_s<4 * V>(s + AQUA_PLANE_TIME * kPitch, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4);
+#pragma unroll
+        for (int q = 0; q < kActPieces; ++q)
+            cp_async_s<kActPiece>(s + (AQUA_N_PLANES + q) * kPitch, p.act0 + (size_t)i * (kActBytes / V) + q * kActPiece);
+    };
+
+    ThreadStats st;
+    WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
+    int n_queued = 0;  // warp-uniform
+
+    // Work distribution: a warp tile is 32 V consecutive envs.  Every warp starts with three
+    // statically assigned tiles and then claims further tiles from a global counter, one claim per
+    // tile, issued a whole tile ahead of its use: SMs do not run at the same speed (distance to
+    // the memory partitions), and a static partition makes the kernel as slow as its slowest SM.
+    // Two staging buffers, prefetch distance two tiles: a buffer is refilled (with the tile after
+    // next) as soon as its slices have been read into registers, so every copy has two tile
+    // times to land.
+    const uint32_t lane_off = (threadIdx.x & 31u) * V;
+    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);  // of the launch
+    constexpr uint32_t kWarpTile = 32u * V;
+    uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kWarpTile + lane_off;  // this tile
+    uint32_t i1 = i + n_warps * kWarpTile;   // the next one (in flight)
+    uint32_t i2 = i1 + n_warps * kWarpTile;  // the one after (to be prefetched)
+    if (i < n) prefetch(s_cur, i);
+    cp_async_commit();
+    if (i1 < n) prefetch(s_nxt, i1);
+    cp_async_commit();
+    for (;;) {
+        const bool live = i < n;  // warp-uniform: n is a multiple of 32 V
+        uint32_t fw = 0u;
+        Pack<uint32_t, V> otw;
+        uint32_t claim = 0u;
+        const uint32_t i_done = i;
+        if (live) {
+            cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
+
+            const Pack<R, V> vx = lds_pack<R, V>(s_cur + AQUA_PLANE_X * kPitch);
+            const Pack<R, V> vy = lds_pack<R, V>(s_cur + AQUA_PLANE_Y * kPitch);
+            const Pack<R, V> vth = lds_pack<R, V>(s_cur + AQUA_PLANE_THETA * kPitch);
+            const Pack<R, V> vgx = lds_pack<R, V>(s_cur + AQUA_PLANE_GOAL_X * kPitch);
+            const Pack<R, V> vgy = lds_pack<R, V>(s_cur + AQUA_PLANE_GOAL_Y * kPitch);
+            const Pack<R, V> vwx = lds_pack<R, V>(s_cur + AQUA_PLANE_WAVE_X * kPitch);
+            const Pack<R, V> vwy = lds_pack<R, V>(s_cur + AQUA_PLANE_WAVE_Y * kPitch);
+            const Pack<uint32_t, V> vtw = lds_pack<uint32_t, V>(s_cur + AQUA_PLANE_TIME * kPitch);
+            uint32_t araw[kActWords];
+#pragma unroll
+            for (int q = 0; q < kActPieces; ++q) {
+                uint32_t w[kActPiece / 4];
+                lds_words<kActPiece>(s_cur + (AQUA_N_PLANES + q) * kPitch, w);
+#pragma unroll
+                for (int k = 0; k < kActPiece / 4; ++k) araw[q * (kActPiece / 4) + k] = w[k];
+            }
+            const ActVals<ACT, V> act = actions_from_raw<ACT, V, kActWords>(araw);
+            const bool more = i2 < n;  // warp-uniform
+            if (more) {
+                prefetch(s_cur, i2);  // refill the buffer just read
+                if ((threadIdx.x & 31u) == 0u) claim = atomicAdd(p.tile_ctr, 1u);  // consumed at the end of this tile
+            }
+            cp_async_commit();
+
+            Drive<R> dr[V];
+            if constexpr (ACT == AQUA_ACT_F32X2) {
+                decode_drives<R, ACT, V>(act, dr, st.bad);
+            } else {
+                uint32_t worst = 0u;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    worst = max(worst, act.w[j]);
+                    const DriveSlot<R> d = s_drive[min(act.w[j], 2u)];  // outside {0,1,2}: full throttle
+                    dr[j].phi = d.phi;
+                    dr[j].h = d.h;
+                    dr[j].chord = d.chord;
+                }
+                if (worst > 2u) {  // rare
+#pragma unroll
+                    for (int j = 0; j < V; ++j) st.bad += (act.w[j] > 2u) ? 1u : 0u;
+                }
+            }
+
+            float nx[V], ny[V];
+            if constexpr (WAVES) {
+                draw_wave_noise_v<V>(p.w.keys, p.env_id0 + i, vtw.v, nx, ny);
+            } else {
+#pragma unroll
+                for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
+            }
+
+            EnvState<R> e[V];
+            MoveTmp<R> m[V];
+            R pxn[V], pyn[V], clr[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
+                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
+                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
+                e[j].tw = vtw.v[j];
+                move_env<R>(e[j], dr[j], (R)nx[j], (R)ny[j], WAVES, m[j]);
+                pxn[j] = e[j].x;
+                pyn[j] = e[j].y;
+                clr[j] = R(kClearFar);
+            }
+            obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
+
+            Pack<R, V> vrew, ox, oy, oth, owx, owy;
+            Pack<uint8_t, V> vfl;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                R reward;
+                const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
+                vrew.v[j] = reward;
+                vfl.v[j] = (uint8_t)f;
+                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
+            }
+            fw = flags_word<V>(vfl);
+            st.add_flags(fw, V);
+#pragma unroll
+            for (int j = 0; j < V; ++j) st.add_env<R>(vrew.v[j]);
+            if (!autoreset) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) st.add_length(vfl.v[j], otw.v[j] & kTimeMask);
+            }
+
+            // ---- stores (the goal only changes at reset: phase B writes it) ----
+            const size_t off = (size_t)i * sizeof(R);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off), ox);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_Y]) + off), oy);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_THETA]) + off), oth);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_X]) + off), owx);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_Y]) + off), owy);
+            st_pack<uint32_t, V>(reinterpret_cast<uint32_t*>(const_cast<char*>(p.pl0[AQUA_PLANE_TIME]) + (size_t)i * 4), otw);
+            st_pack<R, V>(reinterpret_cast<R*>(p.rew0 + off), vrew);
+            st_pack<uint8_t, V>(p.flg0 + i, vfl);
+
+            const uint32_t t = s_cur;
+            s_cur = s_nxt;
+            s_nxt = t;
+            i = i1;
+            i1 = i2;
+            i2 = more ? (3u * n_warps + __shfl_sync(0xffffffffu, claim, 0)) * kWarpTile + lane_off : n;
+        }
+        if (autoreset) {  // phase B, warp-collective
+            if (live && __any_sync(0xffffffffu, fw != 0u)) n_queued = reset_queue_push<V>(wq, n_queued, fw, i_done, otw.v);
+            const int need = live ? kResetGroups : 1;  // full passes only; the rest is flushed at the end
+            if (n_queued >= need) n_queued = reset_queue_drain<R, V>(p, tab, wq, n_queued, need, st.length);
+        }
+        if (!live) break;
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    flush_stats(st, s_stats, p.stats);
+    if (threadIdx.x == 0) {  // the last CTA to finish rearms the tile counter for the next launch
+        __threadfence();
+        if (atomicAdd(p.tile_ctr + 1, 1u) == gridDim.x - 1u) {
+            p.tile_ctr[0] = 0u;
+            p.tile_ctr[1] = 0u;
+            __threadfence();
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -873,8 +1148,70 @@ struct StepLaunchOp {
         return cudaGetLastError();
     }
 };
+// streaming kernel: wide threads only; (precision, action dtype) pairs whose per-thread action
+// footprint cp.async cannot move (double + uint8: 2 bytes) stay with step_kernel
+struct StreamLaunchOp {
+    const StepArgs& a;
+    LaunchGeom g;
+    cudaStream_t s;
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        if constexpr (stream_supported<ACT, V>()) {
+            const size_t smem = stage_bytes<R, V>();
+            if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
+            else step_stream_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
+            return cudaGetLastError();
+        } else {
+            return cudaErrorNotSupported;
+        }
+    }
+};
+struct StreamSupportedOp {
+    bool* out;
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        *out = stream_supported<ACT, V>();
+        return cudaSuccess;
+    }
+};
+static bool has_stream_kernel(int precision, int action_dtype) {
+    bool yes = false;
+    dispatch_step(precision, envs_per_thread(precision), action_dtype, StreamSupportedOp{&yes});
+    return yes;
+}
+
+// Whole warps of wide threads go to the streaming kernel; what is left of the range (fewer than
+// 32 V envs), noise injection and the narrow geometry go to the general kernel.
 cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    return dispatch_step(precision, g.v, action_dtype, StepLaunchOp{a, g, s});
+    const int wide = envs_per_thread(precision);
+    const int64_t n = a.env_end - a.env_begin;
+    const int64_t warp_envs = 32 * wide;
+    int64_t n_stream = 0;
+    if (g.v == wide && wide > 1 && a.noise_x == nullptr && n <= ((int64_t)1 << 31) &&
+        a.env_begin % wide == 0 && has_stream_kernel(precision, action_dtype))
+        n_stream = n / warp_envs * warp_envs;
+    if (n_stream == 0) return dispatch_step(precision, g.v, action_dtype, StepLaunchOp{a, g, s});
+
+    const size_t es = precision == AQUA_F64 ? 8 : 4;
+    size_t ab = 4;
+    if (action_dtype == AQUA_ACT_I64 || action_dtype == AQUA_ACT_F32X2) ab = 8;
+    else if (action_dtype == AQUA_ACT_U8) ab = 1;
+    StepArgs b = a;
+    b.env_end = a.env_begin + n_stream;
+    for (int pl = 0; pl < AQUA_N_PLANES; ++pl)
+        b.pl0[pl] = static_cast<const char*>(a.planes) + ((size_t)pl * (size_t)a.ld) * es +
+                    (size_t)a.env_begin * (pl == AQUA_PLANE_TIME ? 4 : es);
+    b.act0 = static_cast<const char*>(a.actions) + (size_t)a.env_begin * ab;
+    b.rew0 = static_cast<char*>(a.reward) + (size_t)a.env_begin * es;
+    b.flg0 = a.flags + a.env_begin;
+    b.n_stream = (uint32_t)n_stream;
+    b.env_id0 = (uint32_t)(a.w.env_id_base + (uint64_t)a.env_begin);
+    LaunchGeom gs = g;
+    const int64_t tile = (int64_t)g.threads * wide;
+    gs.blocks = (int)std::max<int64_t>(1, std::min<int64_t>(g.blocks, (n_stream + tile - 1) / tile));
+    cudaError_t e = dispatch_step(precision, wide, action_dtype, StreamLaunchOp{b, gs, s});
+    if (e != cudaSuccess || n_stream == n) return e;
+    StepArgs c = a;
+    c.env_begin = a.env_begin + n_stream;
+    return dispatch_step(precision, wide, action_dtype, StepLaunchOp{c, LaunchGeom{g.threads, 1, wide}, s});
 }
 
 struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limit needs an opt-in
@@ -890,6 +1227,20 @@ struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limi
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(step_kernel<R, V, ACT, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
+        if constexpr (stream_supported<ACT, V>()) {
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, false>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes<R, V>());
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes<R, V>());
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, false>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e == cudaSuccess)
+                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, true>,
+                                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        }
         return e;
     }
 };
@@ -913,6 +1264,26 @@ struct StepOccupancyOp {
 };
 cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm) {
     return dispatch_step(precision, v, action_dtype, StepOccupancyOp{threads, blocks_per_sm});
+}
+
+struct StreamOccupancyOp {
+    int threads, waves;
+    int* out;
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        if constexpr (stream_supported<ACT, V>()) {
+            if (waves)
+                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>, threads,
+                                                                     stage_bytes<R, V>());
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>, threads,
+                                                                 stage_bytes<R, V>());
+        } else {
+            *out = 0;
+            return cudaSuccess;
+        }
+    }
+};
+cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int* blocks_per_sm) {
+    return dispatch_step(precision, envs_per_thread(precision), action_dtype, StreamOccupancyOp{threads, waves, blocks_per_sm});
 }
 
 struct RolloutLaunchOp {

@@ -56,6 +56,15 @@ struct StepArgs {
     unsigned long long* stats;  // [kStatSlots][AQUA_N_STATS]
     int64_t steps;          // rollout kernel: steps per launch
     uint64_t step0;         // rollout kernel: ACTION-stream index of the first step
+    // streaming step kernel (whole warps only): everything below is filled by launch_step() so
+    // that the kernel addresses with one 32-bit index and constant-bank base pointers
+    const char* pl0[AQUA_N_PLANES];  // plane p at env_begin
+    const char* act0;                // actions / reward / flags at env_begin
+    char* rew0;
+    uint8_t* flg0;
+    uint32_t* tile_ctr;              // [2], zero between launches: next dynamic warp tile, finished CTAs
+    uint32_t n_stream;               // envs of the launch, a multiple of 32 * (envs per thread)
+    uint32_t env_id0;                // global id of env_begin
 };
 
 struct LaunchGeom {
@@ -82,6 +91,8 @@ cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int cle
 cudaError_t configure_kernels(int precision);
 // occupancy of the step kernel for (precision, action dtype) at `threads` per CTA
 cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm);
+// same for the streaming kernel; *blocks_per_sm = 0 when (precision, action dtype) has none
+cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int* blocks_per_sm);
 cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int* blocks_per_sm);
 
 int envs_per_thread(int precision);

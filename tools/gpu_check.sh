@@ -19,6 +19,6 @@ $NCU_CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv $NCU_CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 $NCU_CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 4 -c 2 -f -o $OUT/${TAG}_step $NCU_CMD > $OUT/${TAG}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:step_ -s 4 -c 2 -f -o $OUT/${TAG}_step $NCU_CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
 ls -la $OUT

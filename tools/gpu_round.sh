@@ -18,5 +18,5 @@ timeout 300 $NCU_CMD > $OUT/${TAG}_ncu_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/${TAG}_launches.csv $NCU_CMD > $OUT/${TAG}_ncu_launches.log 2>&1
 echo "ncu launches exit $?"
 timeout 300 $NCU_CMD > $OUT/${TAG}_ncu_plain2.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 4 -c 2 -f -o $OUT/${TAG}_step $NCU_CMD > $OUT/${TAG}_ncu_full.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:step_ -s 4 -c 2 -f -o $OUT/${TAG}_step $NCU_CMD > $OUT/${TAG}_ncu_full.log 2>&1
 echo "ncu full exit $?"
