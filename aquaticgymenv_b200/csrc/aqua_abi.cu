@@ -72,7 +72,7 @@ struct aqua_env {
     double* d_tab64 = nullptr;
     unsigned long long* d_slots = nullptr;
     int64_t* d_stats_out = nullptr;
-    uint32_t* d_tile_ctr = nullptr;  // kTileCounters pairs, handed out round robin per launch
+    uint32_t* d_tile_ctr = nullptr;  // kTileCounters counter sets, handed out round robin per launch
     unsigned launch_seq = 0;
     aqua::World world;
     // resident CTAs per SM, queried once at create: [action dtype][narrow (V = 1, 128 threads) /
@@ -94,7 +94,7 @@ namespace {
 aqua::StepArgs base_args(aqua_env* env) {
     aqua::StepArgs a;
     memset(&a, 0, sizeof a);
-    a.tile_ctr = env->d_tile_ctr + 2 * (env->launch_seq++ % kTileCounters);
+    a.tile_ctr = env->d_tile_ctr + aqua::kTileCounterWords * (env->launch_seq++ % kTileCounters);
     a.w = env->world;
     a.planes = env->state;
     a.ld = env->ld;
@@ -257,8 +257,8 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     AQ_CREATE(cudaMalloc(&env->d_slots, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
     AQ_CREATE(cudaMemset(env->d_slots, 0, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
     AQ_CREATE(cudaMalloc(&env->d_stats_out, sizeof(int64_t) * AQUA_N_STATS));
-    AQ_CREATE(cudaMalloc(&env->d_tile_ctr, sizeof(uint32_t) * 2 * kTileCounters));
-    AQ_CREATE(cudaMemset(env->d_tile_ctr, 0, sizeof(uint32_t) * 2 * kTileCounters));
+    AQ_CREATE(cudaMalloc(&env->d_tile_ctr, sizeof(uint32_t) * aqua::kTileCounterWords * kTileCounters));
+    AQ_CREATE(cudaMemset(env->d_tile_ctr, 0, sizeof(uint32_t) * aqua::kTileCounterWords * kTileCounters));
 
     aqua::World& w = env->world;
     memset(&w, 0, sizeof w);

@@ -835,15 +835,23 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     // statically assigned tiles and then claims further tiles from a global counter, one claim per
     // tile, issued a whole tile ahead of its use: SMs do not run at the same speed (distance to
     // the memory partitions), and a static partition makes the kernel as slow as its slowest SM.
+    // One counter cannot serve a claim per 128 envs (same-address atomics retire about one per
+    // 1.5 ns), so warp w of every CTA draws from pool w: kTilePools counters on separate lines,
+    // pool w owning the dynamic tiles congruent to w.  Every pool has one warp on every CTA, hence
+    // the pools drain at the same rate.
     // Two staging buffers, prefetch distance two tiles: a buffer is refilled (with the tile after
     // next) as soon as its slices have been read into registers, so every copy has two tile
     // times to land.
     const uint32_t lane_off = (threadIdx.x & 31u) * V;
+    uint32_t lane_id;
+    asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_id));
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);  // of the launch
     constexpr uint32_t kWarpTile = 32u * V;
     uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kWarpTile + lane_off;  // this tile
     uint32_t i1 = i + n_warps * kWarpTile;   // the next one (in flight)
     uint32_t i2 = i1 + n_warps * kWarpTile;  // the one after (to be prefetched)
+    const uint32_t pool = (threadIdx.x >> 5) % kTilePools;
+    uint32_t* const my_ctr = p.tile_ctr + pool * kTilePoolStride + (lane_id & p.tile_lane_mask);
     if (i < n) prefetch(s_cur, i);
     cp_async_commit();
     if (i1 < n) prefetch(s_nxt, i1);
@@ -877,7 +885,13 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             const bool more = i2 < n;  // warp-uniform
             if (more) {
                 prefetch(s_cur, i2);  // refill the buffer just read
-                if ((threadIdx.x & 31u) == 0u) claim = atomicAdd(p.tile_ctr, 1u);  // consumed at the end of this tile
+                // Consumed at the end of this tile.  ptxas lowers an atomic add on a warp-uniform
+                // address to the warp-aggregated form, whose broadcast shuffle would wait for the
+                // result right here; tile_lane_mask = 0 (a parameter) keeps the address formally
+                // lane dependent.
+                if ((threadIdx.x & 31u) == 0u)
+                    asm volatile("atom.global.add.u32 %0, [%1], 1;"
+                                 : "=r"(claim) : "l"(my_ctr) : "memory");
             }
             cp_async_commit();
 
@@ -960,7 +974,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             s_nxt = t;
             i = i1;
             i1 = i2;
-            i2 = more ? (3u * n_warps + __shfl_sync(0xffffffffu, claim, 0)) * kWarpTile + lane_off : n;
+            // the claim is consumed here, after the tile's stores, so that its round trip to the L2
+            // atomic unit overlaps the whole tile
+            asm volatile("" : "+r"(claim) : : "memory");
+            i2 = more ? (3u * n_warps + __shfl_sync(0xffffffffu, claim, 0) * kTilePools + pool) * kWarpTile + lane_off : n;
         }
         if (autoreset) {  // phase B, warp-collective
             if (live && __any_sync(0xffffffffu, fw != 0u)) n_queued = reset_queue_push<V>(wq, n_queued, fw, i_done, otw.v);
@@ -974,9 +991,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     flush_stats(st, s_stats, p.stats);
     if (threadIdx.x == 0) {  // the last CTA to finish rearms the tile counter for the next launch
         __threadfence();
-        if (atomicAdd(p.tile_ctr + 1, 1u) == gridDim.x - 1u) {
-            p.tile_ctr[0] = 0u;
-            p.tile_ctr[1] = 0u;
+        if (atomicAdd(p.tile_ctr + kTilePools * kTilePoolStride, 1u) == gridDim.x - 1u) {
+            for (int k = 0; k <= kTilePools; ++k) p.tile_ctr[k * kTilePoolStride] = 0u;
             __threadfence();
         }
     }
@@ -1203,6 +1219,7 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
     b.rew0 = static_cast<char*>(a.reward) + (size_t)a.env_begin * es;
     b.flg0 = a.flags + a.env_begin;
     b.n_stream = (uint32_t)n_stream;
+    b.tile_lane_mask = 0u;
     b.env_id0 = (uint32_t)(a.w.env_id_base + (uint64_t)a.env_begin);
     LaunchGeom gs = g;
     const int64_t tile = (int64_t)g.threads * wide;

@@ -14,6 +14,11 @@ constexpr int kMaxThreads = 256;   // threads per CTA upper bound (launch bounds
 #define AQUA_MIN_BLOCKS 2
 #endif
 constexpr int kMinBlocks = AQUA_MIN_BLOCKS;  // resident CTAs per SM the kernels are compiled for
+// dynamic tile claims of the streaming kernel: kTilePools counters + the finished-CTA count, one
+// 128-byte line each
+constexpr int kTilePools = 8;
+constexpr int kTilePoolStride = 32;                                   // uint32 words
+constexpr int kTileCounterWords = (kTilePools + 1) * kTilePoolStride;
 constexpr int kStatSlots = 1024;   // per-CTA statistics slots (CTA b adds into slot b % kStatSlots)
 
 // Round keys of the draw streams, computed once on the host so that in the kernels they are
@@ -62,9 +67,10 @@ struct StepArgs {
     const char* act0;                // actions / reward / flags at env_begin
     char* rew0;
     uint8_t* flg0;
-    uint32_t* tile_ctr;              // [2], zero between launches: next dynamic warp tile, finished CTAs
+    uint32_t* tile_ctr;              // one counter set (kTileCounterWords), zero between launches
     uint32_t n_stream;               // envs of the launch, a multiple of 32 * (envs per thread)
     uint32_t env_id0;                // global id of env_begin
+    uint32_t tile_lane_mask;         // 0 (see the tile claim in step_stream_kernel)
 };
 
 struct LaunchGeom {
