@@ -831,10 +831,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
     int n_queued = 0;  // warp-uniform
 
-    // Work distribution: a warp tile is 32 V consecutive envs.  Every warp starts with three
+    // Work distribution: a warp tile is 32 V consecutive envs.  Every warp starts with four
     // statically assigned tiles and then claims further tiles from a global counter, one claim per
-    // tile, issued a whole tile ahead of its use: SMs do not run at the same speed (distance to
-    // the memory partitions), and a static partition makes the kernel as slow as its slowest SM.
+    // tile, issued two tiles ahead of its use (the round trip of an atomic through the loaded
+    // memory system is longer than one tile): SMs do not run at the same speed (distance to the
+    // memory partitions), and a static partition makes the kernel as slow as its slowest SM.
     // One counter cannot serve a claim per 128 envs (same-address atomics retire about one per
     // 1.5 ns), so warp w of every CTA draws from pool w: kTilePools counters on separate lines,
     // pool w owning the dynamic tiles congruent to w.  Every pool has one warp on every CTA, hence
@@ -850,8 +851,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kWarpTile + lane_off;  // this tile
     uint32_t i1 = i + n_warps * kWarpTile;   // the next one (in flight)
     uint32_t i2 = i1 + n_warps * kWarpTile;  // the one after (to be prefetched)
+    uint32_t i3 = i2 + n_warps * kWarpTile;  // and its successor
     const uint32_t pool = (threadIdx.x >> 5) % kTilePools;
     uint32_t* const my_ctr = p.tile_ctr + pool * kTilePoolStride + (lane_id & p.tile_lane_mask);
+    // ptxas lowers an atomic add on a warp-uniform address to the warp-aggregated form, whose
+    // broadcast shuffle waits for the result on the spot; tile_lane_mask = 0 (a parameter) keeps
+    // the address formally lane dependent, so the claim is a plain ATOMG consumed much later.
+    auto claim_tile = [&](uint32_t& claim) {
+        if ((threadIdx.x & 31u) == 0u)
+            asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(claim) : "l"(my_ctr) : "memory");
+    };
+    uint32_t claim_old = 0u;      // issued during the previous tile: the successor of i3
+    bool old_valid = i3 < n;      // warp-uniform
+    if (old_valid) claim_tile(claim_old);
     if (i < n) prefetch(s_cur, i);
     cp_async_commit();
     if (i1 < n) prefetch(s_nxt, i1);
@@ -860,7 +872,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
         const bool live = i < n;  // warp-uniform: n is a multiple of 32 V
         uint32_t fw = 0u;
         Pack<uint32_t, V> otw;
-        uint32_t claim = 0u;
+        uint32_t claim_new = 0u;
         const uint32_t i_done = i;
         if (live) {
             cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
@@ -882,18 +894,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
                 for (int k = 0; k < kActPiece / 4; ++k) araw[q * (kActPiece / 4) + k] = w[k];
             }
             const ActVals<ACT, V> act = actions_from_raw<ACT, V, kActWords>(araw);
-            const bool more = i2 < n;  // warp-uniform
-            if (more) {
-                prefetch(s_cur, i2);  // refill the buffer just read
-                // Consumed at the end of this tile.  ptxas lowers an atomic add on a warp-uniform
-                // address to the warp-aggregated form, whose broadcast shuffle would wait for the
-                // result right here; tile_lane_mask = 0 (a parameter) keeps the address formally
-                // lane dependent.
-                if ((threadIdx.x & 31u) == 0u)
-                    asm volatile("atom.global.add.u32 %0, [%1], 1;"
-                                 : "=r"(claim) : "l"(my_ctr) : "memory");
-            }
+            if (i2 < n) prefetch(s_cur, i2);  // refill the buffer just read
             cp_async_commit();
+            const bool new_valid = old_valid && i3 < n;  // the pool had tiles left at the last look
+            if (new_valid) claim_tile(claim_new);
 
             Drive<R> dr[V];
             if constexpr (ACT == AQUA_ACT_F32X2) {
@@ -972,12 +976,16 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             const uint32_t t = s_cur;
             s_cur = s_nxt;
             s_nxt = t;
+            // the claim of the previous tile is consumed here, after this tile's stores
+            asm volatile("" : "+r"(claim_old) : : "memory");
+            const uint32_t i4 =
+                old_valid ? (4u * n_warps + __shfl_sync(0xffffffffu, claim_old, 0) * kTilePools + pool) * kWarpTile + lane_off : n;
             i = i1;
             i1 = i2;
-            // the claim is consumed here, after the tile's stores, so that its round trip to the L2
-            // atomic unit overlaps the whole tile
-            asm volatile("" : "+r"(claim) : : "memory");
-            i2 = more ? (3u * n_warps + __shfl_sync(0xffffffffu, claim, 0) * kTilePools + pool) * kWarpTile + lane_off : n;
+            i2 = i3;
+            i3 = i4;
+            claim_old = claim_new;
+            old_valid = new_valid;
         }
         if (autoreset) {  // phase B, warp-collective
             if (live && __any_sync(0xffffffffu, fw != 0u)) n_queued = reset_queue_push<V>(wq, n_queued, fw, i_done, otw.v);
