@@ -25,6 +25,32 @@ template <typename T, int V> __device__ __forceinline__ Pack<T, V> ld_pack(const
 template <typename T, int V> __device__ __forceinline__ void st_pack(T* p, const Pack<T, V>& v) {
     *reinterpret_cast<Pack<T, V>*>(p) = v;
 }
+// Stores of the streaming kernel.  AQUA_STORE_CS=1 makes them evict-first (st.global.cs).  Measured
+// on one B200 box (tools/tune.py, 2^24 envs): plain 8.20e10 env-steps/s, evict-first 7.97e10 -- the
+// deferred reset writes 4-byte values into lines the owner stored a few tiles earlier, and those
+// should still be in L2 by then.  Hence plain stores.
+#ifndef AQUA_STORE_CS
+#define AQUA_STORE_CS 0
+#endif
+template <typename T, int V> __device__ __forceinline__ void st_pack_cs(T* p, const Pack<T, V>& v) {
+    if constexpr (!AQUA_STORE_CS) {
+        st_pack<T, V>(p, v);
+    } else if constexpr (sizeof(T) * V == 16) {
+        uint4 r;
+        memcpy(&r, &v, 16);
+        __stcs(reinterpret_cast<uint4*>(p), r);
+    } else if constexpr (sizeof(T) * V == 8) {
+        uint2 r;
+        memcpy(&r, &v, 8);
+        __stcs(reinterpret_cast<uint2*>(p), r);
+    } else if constexpr (sizeof(T) * V == 4) {
+        unsigned r;
+        memcpy(&r, &v, 4);
+        __stcs(reinterpret_cast<unsigned*>(p), r);
+    } else {
+        st_pack<T, V>(p, v);
+    }
+}
 // read-only (non-coherent) path for the caller's action / noise buffers
 template <typename T, int V> __device__ __forceinline__ Pack<T, V> ldg_pack(const T* p) {
     Pack<T, V> out;
@@ -964,14 +990,14 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
             const size_t off = (size_t)i * sizeof(R);
-            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off), ox);
-            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_Y]) + off), oy);
-            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_THETA]) + off), oth);
-            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_X]) + off), owx);
-            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_Y]) + off), owy);
-            st_pack<uint32_t, V>(reinterpret_cast<uint32_t*>(const_cast<char*>(p.pl0[AQUA_PLANE_TIME]) + (size_t)i * 4), otw);
-            st_pack<R, V>(reinterpret_cast<R*>(p.rew0 + off), vrew);
-            st_pack<uint8_t, V>(p.flg0 + i, vfl);
+            st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off), ox);
+            st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_Y]) + off), oy);
+            st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_THETA]) + off), oth);
+            st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_X]) + off), owx);
+            st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_Y]) + off), owy);
+            st_pack_cs<uint32_t, V>(reinterpret_cast<uint32_t*>(const_cast<char*>(p.pl0[AQUA_PLANE_TIME]) + (size_t)i * 4), otw);
+            st_pack_cs<R, V>(reinterpret_cast<R*>(p.rew0 + off), vrew);
+            st_pack_cs<uint8_t, V>(p.flg0 + i, vfl);
 
             const uint32_t t = s_cur;
             s_cur = s_nxt;
