@@ -391,7 +391,9 @@ def run_b200(args):
         "config": workload_config(args, n_local),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": traffic, "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bpe * n_local, "kernel": "aqua::step_kernel<float,I32>"},
+                     "algorithmic_bytes_per_launch": bpe * n_local,
+                     # whole warps of the slab run the streaming kernel (launch_step, aqua_kernels.cu)
+                     "kernel": "aqua::step_stream_kernel<%s,I32,waves>" % ("float,4" if args.precision == "float32" else "double,2")},
         "e2e": {"value": e2e_value, "unit": "env-steps/s", "h2d_bytes_per_step": 4 * n_local * world,
                 "d2h_bytes_per_step": (5 * es + es + 1) * n_local * world, "steps": args.e2e_steps,
                 "api": "aqua_step_host (AquaVecEnv.step_host): int32 actions in, obs[5,N]+reward+flags out, pinned"},
