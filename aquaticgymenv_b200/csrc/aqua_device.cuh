@@ -542,22 +542,13 @@ __device__ __forceinline__ uint32_t finish_env(const EnvState<R>& e, const MoveT
         const R den = P::sqrt_(dp2) + P::sqrt_(dc2);
         step_reward = (R(0.7) * num) * P::rcp_(den);
     }
-    const uint32_t tn = e.tw & kTimeMask;
-    uint32_t flags;
-    if (collided) {
-        flags = AQUA_FLAG_DONE | AQUA_FLAG_COLLIDED;
-        reward = R(-10);
-    } else if (tn > 1000u) {
-        flags = AQUA_FLAG_DONE | AQUA_FLAG_TIME;
-        reward = R(-10);
-    } else if (reached) {
-        flags = AQUA_FLAG_DONE | AQUA_FLAG_SUCCESS;
-        reward = R(10);
-    } else {
-        flags = 0u;
-        reward = step_reward;
-    }
-    return flags;
+    // collision > time > goal > running, written as selects (no divergent branches)
+    const bool late = (e.tw & kTimeMask) > 1000u;
+    const uint32_t f_goal = reached ? (AQUA_FLAG_DONE | AQUA_FLAG_SUCCESS) : 0u;
+    const uint32_t f_time = late ? (AQUA_FLAG_DONE | AQUA_FLAG_TIME) : f_goal;
+    const R r_goal = reached ? R(10) : step_reward;
+    reward = (collided | late) ? R(-10) : r_goal;
+    return collided ? (AQUA_FLAG_DONE | AQUA_FLAG_COLLIDED) : f_time;
 }
 
 // action decode ---------------------------------------------------------------------------

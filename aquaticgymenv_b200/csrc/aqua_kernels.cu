@@ -227,30 +227,21 @@ template <typename R, int V> constexpr int stage_bytes() { return V > 1 ? kStage
 // ------------------------------------------------------------------------------------------
 // per-thread episode statistics and their reduction
 // ------------------------------------------------------------------------------------------
-// The four flag bits of the V envs of a thread arrive packed one byte per env; they are
-// accumulated byte-wise (one add per counter per tile instead of per env) and widened before a
-// byte lane can overflow.
+// The flag bytes of the V envs of a thread arrive packed in one word (byte j = env j).  A finished
+// env carries exactly one of COLLIDED (2), TIME (4), SUCCESS (8) next to DONE (aqua.py:194-211), so
+// three masked byte sums (one LOP3 + one IDP.4A each) count everything: the accumulators hold
+// 2 x collided, 4 x timeouts, 8 x successes, and done is their sum.
 struct ThreadStats {
-    uint32_t pk_done = 0, pk_coll = 0, pk_time = 0, pk_succ = 0;  // 4 byte lanes each
-    uint32_t pk_n = 0;
-    uint32_t done = 0, collided = 0, timeout = 0, success = 0, length = 0, steps = 0, bad = 0;
+    uint32_t coll2 = 0, time4 = 0, succ8 = 0;
+    uint32_t length = 0, steps = 0, bad = 0;
     long long reward_fx = 0;  // sum of step rewards, fixed point 2^-20
 
-    __device__ __forceinline__ void widen() {
-        done += __dp4a(pk_done, 0x01010101u, 0u);
-        collided += __dp4a(pk_coll, 0x01010101u, 0u);
-        timeout += __dp4a(pk_time, 0x01010101u, 0u);
-        success += __dp4a(pk_succ, 0x01010101u, 0u);
-        pk_done = pk_coll = pk_time = pk_succ = pk_n = 0u;
-    }
     // w: flags of the thread's envs, byte j = env j (bytes of padding envs must be 0)
     __device__ __forceinline__ void add_flags(uint32_t w, int nvalid) {
-        pk_done += w & 0x01010101u;
-        pk_coll += (w >> 1) & 0x01010101u;
-        pk_time += (w >> 2) & 0x01010101u;
-        pk_succ += (w >> 3) & 0x01010101u;
+        coll2 = __dp4a(w & 0x02020202u, 0x01010101u, coll2);
+        time4 = __dp4a(w & 0x04040404u, 0x01010101u, time4);
+        succ8 = __dp4a(w & 0x08080808u, 0x01010101u, succ8);
         steps += (uint32_t)nvalid;
-        if (++pk_n == 255u) widen();
     }
     // without auto-reset the episode length is taken here; with it, phase B adds it (the reset
     // pass reads the terminal time word anyway)
@@ -268,12 +259,11 @@ struct ThreadStats {
 // warp reduce (REDUX) -> shared slots -> one global atomic per counter per CTA
 __device__ __forceinline__ void flush_stats(ThreadStats& t, unsigned long long* s_stats,
                                             unsigned long long* g_slots) {
-    t.widen();
     const unsigned full = 0xffffffffu;
-    const uint32_t d = __reduce_add_sync(full, t.done);
-    const uint32_t c = __reduce_add_sync(full, t.collided);
-    const uint32_t o = __reduce_add_sync(full, t.timeout);
-    const uint32_t s = __reduce_add_sync(full, t.success);
+    const uint32_t c = __reduce_add_sync(full, t.coll2 >> 1);
+    const uint32_t o = __reduce_add_sync(full, t.time4 >> 2);
+    const uint32_t s = __reduce_add_sync(full, t.succ8 >> 3);
+    const uint32_t d = c + o + s;
     const uint32_t l = __reduce_add_sync(full, t.length);
     const uint32_t n = __reduce_add_sync(full, t.steps);
     const uint32_t b = __reduce_add_sync(full, t.bad);
@@ -969,23 +959,20 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
 
             Pack<R, V> vrew, ox, oy, oth, owx, owy;
-            Pack<uint8_t, V> vfl;
 #pragma unroll
-            for (int j = 0; j < V; ++j) {
+            for (int j = 0; j < V; ++j) {  // the flags word (byte j = env j) is built in 32-bit arithmetic
                 R reward;
-                const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
+                fw |= finish_env<R>(e[j], m[j], clr[j], reward) << (8 * j);
                 vrew.v[j] = reward;
-                vfl.v[j] = (uint8_t)f;
                 ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
                 owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
             }
-            fw = flags_word<V>(vfl);
             st.add_flags(fw, V);
 #pragma unroll
             for (int j = 0; j < V; ++j) st.add_env<R>(vrew.v[j]);
             if (!autoreset) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) st.add_length(vfl.v[j], otw.v[j] & kTimeMask);
+                for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), otw.v[j] & kTimeMask);
             }
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
@@ -997,7 +984,8 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_Y]) + off), owy);
             st_pack_cs<uint32_t, V>(reinterpret_cast<uint32_t*>(const_cast<char*>(p.pl0[AQUA_PLANE_TIME]) + (size_t)i * 4), otw);
             st_pack_cs<R, V>(reinterpret_cast<R*>(p.rew0 + off), vrew);
-            st_pack_cs<uint8_t, V>(p.flg0 + i, vfl);
+            if constexpr (V == 4) *reinterpret_cast<uint32_t*>(p.flg0 + i) = fw;
+            else *reinterpret_cast<uint16_t*>(p.flg0 + i) = (uint16_t)fw;
 
             const uint32_t t = s_cur;
             s_cur = s_nxt;
