@@ -238,7 +238,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     }
     // obstacle tables
     const size_t tab_bytes = aqua::obstacle_table_bytes(cfg->precision);
-    int k_circ = 0;
+    int k_circ = 0, use_grid = 0;
     {
         void* h_tab = malloc(tab_bytes);
         double h_tab64[AQUA_MAX_OBSTACLES * 5] = {0};
@@ -246,7 +246,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
             aqua_destroy(env);
             return fail(AQUA_ERR_ALLOC, "out of host memory");
         }
-        k_circ = aqua::build_obstacle_tables(cfg->precision, cfg->n_obstacles, cfg->obstacles, h_tab, h_tab64);
+        k_circ = aqua::build_obstacle_tables(cfg->precision, cfg->n_obstacles, cfg->obstacles, h_tab, h_tab64, &use_grid);
         cudaError_t e1 = cudaMalloc(&env->d_tab, tab_bytes);
         if (e1 == cudaSuccess) e1 = cudaMemcpy(env->d_tab, h_tab, tab_bytes, cudaMemcpyHostToDevice);
         free(h_tab);
@@ -281,21 +281,22 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.random_boat = cfg->random_boat != 0;
     w.random_goal = cfg->random_goal != 0;
     w.autoreset = cfg->autoreset != 0;
+    w.use_grid = use_grid != 0;
 
     AQ_CREATE(aqua::configure_kernels(cfg->precision));
     for (int ti = 0; ti < 2; ++ti) {
         const int threads = ti == 0 ? 128 : 256;
         const int v = ti == 0 ? 1 : aqua::envs_per_thread(cfg->precision);
         for (int act = 0; act < 4; ++act) {
-            AQ_CREATE(aqua::step_occupancy(cfg->precision, v, act, threads, &env->occ_step[act][ti]));
+            AQ_CREATE(aqua::step_occupancy(cfg->precision, v, act, threads, use_grid, &env->occ_step[act][ti]));
             env->occ_step[act][ti] = std::max(env->occ_step[act][ti], 1);
             if (ti == 1) {  // wide slabs run the streaming kernel where there is one: size the grid for it
                 int occ = 0;
-                AQ_CREATE(aqua::stream_occupancy(cfg->precision, act, cfg->waves != 0, threads, &occ));
+                AQ_CREATE(aqua::stream_occupancy(cfg->precision, act, cfg->waves != 0, threads, use_grid, &occ));
                 if (occ > 0) env->occ_step[act][ti] = occ;
             }
         }
-        AQ_CREATE(aqua::rollout_occupancy(cfg->precision, v, cfg->continuous, threads, &env->occ_rollout[ti]));
+        AQ_CREATE(aqua::rollout_occupancy(cfg->precision, v, cfg->continuous, threads, use_grid, &env->occ_rollout[ti]));
         env->occ_rollout[ti] = std::max(env->occ_rollout[ti], 1);
     }
     AQ_CREATE(aqua::launch_init_state(cfg->precision, env->state, ld, nullptr));

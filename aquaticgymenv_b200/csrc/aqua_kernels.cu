@@ -9,6 +9,7 @@
 #include "aqua_device.cuh"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace aqua {
@@ -287,16 +288,27 @@ __device__ __forceinline__ void flush_stats(ThreadStats& t, unsigned long long* 
     }
 }
 
+// dynamic shared memory a launch needs for the culling grid (dense maps only), placed behind the
+// staging buffers
+constexpr size_t kCellBytes = sizeof(unsigned long long) * kGridCells;
+__host__ __device__ inline size_t cell_bytes(int use_grid) { return use_grid ? kCellBytes : 0; }
+
+// Copies the obstacle table of the launch (global ObstacleTable<R>) into shared memory: the boxes
+// into `s_box`, the cells of a dense map into `s_cell`; returns the view the kernels read.  The
+// caller synchronises the CTA.
 template <typename R>
-__device__ __forceinline__ void stage_table(ObstacleTable<R>& tab, const void* g_tab, int k_obst) {
+__device__ __forceinline__ ObstacleView<R> stage_table(ObstacleBox<R>* s_box, unsigned char* s_cell, const void* g_tab,
+                                                       int k_obst, bool use_grid) {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(g_tab);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&tab);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_box);
     constexpr int kWordsPerBox = sizeof(ObstacleBox<R>) / 4;
     for (int i = threadIdx.x; i < k_obst * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
-    if (k_obst > kGridMinObstacles) {  // dense map: the culling grid as well
+    if (use_grid) {  // dense map: the culling grid as well
         constexpr int kCellOff = sizeof(ObstacleBox<R>) * AQUA_MAX_OBSTACLES / 4;
-        for (int i = threadIdx.x; i < kGridCells * 2; i += blockDim.x) dst[kCellOff + i] = __ldg(src + kCellOff + i);
+        uint32_t* cdst = reinterpret_cast<uint32_t*>(s_cell);
+        for (int i = threadIdx.x; i < kGridCells * 2; i += blockDim.x) cdst[i] = __ldg(src + kCellOff + i);
     }
+    return ObstacleView<R>{s_box, use_grid ? reinterpret_cast<const unsigned long long*>(s_cell) : nullptr};
 }
 
 // ------------------------------------------------------------------------------------------
@@ -338,7 +350,7 @@ __device__ __forceinline__ int reset_queue_push(WarpResetQueue<V>& wq, int n, ui
 // Resets queued envs in passes of kResetGroups, from the tail, while at least `min_batch` are
 // queued (min_batch = kResetGroups: full passes only; 1: flush).  Returns the new queue length.
 template <typename R, int V>
-__device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const ObstacleTable<R>& tab,
+__device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const ObstacleView<R>& tab,
                                                  const WarpResetQueue<V>& wq, int n, int min_batch, uint32_t& length_sum) {
     const unsigned lane = threadIdx.x & 31u;
     const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
@@ -388,10 +400,10 @@ extern __shared__ __align__(16) unsigned char s_stage[];
 
 template <typename R, int V, int ACT, bool INJECT>
 __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleTable<R> tab;
+    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
-    stage_table<R>(tab, p.w.tab, p.w.k_obst);
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
@@ -607,10 +619,10 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
 // ------------------------------------------------------------------------------------------
 template <typename R, int V, bool CONTINUOUS>
 __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) rollout_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleTable<R> tab;
+    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
-    stage_table<R>(tab, p.w.tab, p.w.k_obst);
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage, p.w.tab, p.w.k_obst, p.w.use_grid != 0);  // no staging buffers here
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
@@ -808,11 +820,11 @@ template <int ACT, int V> constexpr bool stream_supported() {
 
 template <typename R, int V, int ACT, bool WAVES>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleTable<R> tab;
+    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     __shared__ DriveSlot<R> s_drive[3];
-    stage_table<R>(tab, p.w.tab, p.w.k_obst);
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
@@ -1180,7 +1192,7 @@ struct StepLaunchOp {
     LaunchGeom g;
     cudaStream_t s;
     template <typename R, int V, int ACT> cudaError_t run() const {
-        const size_t smem = stage_bytes<R, V>();
+        const size_t smem = stage_bytes<R, V>() + cell_bytes(a.w.use_grid);
         if (a.noise_x != nullptr) step_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
         else step_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
         return cudaGetLastError();
@@ -1194,7 +1206,7 @@ struct StreamLaunchOp {
     cudaStream_t s;
     template <typename R, int V, int ACT> cudaError_t run() const {
         if constexpr (stream_supported<ACT, V>()) {
-            const size_t smem = stage_bytes<R, V>();
+            const size_t smem = stage_bytes<R, V>() + cell_bytes(a.w.use_grid);
             if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
             else step_stream_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
             return cudaGetLastError();
@@ -1255,11 +1267,12 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 
 struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limit needs an opt-in
     template <typename R, int V, int ACT> cudaError_t run() const {
+        constexpr int kMaxDyn = stage_bytes<R, V>() + (int)kCellBytes;  // staging buffers + culling grid
         cudaError_t e = cudaFuncSetAttribute(step_kernel<R, V, ACT, false>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes<R, V>());
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(step_kernel<R, V, ACT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     stage_bytes<R, V>());
+                                     kMaxDyn);
         if (e == cudaSuccess)
             e = cudaFuncSetAttribute(step_kernel<R, V, ACT, false>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
@@ -1269,10 +1282,10 @@ struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limi
         if constexpr (stream_supported<ACT, V>()) {
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes<R, V>());
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes<R, V>());
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
             if (e == cudaSuccess)
                 e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, false>,
                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1294,35 +1307,35 @@ cudaError_t configure_kernels(int precision) {
 }
 
 struct StepOccupancyOp {
-    int threads;
+    int threads, use_grid;
     int* out;
     template <typename R, int V, int ACT> cudaError_t run() const {
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_kernel<R, V, ACT, false>, threads,
-                                                             stage_bytes<R, V>());
+                                                             stage_bytes<R, V>() + cell_bytes(use_grid));
     }
 };
-cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm) {
-    return dispatch_step(precision, v, action_dtype, StepOccupancyOp{threads, blocks_per_sm});
+cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int use_grid, int* blocks_per_sm) {
+    return dispatch_step(precision, v, action_dtype, StepOccupancyOp{threads, use_grid, blocks_per_sm});
 }
 
 struct StreamOccupancyOp {
-    int threads, waves;
+    int threads, waves, use_grid;
     int* out;
     template <typename R, int V, int ACT> cudaError_t run() const {
         if constexpr (stream_supported<ACT, V>()) {
+            const size_t smem = stage_bytes<R, V>() + cell_bytes(use_grid);
             if (waves)
-                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>, threads,
-                                                                     stage_bytes<R, V>());
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>, threads,
-                                                                 stage_bytes<R, V>());
+                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>, threads, smem);
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>, threads, smem);
         } else {
             *out = 0;
             return cudaSuccess;
         }
     }
 };
-cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int* blocks_per_sm) {
-    return dispatch_step(precision, envs_per_thread(precision), action_dtype, StreamOccupancyOp{threads, waves, blocks_per_sm});
+cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int use_grid, int* blocks_per_sm) {
+    return dispatch_step(precision, envs_per_thread(precision), action_dtype,
+                         StreamOccupancyOp{threads, waves, use_grid, blocks_per_sm});
 }
 
 struct RolloutLaunchOp {
@@ -1330,7 +1343,7 @@ struct RolloutLaunchOp {
     LaunchGeom g;
     cudaStream_t s;
     template <typename R, int V, bool CONT> cudaError_t run() const {
-        rollout_kernel<R, V, CONT><<<g.blocks, g.threads, 0, s>>>(a);
+        rollout_kernel<R, V, CONT><<<g.blocks, g.threads, cell_bytes(a.w.use_grid), s>>>(a);
         return cudaGetLastError();
     }
 };
@@ -1338,14 +1351,14 @@ cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, Lau
     return dispatch_rollout(precision, g.v, continuous, RolloutLaunchOp{a, g, s});
 }
 struct RolloutOccupancyOp {
-    int threads;
+    int threads, use_grid;
     int* out;
     template <typename R, int V, bool CONT> cudaError_t run() const {
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, rollout_kernel<R, V, CONT>, threads, 0);
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, rollout_kernel<R, V, CONT>, threads, cell_bytes(use_grid));
     }
 };
-cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int* blocks_per_sm) {
-    return dispatch_rollout(precision, v, continuous, RolloutOccupancyOp{threads, blocks_per_sm});
+cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int use_grid, int* blocks_per_sm) {
+    return dispatch_rollout(precision, v, continuous, RolloutOccupancyOp{threads, use_grid, blocks_per_sm});
 }
 
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -1465,9 +1478,14 @@ static int sorted_rows(int k, const double* rows5, double* out5) {
     return k_circ;
 }
 
-// obstacles whose clearance region (inflated by the radius 2.5 and a 0.05 px safety margin that
-// also covers the rounding of the cell index) touches the cell
+// Classification of one grid cell (float64, 0.05 px safety margin that also covers the rounding of
+// the cell index on the device).  Returns kCellBlocked when the whole cell lies inside one
+// obstacle's clearance region (obstacle inflated by the radius 2.5) shrunk by the margin: the
+// distance to a convex obstacle is a convex function of the position, so its maximum over the cell
+// is attained at a corner.  Otherwise the mask of the obstacles whose clearance region, grown by
+// the margin, touches the cell.
 static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy) {
+    constexpr double kMargin = 0.05;
     const double cw = 100.0 / kGridDim;
     const double x0 = cx * cw, x1 = x0 + cw, y0 = cy * cw, y1 = y0 + cw;
     unsigned long long m = 0ull;
@@ -1475,19 +1493,37 @@ static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy) 
         const double* o = rows5 + 5 * i;
         const bool circle = o[2] == 0.0;
         const double hx = circle ? 0.0 : o[3] / 2, hy = circle ? 0.0 : o[4] / 2;
-        const double reach = (circle ? o[3] + 2.5 : 2.5) + 0.05;
+        const double reach = circle ? o[3] + 2.5 : 2.5;
+        // largest distance of a cell corner to the obstacle's box
+        double far2 = 0.0;
+        for (int c = 0; c < 4; ++c) {
+            const double px = (c & 1) ? x1 : x0, py = (c & 2) ? y1 : y0;
+            const double ex = std::max(std::fabs(px - o[0]) - hx, 0.0), ey = std::max(std::fabs(py - o[1]) - hy, 0.0);
+            far2 = std::max(far2, ex * ex + ey * ey);
+        }
+        if (reach > kMargin && far2 <= (reach - kMargin) * (reach - kMargin)) return kCellBlocked;
         // distance between the obstacle's box and the cell rectangle
         const double dx = std::max(std::max(x0 - (o[0] + hx), (o[0] - hx) - x1), 0.0);
         const double dy = std::max(std::max(y0 - (o[1] + hy), (o[1] - hy) - y1), 0.0);
-        if (dx * dx + dy * dy <= reach * reach) m |= 1ull << i;
+        if (dx * dx + dy * dy <= (reach + kMargin) * (reach + kMargin)) m |= 1ull << i;
     }
     return m;
 }
 
-template <typename R> static void fill_table(int k, const double* rows5, ObstacleTable<R>* t) {
+// Returns whether the culling grid can be used: the table is dense enough to pay for it, and no
+// cell that is not blocked carries a full mask (which would read as kCellBlocked; only possible
+// with AQUA_MAX_OBSTACLES obstacles all reaching one 2 px cell -- such a table is tested by brute
+// force).
+template <typename R> static bool fill_table(int k, const double* rows5, ObstacleTable<R>* t) {
     memset(t, 0, sizeof(*t));
+    bool grid_ok = k > kGridMinObstacles;
+    const unsigned long long full = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
     for (int cy = 0; cy < kGridDim; ++cy)
-        for (int cx = 0; cx < kGridDim; ++cx) t->cell[cy * kGridDim + cx] = cell_mask(k, rows5, cx, cy);
+        for (int cx = 0; cx < kGridDim; ++cx) {
+            unsigned long long m = cell_mask(k, rows5, cx, cy);
+            if (m != kCellBlocked && k >= 64 && m == full) grid_ok = false;
+            t->cell[cy * kGridDim + cx] = m;
+        }
     for (int i = 0; i < k; ++i) {
         const double* o = rows5 + 5 * i;
         const bool circle = o[2] == 0.0;
@@ -1502,13 +1538,17 @@ template <typename R> static void fill_table(int k, const double* rows5, Obstacl
             t->box[i].b = (R)(o[4] / 2);
         }
     }
+    return grid_ok;
 }
 
-int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host) {
+int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host,
+                          int* use_grid) {
     double sorted[AQUA_MAX_OBSTACLES * 5];
     const int k_circ = sorted_rows(k, rows5, sorted);
-    if (precision == AQUA_F64) fill_table<double>(k, sorted, reinterpret_cast<ObstacleTable<double>*>(tab_host));
-    else fill_table<float>(k, sorted, reinterpret_cast<ObstacleTable<float>*>(tab_host));
+    bool grid_ok;
+    if (precision == AQUA_F64) grid_ok = fill_table<double>(k, sorted, reinterpret_cast<ObstacleTable<double>*>(tab_host));
+    else grid_ok = fill_table<float>(k, sorted, reinterpret_cast<ObstacleTable<float>*>(tab_host));
+    *use_grid = grid_ok ? 1 : 0;
     for (int i = 0; i < k; ++i) {
         const double* o = sorted + 5 * i;
         const bool circle = o[2] == 0.0;

@@ -45,6 +45,7 @@ struct World {
     int32_t k_circ;         // obstacles [0, k_circ) are circles, [k_circ, k_obst) rectangles
     float reset_band;       // guard band of the float32 reset test, see reset_blocked()
     uint8_t waves, random_boat, random_goal, autoreset;
+    uint8_t use_grid;       // dense map: obstacles are culled through the cell grid of the table
 };
 
 struct StepArgs {
@@ -95,17 +96,20 @@ cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_
 cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s);
 // per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
 cudaError_t configure_kernels(int precision);
-// occupancy of the step kernel for (precision, action dtype) at `threads` per CTA
-cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int* blocks_per_sm);
+// occupancy of the step kernel for (precision, action dtype) at `threads` per CTA; `use_grid`:
+// the launch carries the culling grid of a dense map in its dynamic shared memory
+cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int use_grid, int* blocks_per_sm);
 // same for the streaming kernel; *blocks_per_sm = 0 when (precision, action dtype) has none
-cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int* blocks_per_sm);
-cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int* blocks_per_sm);
+cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int use_grid, int* blocks_per_sm);
+cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int use_grid, int* blocks_per_sm);
 
 int envs_per_thread(int precision);
 
 // host-side construction of the device obstacle tables; `out` sized for the precision
 size_t obstacle_table_bytes(int precision);
-// (circles first, then rectangles); returns the number of circles
-int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host);
+// (circles first, then rectangles); returns the number of circles.  *use_grid: the table is dense
+// enough for the culling grid and its cell masks are unambiguous (see kCellBlocked)
+int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host,
+                          int* use_grid);
 
 }  // namespace aqua

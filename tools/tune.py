@@ -1,6 +1,8 @@
 #!/usr/bin/env python
-"""Time the build variants of libaquagym.so (make -C aquaticgymenv_b200/csrc variants) with the
-bench workload, one subprocess per variant.  usage (GPU box): python tools/tune.py [envs] [steps]"""
+"""Time the build variants of libaquagym.so (make -C aquaticgymenv_b200/csrc variant NAME=.. FLAGS=..)
+on ONE box, one subprocess per variant and workload: the bench headline (AquaEnv-v1, default
+obstacles) and the 64-obstacle stress map.  Boxes differ by a few per cent, so variants are only
+comparable within one call.  usage (GPU box): python tools/tune.py [envs] [steps]"""
 import glob
 import json
 import os
@@ -22,3 +24,11 @@ for lib in libs:
             os.path.basename(lib), j["value"], j["roofline"]["frac"], j["ms_per_step"]), flush=True)
     except Exception:
         print(os.path.basename(lib), "FAILED", out.stdout[-300:], out.stderr[-600:], flush=True)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config_rate.py"), "AquaEnv-v0", str(1 << 22),
+                          "float32", "dense64", "100"], env=env, capture_output=True, text=True)
+    try:
+        j = json.loads(out.stdout.strip().splitlines()[-1])
+        print("%-34s %.4g env-steps/s  dense64 map, 2^22 envs, %.1f us/step" % (
+            "", j["env_steps_per_s"], j["us_per_step"]), flush=True)
+    except Exception:
+        print(os.path.basename(lib), "dense64 FAILED", out.stdout[-300:], out.stderr[-600:], flush=True)
