@@ -1479,12 +1479,13 @@ static int sorted_rows(int k, const double* rows5, double* out5) {
 }
 
 // Classification of one grid cell (float64, 0.05 px safety margin that also covers the rounding of
-// the cell index on the device).  Returns kCellBlocked when the whole cell lies inside one
-// obstacle's clearance region (obstacle inflated by the radius 2.5) shrunk by the margin: the
-// distance to a convex obstacle is a convex function of the position, so its maximum over the cell
-// is attained at a corner.  Otherwise the mask of the obstacles whose clearance region, grown by
-// the margin, touches the cell.
-static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy) {
+// the cell index on the device).  *blocked: the whole cell lies inside one obstacle's clearance
+// region (obstacle inflated by the radius 2.5) shrunk by the margin -- the distance to a convex
+// obstacle is a convex function of the position, so its maximum over the cell is attained at a
+// corner.  Otherwise the return value is the mask of the obstacles whose clearance region, grown
+// by the margin, touches the cell.  (With 64 obstacles a genuine mask can equal kCellBlocked, hence
+// the separate flag.)
+static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy, bool* blocked) {
     constexpr double kMargin = 0.05;
     const double cw = 100.0 / kGridDim;
     const double x0 = cx * cw, x1 = x0 + cw, y0 = cy * cw, y1 = y0 + cw;
@@ -1501,12 +1502,16 @@ static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy) 
             const double ex = std::max(std::fabs(px - o[0]) - hx, 0.0), ey = std::max(std::fabs(py - o[1]) - hy, 0.0);
             far2 = std::max(far2, ex * ex + ey * ey);
         }
-        if (reach > kMargin && far2 <= (reach - kMargin) * (reach - kMargin)) return kCellBlocked;
+        if (reach > kMargin && far2 <= (reach - kMargin) * (reach - kMargin)) {
+            *blocked = true;
+            return kCellBlocked;
+        }
         // distance between the obstacle's box and the cell rectangle
         const double dx = std::max(std::max(x0 - (o[0] + hx), (o[0] - hx) - x1), 0.0);
         const double dy = std::max(std::max(y0 - (o[1] + hy), (o[1] - hy) - y1), 0.0);
         if (dx * dx + dy * dy <= (reach + kMargin) * (reach + kMargin)) m |= 1ull << i;
     }
+    *blocked = false;
     return m;
 }
 
@@ -1517,11 +1522,11 @@ static unsigned long long cell_mask(int k, const double* rows5, int cx, int cy) 
 template <typename R> static bool fill_table(int k, const double* rows5, ObstacleTable<R>* t) {
     memset(t, 0, sizeof(*t));
     bool grid_ok = k > kGridMinObstacles;
-    const unsigned long long full = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
     for (int cy = 0; cy < kGridDim; ++cy)
         for (int cx = 0; cx < kGridDim; ++cx) {
-            unsigned long long m = cell_mask(k, rows5, cx, cy);
-            if (m != kCellBlocked && k >= 64 && m == full) grid_ok = false;
+            bool blocked = false;
+            const unsigned long long m = cell_mask(k, rows5, cx, cy, &blocked);
+            if (!blocked && m == kCellBlocked) grid_ok = false;  // a genuine full mask: ambiguous
             t->cell[cy * kGridDim + cx] = m;
         }
     for (int i = 0; i < k; ++i) {

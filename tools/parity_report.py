@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Measured parity of the float32 (throughput) and float64 instantiations against the C oracle:
 flag-flip rate, decision margins of the flips, and drift, over lock-step random rollouts with
-teacher forcing after a flip (SURVEY.md section 7.3 H3 iv).  Prints one JSON object.
+teacher forcing after a flip (SURVEY.md section 7.3 H3 iv), for both kernel families.  Prints one
+JSON object.
 usage (GPU box): python tools/parity_report.py [envs] [steps]"""
 import json
 import os
@@ -22,8 +23,10 @@ threads = len(os.sched_getaffinity(0))
 out = {"envs": n, "steps": steps, "configs": []}
 for name, cont, tab in [("AquaEnv-v1", False, "v1"), ("AquaContinuousEnv-v2", True, "v2"), ("AquaEnv dense64", False, "dense64")]:
     table = np.load(os.path.join(ROOT, "tests", "golden", tab + "_table.npy"))
-    for precision in ("float32", "float64"):
-        env = AquaVecEnv(n, continuous=cont, obstacles=table, seed=11, precision=precision, device="cuda:0")
+    # "wide": whole warps run step_stream_kernel (what large slabs run); "narrow": step_kernel, V = 1
+    for precision, geometry in [("float32", "wide"), ("float64", "wide"), ("float32", "narrow"), ("float64", "narrow")]:
+        env = AquaVecEnv(n, continuous=cont, obstacles=table, seed=11, precision=precision, geometry=geometry,
+                         device="cuda:0")
         ref = ao.OracleVecEnv(n, continuous=cont, obstacles=table, seed=11)
         env.reset()
         ref.reset()
@@ -44,7 +47,9 @@ for name, cont, tab in [("AquaEnv-v1", False, "v1"), ("AquaContinuousEnv-v2", Tr
                 flip_margins.extend(margin[differ].tolist())
                 env.set_state(torch.as_tensor(want))
         out["configs"].append({
-            "env": name, "precision": precision, "env_steps": n * steps, "flag_flips": flips,
+            "env": name, "precision": precision, "geometry": geometry,
+            "kernel": "step_stream_kernel" if geometry == "wide" else "step_kernel (V = 1)",
+            "env_steps": n * steps, "flag_flips": flips,
             "flips_per_env_step": flips / (n * steps),
             "max_margin_of_a_flip_px": max(flip_margins) if flip_margins else None,
             "max_abs_position_error_px": worst_pos, "max_abs_heading_error_rad": worst_ang,
