@@ -111,9 +111,9 @@ aqua::StepArgs base_args(aqua_env* env) {
 int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aqua::LaunchGeom* g) {
     const int wide = aqua::envs_per_thread(env->cfg.precision);
     const bool narrow = env->cfg.geometry == AQUA_GEOM_NARROW ||
-                        (env->cfg.geometry == AQUA_GEOM_AUTO && n < (int64_t)256 * wide * env->sm_count * 2);
+                        (env->cfg.geometry == AQUA_GEOM_AUTO && n < (int64_t)256 * wide * env->sm_count * 2);  // ~300k envs
     const int V = narrow ? 1 : wide;
-    const int threads = narrow ? 128 : 256;
+    const int threads = narrow ? aqua::kNarrowThreads : aqua::kWideThreads;
     const int ti = narrow ? 0 : 1;
     const int per_sm = rollout ? env->occ_rollout[ti] : env->occ_step[action_dtype][ti];
     const int64_t tiles = (n + (int64_t)threads * V - 1) / ((int64_t)threads * V);
@@ -285,7 +285,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
 
     AQ_CREATE(aqua::configure_kernels(cfg->precision));
     for (int ti = 0; ti < 2; ++ti) {
-        const int threads = ti == 0 ? 128 : 256;
+        const int threads = ti == 0 ? aqua::kNarrowThreads : aqua::kWideThreads;
         const int v = ti == 0 ? 1 : aqua::envs_per_thread(cfg->precision);
         for (int act = 0; act < 4; ++act) {
             AQ_CREATE(aqua::step_occupancy(cfg->precision, v, act, threads, use_grid, &env->occ_step[act][ti]));

@@ -865,8 +865,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     // memory system is longer than one tile): SMs do not run at the same speed (distance to the
     // memory partitions), and a static partition makes the kernel as slow as its slowest SM.
     // One counter cannot serve a claim per 128 envs (same-address atomics retire about one per
-    // 1.5 ns), so warp w of every CTA draws from pool w: kTilePools counters on separate lines,
-    // pool w owning the dynamic tiles congruent to w.  Every pool has one warp on every CTA, hence
+    // 1.5 ns), so warp w of every CTA draws from pool w mod n_pools: up to kTilePools counters on
+    // separate lines, pool q owning the dynamic tiles congruent to q modulo n_pools.  Every pool has
+    // the same number of warps on every CTA (warps per CTA: up to 8, or a multiple of 8), hence
     // the pools drain at the same rate.
     // Two staging buffers, prefetch distance two tiles: a buffer is refilled (with the tile after
     // next) as soon as its slices have been read into registers, so every copy has two tile
@@ -880,7 +881,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     uint32_t i1 = i + n_warps * kWarpTile;   // the next one (in flight)
     uint32_t i2 = i1 + n_warps * kWarpTile;  // the one after (to be prefetched)
     uint32_t i3 = i2 + n_warps * kWarpTile;  // and its successor
-    const uint32_t pool = (threadIdx.x >> 5) % kTilePools;
+    // pools in use = warps per CTA, at most kTilePools: every pool needs a drawer on every CTA
+    const uint32_t n_pools = min((uint32_t)kTilePools, blockDim.x >> 5);
+    const uint32_t pool = (threadIdx.x >> 5) % n_pools;
     uint32_t* const my_ctr = p.tile_ctr + pool * kTilePoolStride + (lane_id & p.tile_lane_mask);
     // ptxas lowers an atomic add on a warp-uniform address to the warp-aggregated form, whose
     // broadcast shuffle waits for the result on the spot; tile_lane_mask = 0 (a parameter) keeps
@@ -1005,7 +1008,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             // the claim of the previous tile is consumed here, after this tile's stores
             asm volatile("" : "+r"(claim_old) : : "memory");
             const uint32_t i4 =
-                old_valid ? (4u * n_warps + __shfl_sync(0xffffffffu, claim_old, 0) * kTilePools + pool) * kWarpTile + lane_off : n;
+                old_valid ? (4u * n_warps + __shfl_sync(0xffffffffu, claim_old, 0) * n_pools + pool) * kWarpTile + lane_off : n;
             i = i1;
             i1 = i2;
             i2 = i3;

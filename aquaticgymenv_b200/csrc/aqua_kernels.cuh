@@ -9,11 +9,21 @@
 
 namespace aqua {
 
-constexpr int kMaxThreads = 256;   // threads per CTA upper bound (launch bounds)
+// CTA shape of the wide kernels (V envs per thread): kWideThreads threads, compiled for kMinBlocks
+// resident CTAs per SM.  Narrow launches (V = 1) use 128-thread CTAs of the same kernels.
+// Measured on one box (profiles/r01F_cta_shape_ab.txt): 256 x 2 (112 registers, 16 warps per SM)
+// 8.27e10 env-steps/s; 192 x 3 (96 registers, 18 warps per SM) 8.15e10, and 11 % slower on the
+// 64-obstacle map: the registers are worth more than the two extra warps.
+#ifndef AQUA_WIDE_THREADS
+#define AQUA_WIDE_THREADS 256
+#endif
 #ifndef AQUA_MIN_BLOCKS
 #define AQUA_MIN_BLOCKS 2
 #endif
-constexpr int kMinBlocks = AQUA_MIN_BLOCKS;  // resident CTAs per SM the kernels are compiled for
+constexpr int kWideThreads = AQUA_WIDE_THREADS;
+constexpr int kNarrowThreads = 128;
+constexpr int kMaxThreads = kWideThreads > kNarrowThreads ? kWideThreads : kNarrowThreads;  // launch bounds
+constexpr int kMinBlocks = AQUA_MIN_BLOCKS;
 // dynamic tile claims of the streaming kernel: kTilePools counters + the finished-CTA count, one
 // 128-byte line each
 constexpr int kTilePools = 8;
