@@ -227,6 +227,41 @@ def test_dense_table_without_grid(precision):
     assert flips == 0 if precision == "float64" else flips <= 3
 
 
+def _random_table(rs, k):
+    """k obstacles, circles and rectangles mixed, sizes from slivers to a fifth of the world,
+    overlaps allowed, a few hanging over the border; rows {cx, cy, type, a, b} (aqua.py:56-68)."""
+    rows = []
+    for _ in range(k):
+        cx, cy = rs.uniform(-3.0, 103.0, 2)
+        if rs.rand() < 0.5:
+            rows.append([cx, cy, 0.0, rs.choice([0.0, 0.3, 2.0, 6.0, 11.0]) + rs.uniform(0.0, 2.0), 0.0])
+        else:
+            w, h = rs.choice([0.2, 1.0, 5.0, 14.0], 2) + rs.uniform(0.0, 3.0, 2)
+            rows.append([cx, cy, 1.0, w, h])
+    return np.asarray(rows, np.float64).reshape(k, 5)
+
+
+@pytest.mark.parametrize("k", [1, 5, 12, 13, 24, 40, 64])
+@pytest.mark.parametrize("geometry", ["wide", "narrow"])
+def test_random_obstacle_tables_f64(k, geometry):
+    """Random tables on both sides of the culling-grid threshold (12): brute force and grid (cell
+    masks, blocked cells of circles and rectangles) must give the oracle's flags exactly."""
+    rs = np.random.RandomState(1000 + k)
+    for trial in range(3):
+        cfg = dict(continuous=bool(trial & 1), table=_random_table(rs, k), waves=True, seed=20 + trial,
+                   env_id_base=trial)
+        flips, _ = _lockstep(cfg, 2048, 60, "float64", geometry=geometry)
+        assert flips == 0, (k, trial)
+
+
+@pytest.mark.parametrize("k", [13, 64])
+def test_random_obstacle_tables_f32(k):
+    rs = np.random.RandomState(2000 + k)
+    cfg = dict(continuous=False, table=_random_table(rs, k), waves=True, seed=31, env_id_base=0)
+    flips, _ = _lockstep(cfg, 4096, 100, "float32", geometry="wide")
+    assert flips <= 3, flips
+
+
 def test_wide_and_narrow_kernels_agree_bitwise():
     """The two kernel families run the same arithmetic: identical state, rewards and statistics,
     also across the auto-selection threshold (a ragged slab large enough for the wide path)."""
