@@ -26,6 +26,9 @@ template <typename T, int V> __device__ __forceinline__ Pack<T, V> ld_pack(const
 template <typename T, int V> __device__ __forceinline__ void st_pack(T* p, const Pack<T, V>& v) {
     *reinterpret_cast<Pack<T, V>*>(p) = v;
 }
+#ifndef AQUA_MEMBENCH
+#define AQUA_MEMBENCH 0
+#endif
 // Stores of the streaming kernel.  AQUA_STORE_CS=1 makes them evict-first (st.global.cs).  Measured
 // on one B200 box (tools/tune.py, 2^24 envs): plain 8.20e10 env-steps/s, evict-first 7.97e10 -- the
 // deferred reset writes 4-byte values into lines the owner stored a few tiles earlier, and those
@@ -930,6 +933,19 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             const bool new_valid = old_valid && i3 < n;  // the pool had tiles left at the last look
             if (new_valid) claim_tile(claim_new);
 
+#if AQUA_MEMBENCH
+            // Measurement build only (make variant FLAGS=-DAQUA_MEMBENCH=1): the data movement of
+            // this kernel -- staging pipeline, dynamic tiles, every load consumed, every store
+            // issued -- without the step's arithmetic.  Flags stay 0 (no resets).  Timed next to the
+            // real kernel on one box it gives the ceiling of this structure; never the shipped build.
+            Pack<R, V> vrew, ox = vx, oy = vy, oth = vth, owx = vwx, owy = vwy;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                vrew.v[j] = vgx.v[j] + vgy.v[j];
+                otw.v[j] = vtw.v[j] + act.w[j];
+            }
+            st.steps += V;
+#else
             Drive<R> dr[V];
             if constexpr (ACT == AQUA_ACT_F32X2) {
                 decode_drives<R, ACT, V>(act, dr, st.bad);
@@ -990,6 +1006,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
                 for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), otw.v[j] & kTimeMask);
             }
 
+#endif
             // ---- stores (the goal only changes at reset: phase B writes it) ----
             const size_t off = (size_t)i * sizeof(R);
             st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off), ox);
