@@ -841,7 +841,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     constexpr int kActPiece = kActBytes < 16 ? kActBytes : 16;
     constexpr int kActPieces = kActBytes / kActPiece;
     constexpr int kActWords = kActBytes / 4;
-    static_assert(stream_supported<ACT, V>() && kSlot == 16 && kStages == 2, "streaming kernel layout");
+    static_assert(stream_supported<ACT, V>() && (kSlot == 16 || kSlot == 8) && kStages == 2, "streaming kernel layout");
 
     const uint32_t n = p.n_stream;
     const bool autoreset = p.w.autoreset != 0;
