@@ -185,7 +185,9 @@ constexpr double kRectR2 = 6.25;  // (boat or goal radius 2.5)^2, aqua.py:72,75
 template <typename R, int V>
 __device__ __forceinline__ void obstacle_clearance(const ObstacleView<R>& tab, int k_circ, int k_obst,
                                                    const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
-#pragma unroll 2
+    // one obstacle per iteration (the body already carries V independent chains): with runtime
+    // counts an unrolled loop spends more on its remainder handling than it saves
+#pragma unroll 1
     for (int k = 0; k < k_circ; ++k) {
         const ObstacleBox<R> o = tab.box[k];
 #pragma unroll
@@ -194,6 +196,7 @@ __device__ __forceinline__ void obstacle_clearance(const ObstacleView<R>& tab, i
             clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, -o.a)));
         }
     }
+#pragma unroll 1
     for (int k = k_circ; k < k_obst; ++k) {
         const ObstacleBox<R> o = tab.box[k];
 #pragma unroll
