@@ -29,6 +29,18 @@ template <typename T, int V> __device__ __forceinline__ void st_pack(T* p, const
 #ifndef AQUA_MEMBENCH
 #define AQUA_MEMBENCH 0
 #endif
+// AQUA_SCHED_WARP=1: the streaming kernel runs one extra warp per CTA that does all tile claims and
+// feeds the worker warps through shared-memory rings (see step_stream_kernel), so that no worker
+// waits for the reply of a global atomic.  Correct (all GPU tests pass with it) and NOT faster:
+// 8.335e10 vs 8.304e10 env-steps/s on one box, 3 % slower on the 64-obstacle map
+// (profiles/r01L_scheduler_warp_ab.txt) -- the time a worker spends waiting for its claim is time
+// the other warps of its scheduler use.  Off by default.
+#ifndef AQUA_SCHED_WARP
+#define AQUA_SCHED_WARP 0
+#endif
+constexpr int kSchedThreads = AQUA_SCHED_WARP ? 32 : 0;  // added to the CTA of the streaming kernel
+constexpr int kRing = 4;                                 // tiles queued per worker warp
+constexpr uint32_t kRingEmpty = 0xffffffffu, kRingDone = 0xfffffffeu;
 // Stores of the streaming kernel.  AQUA_STORE_CS=1 makes them evict-first (st.global.cs).  Measured
 // on one B200 box (tools/tune.py, 2^24 envs): plain 8.20e10 env-steps/s, evict-first 7.97e10 -- the
 // deferred reset writes 4-byte values into lines the owner stored a few tiles earlier, and those
@@ -822,11 +834,16 @@ template <int ACT, int V> constexpr bool stream_supported() {
 }
 
 template <typename R, int V, int ACT, bool WAVES>
-__global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(const __grid_constant__ StepArgs p) {
+__global__ void __launch_bounds__(kMaxThreads + kSchedThreads, kMinBlocks)
+step_stream_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[AQUA_N_STATS];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     __shared__ DriveSlot<R> s_drive[3];
+#if AQUA_SCHED_WARP
+    __shared__ uint32_t s_ring[kMaxThreads / 32][kRing];
+    if (threadIdx.x < (kMaxThreads / 32) * kRing) (&s_ring[0][0])[threadIdx.x] = kRingEmpty;
+#endif
     const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
@@ -859,7 +876,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     };
 
     ThreadStats st;
-    WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
+    WarpResetQueue<V>& wq = s_wq[(threadIdx.x >> 5) % (kMaxThreads / 32)];  // (the scheduler warp queues nothing)
     int n_queued = 0;  // warp-uniform
 
     // Work distribution: a warp tile is 32 V consecutive envs.  Every warp starts with four
@@ -876,10 +893,74 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     // next) as soon as its slices have been read into registers, so every copy has two tile
     // times to land.
     const uint32_t lane_off = (threadIdx.x & 31u) * V;
+    constexpr uint32_t kWarpTile = 32u * V;
+#if AQUA_SCHED_WARP
+    // Scheduler warp: the last warp of the CTA does every tile claim, so that no worker ever waits
+    // for the reply of a global atomic (measured: 21 % of a worker's time when it claimed its own
+    // tiles).  Lane l feeds worker warp l through the ring s_ring[l]: it claims two tiles at a time
+    // (atomicAdd 2 on the worker's pool) whenever two slots are free and writes kRingDone when the
+    // pool is dry.  A worker pops one tile per tile it processes and always drains its ring up to
+    // kRingDone, so no claimed tile is lost.  All spins are bounded (trap, not hang).
+    const uint32_t n_workers = (blockDim.x >> 5) - 1u;
+    const uint32_t n_warps = gridDim.x * n_workers;  // worker warps of the launch
+    const uint32_t n_pools = min((uint32_t)kTilePools, n_workers);
+    const uint32_t n_tiles = n / kWarpTile;
+    const bool is_sched = (threadIdx.x >> 5) == n_workers;
+    constexpr uint32_t kStatic = 3u;  // statically assigned tiles per worker
+    if (is_sched) {
+        const uint32_t l = threadIdx.x & 31u;
+        if (l < n_workers) {
+            volatile uint32_t* const ring = s_ring[l];
+            const uint32_t q = l % n_pools;
+            uint32_t* const ctr = p.tile_ctr + q * kTilePoolStride;
+            uint32_t head = 0u;
+            for (;;) {
+                uint32_t spins = 0u;
+                while (ring[head % kRing] != kRingEmpty || ring[(head + 1u) % kRing] != kRingEmpty) {
+                    __nanosleep(100);
+                    if (++spins > (1u << 24)) __trap();
+                }
+                const uint32_t c = atomicAdd(ctr, 2u);  // positions c, c + 1 of pool q's tile sequence
+                const uint32_t t0 = kStatic * n_warps + c * n_pools + q, t1 = t0 + n_pools;
+                if (t0 >= n_tiles) { ring[head % kRing] = kRingDone; break; }
+                ring[head % kRing] = t0;
+                if (t1 >= n_tiles) { ring[(head + 1u) % kRing] = kRingDone; break; }
+                ring[(head + 1u) % kRing] = t1;
+                head += 2u;
+            }
+        }
+    }
+    const uint32_t warp_g = blockIdx.x * n_workers + (threadIdx.x >> 5);
+    uint32_t i = is_sched ? n : warp_g * kWarpTile + lane_off;       // this tile
+    uint32_t i1 = is_sched ? n : i + n_warps * kWarpTile;            // the next one (in flight)
+    uint32_t i2 = is_sched ? n : i1 + n_warps * kWarpTile;           // the one after (to be prefetched)
+    volatile uint32_t* const my_ring = s_ring[is_sched ? 0u : (threadIdx.x >> 5)];
+    uint32_t ring_head = 0u;
+    bool ring_done = is_sched;  // warp-uniform
+    // next tile of this worker (env index of this thread's slice), n once the pool is dry
+    auto ring_pop = [&]() -> uint32_t {
+        if (ring_done) return n;
+        uint32_t t = 0u;
+        if ((threadIdx.x & 31u) == 0u) {
+            uint32_t spins = 0u;
+            while ((t = my_ring[ring_head % kRing]) == kRingEmpty) {
+                __nanosleep(50);
+                if (++spins > (1u << 24)) __trap();
+            }
+            if (t != kRingDone) my_ring[ring_head % kRing] = kRingEmpty;  // hand the slot back
+        }
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t == kRingDone) {
+            ring_done = true;
+            return n;
+        }
+        ++ring_head;
+        return t * kWarpTile + lane_off;
+    };
+#else
     uint32_t lane_id;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_id));
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);  // of the launch
-    constexpr uint32_t kWarpTile = 32u * V;
     uint32_t i = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kWarpTile + lane_off;  // this tile
     uint32_t i1 = i + n_warps * kWarpTile;   // the next one (in flight)
     uint32_t i2 = i1 + n_warps * kWarpTile;  // the one after (to be prefetched)
@@ -898,6 +979,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
     uint32_t claim_old = 0u;      // issued during the previous tile: the successor of i3
     bool old_valid = i3 < n;      // warp-uniform
     if (old_valid) claim_tile(claim_old);
+#endif
     if (i < n) prefetch(s_cur, i);
     cp_async_commit();
     if (i1 < n) prefetch(s_nxt, i1);
@@ -906,7 +988,9 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
         const bool live = i < n;  // warp-uniform: n is a multiple of 32 V
         uint32_t fw = 0u;
         Pack<uint32_t, V> otw;
+#if !AQUA_SCHED_WARP
         uint32_t claim_new = 0u;
+#endif
         const uint32_t i_done = i;
         if (live) {
             cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
@@ -930,8 +1014,10 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             const ActVals<ACT, V> act = actions_from_raw<ACT, V, kActWords>(araw);
             if (i2 < n) prefetch(s_cur, i2);  // refill the buffer just read
             cp_async_commit();
+#if !AQUA_SCHED_WARP
             const bool new_valid = old_valid && i3 < n;  // the pool had tiles left at the last look
             if (new_valid) claim_tile(claim_new);
+#endif
 
 #if AQUA_MEMBENCH
             // Measurement build only (make variant FLAGS=-DAQUA_MEMBENCH=1): the data movement of
@@ -1022,6 +1108,11 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             const uint32_t t = s_cur;
             s_cur = s_nxt;
             s_nxt = t;
+#if AQUA_SCHED_WARP
+            i = i1;
+            i1 = i2;
+            i2 = ring_pop();
+#else
             // the claim of the previous tile is consumed here, after this tile's stores
             asm volatile("" : "+r"(claim_old) : : "memory");
             const uint32_t i4 =
@@ -1032,6 +1123,7 @@ __global__ void __launch_bounds__(kMaxThreads, kMinBlocks) step_stream_kernel(co
             i3 = i4;
             claim_old = claim_new;
             old_valid = new_valid;
+#endif
         }
         if (autoreset) {  // phase B, warp-collective
             if (live && __any_sync(0xffffffffu, fw != 0u)) n_queued = reset_queue_push<V>(wq, n_queued, fw, i_done, otw.v);
@@ -1227,8 +1319,9 @@ struct StreamLaunchOp {
     template <typename R, int V, int ACT> cudaError_t run() const {
         if constexpr (stream_supported<ACT, V>()) {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(a.w.use_grid);
-            if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
-            else step_stream_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
+            const int threads = g.threads + kSchedThreads;
+            if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, threads, smem, s>>>(a);
+            else step_stream_kernel<R, V, ACT, false><<<g.blocks, threads, smem, s>>>(a);
             return cudaGetLastError();
         } else {
             return cudaErrorNotSupported;
@@ -1345,8 +1438,10 @@ struct StreamOccupancyOp {
         if constexpr (stream_supported<ACT, V>()) {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(use_grid);
             if (waves)
-                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>, threads, smem);
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>, threads, smem);
+                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>,
+                                                                     threads + kSchedThreads, smem);
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>,
+                                                                 threads + kSchedThreads, smem);
         } else {
             *out = 0;
             return cudaSuccess;
