@@ -69,7 +69,10 @@ SIGNATURES = {
     "aqua_set_state": (_int, [_vp, _vp, _vp]),
     "aqua_stats_reduce": (_int, [_vp, _vp, _vp, _int]),
     "aqua_get_stats": (_int, [_vp, _vp, C.POINTER(C.c_int64), _int]),
+    "aqua_obstacle_grid": (_int, [_vp, _int, _vp, _vp, C.POINTER(_int)]),
 }
+GRID_DIM = 48                      # AQUA_GRID_DIM
+CELL_BLOCKED = 0xFFFFFFFFFFFFFFFF  # AQUA_CELL_BLOCKED
 
 _lib = None
 
@@ -99,3 +102,19 @@ def load():
 def check(status):
     if status != OK:
         raise AquaError(status, load().aqua_last_error().decode("utf-8", "replace"))
+
+
+def obstacle_grid(obstacles):
+    """aqua_obstacle_grid: the culling grid the kernels use for an obstacle table [K, 5]
+    (host-only, no CUDA device needed).  Returns (rows [K, 5] = {cx, cy, half_x, half_y, reach^2} in
+    the kernels' order, cells uint64 [GRID_DIM, GRID_DIM] indexed [cy, cx], use_grid)."""
+    import numpy as np
+    tab = np.ascontiguousarray(np.asarray(obstacles, np.float64).reshape(-1, 5))
+    k = tab.shape[0]
+    rows = np.zeros((max(k, 1), 5), np.float64)
+    cells = np.zeros(GRID_DIM * GRID_DIM, np.uint64)
+    use_grid = C.c_int(0)
+    check(load().aqua_obstacle_grid(tab.ctypes.data if k else None, k, rows.ctypes.data, cells.ctypes.data,
+                                    C.byref(use_grid)))
+    return rows[:k], cells.reshape(GRID_DIM, GRID_DIM), bool(use_grid.value)
+

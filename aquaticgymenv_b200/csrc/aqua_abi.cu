@@ -510,4 +510,20 @@ int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear) {
     return AQUA_OK;
 }
 
+int aqua_obstacle_grid(const double* obstacles, int n_obstacles, double* rows_out, uint64_t* cells_out,
+                       int* use_grid_out) {
+    if (n_obstacles < 0 || n_obstacles > AQUA_MAX_OBSTACLES)
+        return fail(AQUA_ERR_INVALID, "n_obstacles must be in [0, %d], got %d", AQUA_MAX_OBSTACLES, n_obstacles);
+    if ((n_obstacles > 0 && (obstacles == nullptr || rows_out == nullptr)) || cells_out == nullptr || use_grid_out == nullptr)
+        return fail(AQUA_ERR_INVALID, "obstacles, rows_out, cells_out and use_grid_out must not be NULL");
+    void* h_tab = malloc(aqua::obstacle_table_bytes(AQUA_F64));
+    if (h_tab == nullptr) return fail(AQUA_ERR_ALLOC, "out of host memory");
+    double h_tab64[AQUA_MAX_OBSTACLES * 5] = {0};
+    aqua::build_obstacle_tables(AQUA_F64, n_obstacles, obstacles, h_tab, h_tab64, use_grid_out);
+    aqua::copy_table_cells(AQUA_F64, h_tab, reinterpret_cast<unsigned long long*>(cells_out));
+    free(h_tab);
+    if (n_obstacles > 0) memcpy(rows_out, h_tab64, sizeof(double) * 5 * (size_t)n_obstacles);
+    return AQUA_OK;
+}
+
 }  // extern "C"

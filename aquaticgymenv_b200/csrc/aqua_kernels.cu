@@ -1683,4 +1683,11 @@ int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_h
     return k_circ;
 }
 
+void copy_table_cells(int precision, const void* tab_host, unsigned long long* out) {
+    static_assert(kGridDim == AQUA_GRID_DIM && kCellBlocked == AQUA_CELL_BLOCKED, "header and kernels agree on the grid");
+    const unsigned long long* cell = precision == AQUA_F64 ? reinterpret_cast<const ObstacleTable<double>*>(tab_host)->cell
+                                                            : reinterpret_cast<const ObstacleTable<float>*>(tab_host)->cell;
+    memcpy(out, cell, sizeof(unsigned long long) * kGridCells);
+}
+
 }  // namespace aqua

@@ -121,5 +121,7 @@ size_t obstacle_table_bytes(int precision);
 // enough for the culling grid and its cell masks are unambiguous (see kCellBlocked)
 int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host,
                           int* use_grid);
+// the cell masks of a host table built by build_obstacle_tables (aqua_obstacle_grid)
+void copy_table_cells(int precision, const void* tab_host, unsigned long long* out);
 
 }  // namespace aqua

@@ -195,6 +195,24 @@ int aqua_stats_reduce(aqua_env* env, void* stream, int64_t* out_dev, int clear);
 /* Same into a HOST int64[AQUA_N_STATS]; synchronises `stream`. */
 int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear);
 
+/* ---- obstacle table inspection (host only) --------------------------------------------- */
+/* The obstacle tests of aqua.py:429-451 are exact for every table; tables of more than 12
+ * obstacles are first culled through a grid of AQUA_GRID_DIM x AQUA_GRID_DIM cells over the
+ * 100 x 100 world.  This returns that grid as the kernels would use it, for tests of its
+ * classification.  Pure host computation: needs no CUDA device and no handle.
+ *   obstacles  : HOST [n_obstacles][5], as in aqua_config
+ *   rows_out   : HOST double[n_obstacles][5] = {cx, cy, half_x, half_y, reach^2} in the kernels'
+ *                order (circles first; a circle has zero half extents): a boat or goal centre p
+ *                collides with row i iff max(|px-cx|-half_x,0)^2 + max(|py-cy|-half_y,0)^2 <= reach^2
+ *   cells_out  : HOST uint64[AQUA_GRID_DIM * AQUA_GRID_DIM], cell = cy * AQUA_GRID_DIM + cx with
+ *                cx = (int)(float(px) * AQUA_GRID_DIM / 100) clamped: bit i set = row i may be
+ *                reached from that cell; AQUA_CELL_BLOCKED = every point of the cell collides
+ *   use_grid_out : 1 if the kernels cull this table through the grid, 0 if they test all rows */
+#define AQUA_GRID_DIM 48
+#define AQUA_CELL_BLOCKED 0xFFFFFFFFFFFFFFFFull
+int aqua_obstacle_grid(const double* obstacles, int n_obstacles, double* rows_out, uint64_t* cells_out,
+                       int* use_grid_out);
+
 #ifdef __cplusplus
 }
 #endif
