@@ -51,13 +51,15 @@ def test_random_policy_statistics_match_reference_scale():
     env.close()
 
 
-def test_batched_dqn_trains_on_the_gpu_env(tmp_path):
+@pytest.mark.parametrize("cuda_graph", [False, True])
+def test_batched_dqn_trains_on_the_gpu_env(tmp_path, cuda_graph):
     """dqn_train_policy.py:19-21 flow on the batched env: a short run improves on the random
-    policy's success rate and writes the reference's progress files."""
+    policy's success rate and writes the reference's progress files.  Eagerly, and with one CUDA
+    graph per vector step (the env's launches captured together with the torch ops)."""
     import torch
     from aquaticgymenv_b200 import dqn, gym_aqua, policies
     env = gym_aqua.make("AquaEnv-v0", num_envs=2048, seed=5)
-    agent = dqn.BatchedDQN(env, save_directory=str(tmp_path), save_freq=5000,
+    agent = dqn.BatchedDQN(env, save_directory=str(tmp_path), save_freq=5000, cuda_graph=cuda_graph,
                            hyperparams={"EPSILON_DECAY": 20000, "BUFFER_SIZE": 200000,
                                         "MINIBATCH_SIZE": 512, "UPDATES_PER_STEP": 2})
     agent.train(env_steps=1500)
@@ -66,4 +68,31 @@ def test_batched_dqn_trains_on_the_gpu_env(tmp_path):
     res = policies.evaluate(env, policies.GreedyQPolicy(env, agent.q_function), episodes=8000)
     assert res["success_rate"] > 0.25, res        # random policy: ~0.05; the reference reaches 0.94 after 15k episodes
     assert (tmp_path / "rewards.txt").exists() and (tmp_path / "success.txt").exists()
+    # the episodes the env counted are the episodes the agent logged (nothing lost in the device log)
+    assert env.stats()["episodes"] >= len(agent.reward_list) > 0
+    assert agent.exp_buffer.size == min(1500 * 2048, 200000) == int(agent.exp_buffer.size_dev.item())
     env.close()
+
+
+def test_dqn_graph_mode_reproduces_the_eager_run():
+    """The captured vector step must be the eager one: same seeds (the agent's generator in eager
+    mode, the default generator under capture, seeded alike and called alike) give the same
+    episode log and the same network, bit for bit.  A host value baked into the graph at capture
+    time (epsilon, replay cursor, episode count) would show up here."""
+    import torch
+    from aquaticgymenv_b200 import dqn, gym_aqua
+    out = []
+    for cuda_graph in (False, True):
+        env = gym_aqua.make("AquaEnv-v0", obstacles=True, num_envs=1024, seed=3)
+        agent = dqn.BatchedDQN(env, seed=7, cuda_graph=cuda_graph,
+                               hyperparams={"EPSILON_DECAY": 3000, "BUFFER_SIZE": 30000, "MINIBATCH_SIZE": 256})
+        agent.train(env_steps=300)   # the replay ring wraps (300 * 1024 > 30000), epsilon decays to its floor
+        out.append((list(agent.reward_list), list(agent.success_list),
+                    [p.detach().clone() for p in agent.q_function.parameters()],
+                    [p.detach().clone() for p in agent.q_function_target.parameters()],
+                    agent.exp_buffer.s.clone(), env.stats()))
+        env.close()
+    (r0, s0, w0, t0, b0, st0), (r1, s1, w1, t1, b1, st1) = out
+    assert len(r0) > 1000 and r0 == r1 and s0 == s1
+    assert all(torch.equal(a, b) for a, b in zip(w0, w1)) and all(torch.equal(a, b) for a, b in zip(t0, t1))
+    assert torch.equal(b0, b1) and st0 == st1
