@@ -272,7 +272,7 @@ struct ResetResult {
 
 // env.reset() for one env: aqua.py:100-126.  `ep` is the NEW episode index.  Try n of the
 // reference's `observation_space.sample()` sequence is Philox(env, ep, n, RESET).
-__device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
+inline __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
                                               const double* __restrict__ tab64, int k_obst,
                                               WorldFlags wf) {
     ResetResult o;

@@ -220,7 +220,7 @@ def test_ragged_sizes(n, precision, geometry):
 def test_dense_table_without_grid(precision):
     """64 identical circles: the cells on their common rim are reached by all 64 obstacles and lie
     inside none, so their mask would read as the 'blocked' sentinel of the culling grid.  The host
-    must fall back to the brute-force test for such a table (aqua_kernels.cu: fill_table)."""
+    must fall back to the brute-force test for such a table (aqua_tables.cu: fill_table)."""
     table = np.tile(np.array([[50.0, 50.0, 0.0, 6.0, 0.0]]), (64, 1))
     cfg = dict(continuous=False, table=table, waves=True, seed=11, env_id_base=3)
     flips, _ = _lockstep(cfg, 2048, 80, precision)
