@@ -419,6 +419,44 @@ def test_step_host_equals_device_step(precision):
     b.close()
 
 
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+def test_cuda_graph_replay_of_the_streaming_kernel(precision):
+    """Three steps captured in one CUDA graph and replayed 30 times give the state, rewards and
+    statistics of 90 eager steps, bit for bit.  n is not a multiple of the warp tile, so every step
+    is a streaming launch plus a tail launch; the streaming kernel's tile counters are rearmed by
+    the last CTA of each launch (no memset node), and 90 launches wrap the handle's 64 counter sets."""
+    torch = _torch()
+    cfg = _cfg("v1_discrete", seed=12)
+    n = 300000 + 77
+    a = _make_gpu(cfg, n, precision, autoreset=True, geometry="wide")
+    b = _make_gpu(cfg, n, precision, autoreset=True, geometry="wide")
+    a.reset()
+    b.reset()
+    pool = [a.random_actions(k).clone() for k in range(3)]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        b.step_flags(pool[0])      # one eager step on the capture stream first (lazy initialisation)
+    torch.cuda.current_stream().wait_stream(side)
+    a.step_flags(pool[0])
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        for k in range(3):
+            b.step_flags(pool[k])
+    for r in range(30):
+        graph.replay()
+        for k in range(3):
+            a.step_flags(pool[k])
+        if r % 10 == 9:
+            assert torch.equal(a.reward, b.reward) and torch.equal(a.flags, b.flags), r
+    torch.cuda.synchronize()
+    assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy())
+    sa, sb = a.stats(), b.stats()
+    assert sa == sb and sa["steps"] == 91 * n
+    a.close()
+    b.close()
+
+
 def test_sharding_invariance():
     """One slab of N envs == two slabs of N/2 with env_id_base set: bitwise (Philox is keyed by
     the global env id)."""
