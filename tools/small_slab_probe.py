@@ -27,6 +27,23 @@ for n in sizes:
     b.record()
     torch.cuda.synchronize()
     eager_us = a.elapsed_time(b) * 1e3 / 400
+    # the same launches through the bare C ABI with prebuilt arguments: what the Python wrapper adds
+    import ctypes as C
+    import time
+    from aquaticgymenv_b200 import _native as N
+    args = [(env._h, env._stream(), C.c_void_p(pool[k].data_ptr()), N.ACT_I32 if pool[k].dtype == torch.int32 else N.ACT_I64,
+             C.c_void_p(env.reward.data_ptr()), C.c_void_p(env.flags.data_ptr()), None) for k in range(4)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(400):
+        env.lib.aqua_step_ex(*args[k % 4])
+    t_issue_raw = (time.perf_counter() - t0) * 1e6 / 400
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(400):
+        env.step_flags(pool[k % 4])
+    t_issue_wrapped = (time.perf_counter() - t0) * 1e6 / 400
+    torch.cuda.synchronize()
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     g = torch.cuda.CUDAGraph()
@@ -44,6 +61,7 @@ for n in sizes:
     b.record()
     torch.cuda.synchronize()
     graph_us = a.elapsed_time(b) * 1e3 / 1000
-    print(json.dumps({"envs": n, "eager_us_per_step": eager_us, "graph_us_per_step": graph_us,
+    print(json.dumps({"envs": n, "eager_us_per_step": eager_us, "host_us_per_call_raw_abi": t_issue_raw,
+                      "host_us_per_call_python_wrapper": t_issue_wrapped, "graph_us_per_step": graph_us,
                       "graph_env_steps_per_s": n / graph_us * 1e6}), flush=True)
     env.close()
