@@ -12,9 +12,10 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from aquaticgymenv_b200 import gym_aqua  # noqa: E402
 
+geometry = os.environ.get("AQUA_PROBE_GEOMETRY", "auto")   # auto | wide | narrow
 sizes = [int(a) for a in sys.argv[1:]] or [65536, 131072, 1 << 20]
 for n in sizes:
-    env = gym_aqua.make("AquaEnv-v1", num_envs=n, seed=0)
+    env = gym_aqua.make("AquaEnv-v1", num_envs=n, seed=0, geometry=geometry)
     env.reset()
     pool = [env.random_actions(k).clone() for k in range(4)]
     for k in range(20):
@@ -61,7 +62,7 @@ for n in sizes:
     b.record()
     torch.cuda.synchronize()
     graph_us = a.elapsed_time(b) * 1e3 / 1000
-    print(json.dumps({"envs": n, "eager_us_per_step": eager_us, "host_us_per_call_raw_abi": t_issue_raw,
+    print(json.dumps({"envs": n, "geometry": geometry, "eager_us_per_step": eager_us, "host_us_per_call_raw_abi": t_issue_raw,
                       "host_us_per_call_python_wrapper": t_issue_wrapped, "graph_us_per_step": graph_us,
                       "graph_env_steps_per_s": n / graph_us * 1e6}), flush=True)
     env.close()
