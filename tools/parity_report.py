@@ -19,12 +19,17 @@ from tests.helpers import SCALE_POS, SCALE_REWARD, err_angle, err_scaled  # noqa
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
+# optional third argument "soak": only the headline table (AquaEnv-v1) and the streaming kernel, both
+# precisions -- for large slabs (e.g. 1048576 1000 soak: BASELINE's 1M envs, 1,000-step rollouts)
+soak = len(sys.argv) > 3 and sys.argv[3] == "soak"
 threads = len(os.sched_getaffinity(0))
 out = {"envs": n, "steps": steps, "configs": []}
-for name, cont, tab in [("AquaEnv-v1", False, "v1"), ("AquaContinuousEnv-v2", True, "v2"), ("AquaEnv dense64", False, "dense64")]:
+tables = [("AquaEnv-v1", False, "v1"), ("AquaContinuousEnv-v2", True, "v2"), ("AquaEnv dense64", False, "dense64")]
+for name, cont, tab in (tables[:1] if soak else tables):
     table = np.load(os.path.join(ROOT, "tests", "golden", tab + "_table.npy"))
     # "wide": whole warps run step_stream_kernel (what large slabs run); "narrow": step_kernel, V = 1
-    for precision, geometry in [("float32", "wide"), ("float64", "wide"), ("float32", "narrow"), ("float64", "narrow")]:
+    runs = [("float32", "wide"), ("float64", "wide"), ("float32", "narrow"), ("float64", "narrow")]
+    for precision, geometry in (runs[:2] if soak else runs):
         env = AquaVecEnv(n, continuous=cont, obstacles=table, seed=11, precision=precision, geometry=geometry,
                          device="cuda:0")
         ref = ao.OracleVecEnv(n, continuous=cont, obstacles=table, seed=11)
