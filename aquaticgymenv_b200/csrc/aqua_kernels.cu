@@ -8,13 +8,15 @@
 // bandwidth (65 B per discrete env-step).
 //
 // The kernels live in headers by family -- aqua_step_stream.cuh (K1s, large slabs),
-// aqua_step_general.cuh (K1 general step, K1r rollout), helpers in aqua_kernel_util.cuh, device
+// aqua_step_narrow.cuh (K1n, small slabs), aqua_step_general.cuh (K1 general step, K1r rollout),
+// helpers in aqua_kernel_util.cuh, device
 // arithmetic in aqua_device.cuh; this file holds the small kernels (K2 reset, K3 statistics, K4
 // state access) and every launcher.  Host-side tables: aqua_tables.cu.
 #include <algorithm>
 #include <cstring>
 
 #include "aqua_step_general.cuh"
+#include "aqua_step_narrow.cuh"
 #include "aqua_step_stream.cuh"
 
 namespace aqua {
@@ -216,11 +218,47 @@ static bool has_stream_kernel(int precision, int action_dtype) {
     return yes;
 }
 
-// Whole warps of wide threads go to the streaming kernel; what is left of the range (fewer than
-// 32 V envs), noise injection and the narrow geometry go to the general kernel.
+// narrow kernel: one env per thread, one CTA of kNarrowThreads per 128 envs (not persistent)
+struct NarrowLaunchOp {
+    const StepArgs& a;
+    int blocks;
+    cudaStream_t s;
+    template <typename R, int V, int ACT> cudaError_t run() const {
+        if (a.w.waves) step_narrow_kernel<R, ACT, true><<<blocks, kNarrowThreads, 0, s>>>(a);
+        else step_narrow_kernel<R, ACT, false><<<blocks, kNarrowThreads, 0, s>>>(a);
+        return cudaGetLastError();
+    }
+};
+
+// the fields the streaming and narrow kernels address with: base pointers at env_begin
+static void fill_offsets(StepArgs& b, const StepArgs& a, int precision, int action_dtype) {
+    const size_t es = precision == AQUA_F64 ? 8 : 4;
+    size_t ab = 4;
+    if (action_dtype == AQUA_ACT_I64 || action_dtype == AQUA_ACT_F32X2) ab = 8;
+    else if (action_dtype == AQUA_ACT_U8) ab = 1;
+    for (int pl = 0; pl < AQUA_N_PLANES; ++pl)
+        b.pl0[pl] = static_cast<const char*>(a.planes) + ((size_t)pl * (size_t)a.ld) * es +
+                    (size_t)a.env_begin * (pl == AQUA_PLANE_TIME ? 4 : es);
+    b.act0 = static_cast<const char*>(a.actions) + (size_t)a.env_begin * ab;
+    b.rew0 = static_cast<char*>(a.reward) + (size_t)a.env_begin * es;
+    b.flg0 = a.flags + a.env_begin;
+    b.tile_lane_mask = 0u;
+    b.env_id0 = (uint32_t)(a.w.env_id_base + (uint64_t)a.env_begin);
+}
+
+// Narrow geometry: the narrow kernel.  Wide geometry: whole warps of wide threads go to the
+// streaming kernel, what is left of the range (fewer than 32 V envs) to the general kernel.  Noise
+// injection (parity tests) always runs the general kernel.
 cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
     const int wide = envs_per_thread(precision);
     const int64_t n = a.env_end - a.env_begin;
+    if (g.v == 1 && a.noise_x == nullptr && n > 0 && n <= ((int64_t)1 << 31)) {
+        StepArgs b = a;
+        fill_offsets(b, a, precision, action_dtype);
+        b.n_stream = (uint32_t)n;
+        const int blocks = (int)((n + kNarrowThreads - 1) / kNarrowThreads);
+        return dispatch_step(precision, 1, action_dtype, NarrowLaunchOp{b, blocks, s});
+    }
     const int64_t warp_envs = 32 * wide;
     int64_t n_stream = 0;
     if (g.v == wide && wide > 1 && a.noise_x == nullptr && n <= ((int64_t)1 << 31) &&
@@ -228,21 +266,10 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
         n_stream = n / warp_envs * warp_envs;
     if (n_stream == 0) return dispatch_step(precision, g.v, action_dtype, StepLaunchOp{a, g, s});
 
-    const size_t es = precision == AQUA_F64 ? 8 : 4;
-    size_t ab = 4;
-    if (action_dtype == AQUA_ACT_I64 || action_dtype == AQUA_ACT_F32X2) ab = 8;
-    else if (action_dtype == AQUA_ACT_U8) ab = 1;
     StepArgs b = a;
     b.env_end = a.env_begin + n_stream;
-    for (int pl = 0; pl < AQUA_N_PLANES; ++pl)
-        b.pl0[pl] = static_cast<const char*>(a.planes) + ((size_t)pl * (size_t)a.ld) * es +
-                    (size_t)a.env_begin * (pl == AQUA_PLANE_TIME ? 4 : es);
-    b.act0 = static_cast<const char*>(a.actions) + (size_t)a.env_begin * ab;
-    b.rew0 = static_cast<char*>(a.reward) + (size_t)a.env_begin * es;
-    b.flg0 = a.flags + a.env_begin;
+    fill_offsets(b, a, precision, action_dtype);
     b.n_stream = (uint32_t)n_stream;
-    b.tile_lane_mask = 0u;
-    b.env_id0 = (uint32_t)(a.w.env_id_base + (uint64_t)a.env_begin);
     LaunchGeom gs = g;
     const int64_t tile = (int64_t)g.threads * wide;
     gs.blocks = (int)std::max<int64_t>(1, std::min<int64_t>(g.blocks, (n_stream + tile - 1) / tile));
