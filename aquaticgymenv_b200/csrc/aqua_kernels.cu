@@ -224,9 +224,18 @@ struct NarrowLaunchOp {
     int blocks;
     cudaStream_t s;
     template <typename R, int V, int ACT> cudaError_t run() const {
-        if (a.w.waves) step_narrow_kernel<R, ACT, true><<<blocks, kNarrowThreads, 0, s>>>(a);
-        else step_narrow_kernel<R, ACT, false><<<blocks, kNarrowThreads, 0, s>>>(a);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)blocks);
+        cfg.blockDim = dim3((unsigned)kNarrowThreads);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = AQUA_PDL;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        if (a.w.waves) return cudaLaunchKernelEx(&cfg, step_narrow_kernel<R, ACT, true>, a);
+        return cudaLaunchKernelEx(&cfg, step_narrow_kernel<R, ACT, false>, a);
     }
 };
 

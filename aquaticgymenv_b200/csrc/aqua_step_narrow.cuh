@@ -42,6 +42,11 @@ __device__ __forceinline__ void flush_stats_warp(ThreadStats& t, unsigned long l
     if (lane < AQUA_N_STATS && v != 0ull) atomicAdd(&g_slots[(warp % kStatSlots) * AQUA_N_STATS + lane], v);
 }
 
+// AQUA_PDL=1: consecutive narrow launches overlap their launch latency (see the kernel's first lines)
+#ifndef AQUA_PDL
+#define AQUA_PDL 1
+#endif
+
 // launch: ceil(n_stream / blockDim.x) CTAs of kNarrowThreads threads; pl0 / act0 / rew0 / flg0 /
 // n_stream / env_id0 of StepArgs filled as for the streaming kernel (any n_stream, no multiple)
 template <typename R, int ACT, bool WAVES>
@@ -50,6 +55,15 @@ __global__ void __launch_bounds__(kNarrowThreads, 8) step_narrow_kernel(const __
     const ObstacleTable<R>* const g_tab = reinterpret_cast<const ObstacleTable<R>*>(p.w.tab);
     const ObstacleView<R> tab{g_tab->box, p.w.use_grid ? g_tab->cell : nullptr};
 
+#if AQUA_PDL
+    // Programmatic dependent launch (launch_step sets the attribute): the CTAs of this launch may
+    // become resident while the previous kernel of the stream is still running, and wait here,
+    // before their first read, until it has completed and its writes are visible.  The trigger right
+    // behind lets the NEXT launch do the same with respect to this one.  Without the launch
+    // attribute both instructions do nothing.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
     const uint32_t n = p.n_stream;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;  // env index relative to env_begin
     const bool autoreset = p.w.autoreset != 0;
