@@ -95,6 +95,22 @@ def test_no_cpu_fallback_and_validation(native):
     assert lib.aqua_destroy(None) == native.OK
 
 
+def test_build_script_loads_without_the_package():
+    """__graft_entry__.build() must be able to build a fresh checkout: the package refuses to
+    import before libaquagym.so exists, so the build script is loaded by path and must not pull
+    the package in."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import importlib.util, os, sys\n"
+            "spec = importlib.util.spec_from_file_location('_b', os.path.join(%r, 'aquaticgymenv_b200', 'build.py'))\n"
+            "m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)\n"
+            "assert callable(m.build) and 'aquaticgymenv_b200' not in sys.modules\n" % root)
+    subprocess.run([sys.executable, "-c", code], check=True)
+    src = open(os.path.join(root, "__graft_entry__.py")).read()
+    assert "spec_from_file_location" in src and "from aquaticgymenv_b200.build import" not in src
+
+
 def test_product_package_never_touches_the_oracle():
     """The product path must not import or load anything under oracle/."""
     pkg = os.path.join(ROOT, "aquaticgymenv_b200")
