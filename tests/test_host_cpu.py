@@ -99,8 +99,6 @@ def test_build_script_loads_without_the_package():
     """__graft_entry__.build() must be able to build a fresh checkout: the package refuses to
     import before libaquagym.so exists, so the build script is loaded by path and must not pull
     the package in."""
-    import subprocess
-    import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     code = ("import importlib.util, os, sys\n"
             "spec = importlib.util.spec_from_file_location('_b', os.path.join(%r, 'aquaticgymenv_b200', 'build.py'))\n"
