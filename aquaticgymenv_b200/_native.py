@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AQUAGYM_LIB") or os.path.join(_HERE, "libaquagym.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aquagym.h")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 GEOM_AUTO, GEOM_WIDE, GEOM_NARROW = 0, 1, 2
@@ -23,9 +23,9 @@ TIME_BITS = 11
 EPISODE_MASK = 0x1FFFFF
 N_PLANES = 8
 TILE = 1024
-N_STATS = 8
+N_STATS = 9
 STAT_NAMES = ("episodes", "collided", "timeout", "success", "length_sum", "reward_sum_fx", "steps",
-              "bad_actions")
+              "bad_actions", "forced_resets")
 REWARD_FIXED_POINT = 1048576.0
 
 
@@ -42,12 +42,13 @@ class Config(C.Structure):
         ("random_goal", C.c_int32), ("precision", C.c_int32), ("autoreset", C.c_int32),
         ("n_obstacles", C.c_int32), ("geometry", C.c_int32),
         ("obstacles", C.POINTER(C.c_double)), ("seed", C.c_uint64), ("env_id_base", C.c_uint64),
-        ("state", C.c_void_p), ("ld", C.c_int64)]
+        ("state", C.c_void_p), ("ld", C.c_int64), ("keep_terminal", C.c_int32), ("_reserved", C.c_int32),
+        ("terminal", C.c_void_p)]
 
 
 class StateView(C.Structure):
     _fields_ = [("planes", C.c_void_p * N_PLANES), ("ld", C.c_int64), ("n_envs", C.c_int64),
-                ("precision", C.c_int32), ("_pad", C.c_int32)]
+                ("precision", C.c_int32), ("_pad", C.c_int32), ("terminal", C.c_void_p * 5)]
 
 
 _vp, _u64, _i64, _int = C.c_void_p, C.c_uint64, C.c_int64, C.c_int
@@ -62,6 +63,7 @@ SIGNATURES = {
     "aqua_step": (_int, [_vp, _vp, _vp, _int, _vp, _vp]),
     "aqua_step_ex": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "aqua_random_actions": (_int, [_vp, _vp, _u64, _vp, _int]),
+    "aqua_step_many": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _i64]),
     "aqua_rollout_random": (_int, [_vp, _vp, _i64, _u64]),
     "aqua_step_host": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "aqua_observe": (_int, [_vp, _vp, _vp, _int]),

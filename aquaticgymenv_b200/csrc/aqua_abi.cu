@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -73,12 +74,15 @@ struct aqua_env {
     unsigned long long* d_slots = nullptr;
     int64_t* d_stats_out = nullptr;
     uint32_t* d_tile_ctr = nullptr;  // kTileCounters counter sets, handed out round robin per launch
+    unsigned int* d_forced = nullptr;  // AQUA_STAT_FORCED_RESETS
+    uint4* d_stash = nullptr;          // step_many: pre-drawn next episodes, 32 bytes per env (lazy)
+    void* d_term = nullptr;            // keep_terminal: 5 planes [ld]
+    bool owns_term = false;
     unsigned launch_seq = 0;
     aqua::World world;
     // resident CTAs per SM, queried once at create: [action dtype][narrow (V = 1, 128 threads) /
     // wide (256 threads)]
     int occ_step[4][2] = {};
-    int occ_rollout[2] = {};
     // host-step pipeline (lazily created)
     cudaStream_t hs[kHostStreams] = {};
     cudaEvent_t ev_in = nullptr;
@@ -101,6 +105,8 @@ aqua::StepArgs base_args(aqua_env* env) {
     a.env_begin = 0;
     a.env_end = env->cfg.n_envs;
     a.stats = env->d_slots;
+    a.term = env->d_term;
+    a.stash = env->d_stash;
     return a;
 }
 
@@ -115,7 +121,8 @@ int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aq
     const int V = narrow ? 1 : wide;
     const int threads = narrow ? aqua::kNarrowThreads : aqua::kWideThreads;
     const int ti = narrow ? 0 : 1;
-    const int per_sm = rollout ? env->occ_rollout[ti] : env->occ_step[action_dtype][ti];
+    (void)rollout;
+    const int per_sm = env->occ_step[action_dtype][ti];
     const int64_t tiles = (n + (int64_t)threads * V - 1) / ((int64_t)threads * V);
     const int64_t resident = (int64_t)per_sm * env->sm_count;
     g->threads = threads;
@@ -196,6 +203,8 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
         return fail(AQUA_ERR_INVALID, "ld = %lld must be a multiple of %d and >= n_envs", (long long)ld, AQUA_TILE);
     if (cfg->state != nullptr && (reinterpret_cast<uintptr_t>(cfg->state) & 15u))
         return fail(AQUA_ERR_INVALID, "state buffer must be 16-byte aligned");
+    if (cfg->terminal != nullptr && (reinterpret_cast<uintptr_t>(cfg->terminal) & 15u))
+        return fail(AQUA_ERR_INVALID, "terminal buffer must be 16-byte aligned");
 
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -254,8 +263,17 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
         AQ_CREATE(cudaMalloc(&env->d_tab64, sizeof h_tab64));
         AQ_CREATE(cudaMemcpy(env->d_tab64, h_tab64, sizeof h_tab64, cudaMemcpyHostToDevice));
     }
-    AQ_CREATE(cudaMalloc(&env->d_slots, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
-    AQ_CREATE(cudaMemset(env->d_slots, 0, sizeof(unsigned long long) * aqua::kStatSlots * AQUA_N_STATS));
+    AQ_CREATE(cudaMalloc(&env->d_slots, sizeof(unsigned long long) * aqua::kStatSlots * aqua::kSlotStats));
+    AQ_CREATE(cudaMemset(env->d_slots, 0, sizeof(unsigned long long) * aqua::kStatSlots * aqua::kSlotStats));
+    AQ_CREATE(cudaMalloc(&env->d_forced, sizeof(unsigned int)));
+    AQ_CREATE(cudaMemset(env->d_forced, 0, sizeof(unsigned int)));
+    if (cfg->keep_terminal && cfg->terminal != nullptr) {
+        env->d_term = cfg->terminal;
+    } else if (cfg->keep_terminal) {
+        AQ_CREATE(cudaMalloc(&env->d_term, (size_t)5 * (size_t)ld * es));
+        env->owns_term = true;
+        AQ_CREATE(cudaMemset(env->d_term, 0, (size_t)5 * (size_t)ld * es));
+    }
     AQ_CREATE(cudaMalloc(&env->d_stats_out, sizeof(int64_t) * AQUA_N_STATS));
     AQ_CREATE(cudaMalloc(&env->d_tile_ctr, sizeof(uint32_t) * aqua::kTileCounterWords * kTileCounters));
     AQ_CREATE(cudaMemset(env->d_tile_ctr, 0, sizeof(uint32_t) * aqua::kTileCounterWords * kTileCounters));
@@ -282,6 +300,7 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.random_goal = cfg->random_goal != 0;
     w.autoreset = cfg->autoreset != 0;
     w.use_grid = use_grid != 0;
+    w.forced = env->d_forced;
 
     AQ_CREATE(aqua::configure_kernels(cfg->precision));
     for (int ti = 0; ti < 2; ++ti) {
@@ -296,8 +315,6 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
                 if (occ > 0) env->occ_step[act][ti] = occ;
             }
         }
-        AQ_CREATE(aqua::rollout_occupancy(cfg->precision, v, cfg->continuous, threads, use_grid, &env->occ_rollout[ti]));
-        env->occ_rollout[ti] = std::max(env->occ_rollout[ti], 1);
     }
     AQ_CREATE(aqua::launch_init_state(cfg->precision, env->state, ld, nullptr));
     AQ_CREATE(cudaStreamSynchronize(nullptr));
@@ -330,6 +347,9 @@ int aqua_destroy(aqua_env* env) {
     if (env->d_slots) keep(cudaFree(env->d_slots));
     if (env->d_stats_out) keep(cudaFree(env->d_stats_out));
     if (env->d_tile_ctr) keep(cudaFree(env->d_tile_ctr));
+    if (env->d_forced) keep(cudaFree(env->d_forced));
+    if (env->d_stash) keep(cudaFree(env->d_stash));
+    if (env->owns_term && env->d_term) keep(cudaFree(env->d_term));
     delete env;
     if (first != cudaSuccess) return fail(AQUA_ERR_CUDA, "aqua_destroy: %s", cudaGetErrorString(first));
     return AQUA_OK;
@@ -345,6 +365,8 @@ int aqua_state(aqua_env* env, aqua_state_view* out) {
     out->n_envs = env->cfg.n_envs;
     out->precision = env->cfg.precision;
     out->_pad = 0;
+    for (int k = 0; k < 5; ++k)
+        out->terminal[k] = env->d_term ? static_cast<char*>(env->d_term) + (size_t)k * (size_t)env->ld * es : nullptr;
     return AQUA_OK;
 }
 
@@ -395,17 +417,89 @@ int aqua_random_actions(aqua_env* env, void* stream, uint64_t step_index, void* 
     return AQUA_OK;
 }
 
+namespace {
+
+// the stash of step_many_kernel, allocated on first use (32 bytes per env; not capturable)
+int ensure_stash(aqua_env* env, cudaStream_t s) {
+    if (env->d_stash != nullptr) return AQUA_OK;
+    void* ptr = nullptr;
+    AQ_CUDA(cudaMalloc(&ptr, (size_t)env->ld * 32));
+    env->d_stash = static_cast<uint4*>(ptr);
+    AQ_CUDA(aqua::launch_stash_init(env->d_stash, env->ld, s));
+    return AQUA_OK;
+}
+
+// Geometry of a multi-step launch: every env belongs to one thread for the whole launch, so the
+// grid is not persistent.  Envs per thread and threads per CTA are picked so that the launch fills
+// the GPU in whole waves where it can: narrow threads and small CTAs for small slabs (one wave, all
+// SMs evenly loaded), wide threads for large ones (fewer instructions per env-step).
+// AQUA_MANY_V / AQUA_MANY_THREADS (environment) override the choice: tuning only.
+int pick_many_geom(const aqua_env* env, int64_t n, aqua::LaunchGeom* g) {
+    const int wide = aqua::envs_per_thread(env->cfg.precision);
+    int v = 1, threads = 64;
+    const int64_t lanes = (int64_t)env->sm_count * 1024;  // threads one wave of narrow CTAs can hold (about)
+    if (n > 4 * lanes) { v = wide; threads = 128; }
+    else if (n > lanes) { v = 2; threads = 128; }
+    if (env->cfg.geometry == AQUA_GEOM_WIDE) { v = wide; threads = 128; }
+    if (env->cfg.geometry == AQUA_GEOM_NARROW) { v = 1; threads = 64; }
+    if (const char* s = getenv("AQUA_MANY_V")) {
+        const int x = atoi(s);
+        if (x == 1 || x == 2 || (x == 4 && wide == 4)) v = x;
+    }
+    if (const char* s = getenv("AQUA_MANY_THREADS")) {
+        const int x = atoi(s);
+        if (x == 32 || x == 64 || x == 128 || x == 256) threads = x;
+    }
+    g->v = v;
+    g->threads = threads;
+    g->blocks = 0;  // launch_step_many derives it
+    return AQUA_OK;
+}
+
+}  // namespace
+
+int aqua_step_many(aqua_env* env, void* stream, int64_t steps, const void* actions, int action_dtype,
+                   void* reward, uint8_t* flags, int64_t row_stride) {
+    if (int rc = check_env(env)) return rc;
+    if (int rc = check_action_dtype(env, action_dtype)) return rc;
+    if (steps < 0) return fail(AQUA_ERR_INVALID, "steps must be >= 0");
+    if (actions == nullptr) return fail(AQUA_ERR_INVALID, "actions is NULL");
+    if (row_stride < env->cfg.n_envs || row_stride % 16 != 0)
+        return fail(AQUA_ERR_INVALID, "row_stride = %lld must be a multiple of 16 and >= n_envs = %lld",
+                    (long long)row_stride, (long long)env->cfg.n_envs);
+    if ((reinterpret_cast<uintptr_t>(actions) & 15u) || (reinterpret_cast<uintptr_t>(reward) & 15u) ||
+        (reinterpret_cast<uintptr_t>(flags) & 15u))
+        return fail(AQUA_ERR_INVALID, "actions, reward and flags must be 16-byte aligned");
+    if (steps == 0) return AQUA_OK;
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = ensure_stash(env, s)) return rc;
+    aqua::StepArgs a = base_args(env);
+    a.actions = actions;
+    a.reward = reward;
+    a.flags = flags;
+    a.row_stride = row_stride;
+    a.steps = steps;
+    aqua::LaunchGeom g;
+    if (int rc = pick_many_geom(env, env->cfg.n_envs, &g)) return rc;
+    AQ_CUDA(aqua::launch_step_many(env->cfg.precision, action_dtype, 1, a, g, s));
+    return AQUA_OK;
+}
+
 int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t first_step_index) {
     if (int rc = check_env(env)) return rc;
     if (steps < 0) return fail(AQUA_ERR_INVALID, "steps must be >= 0");
     if (steps == 0) return AQUA_OK;
     DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = ensure_stash(env, s)) return rc;
     aqua::StepArgs a = base_args(env);
     a.steps = steps;
     a.step0 = first_step_index;
+    a.row_stride = 0;
     aqua::LaunchGeom g;
-    if (int rc = pick_geom(env, env->cfg.n_envs, true, 0, &g)) return rc;
-    AQ_CUDA(aqua::launch_rollout(env->cfg.precision, env->cfg.continuous, a, g, static_cast<cudaStream_t>(stream)));
+    if (int rc = pick_many_geom(env, env->cfg.n_envs, &g)) return rc;
+    AQ_CUDA(aqua::launch_step_many(env->cfg.precision, env->cfg.continuous ? AQUA_ACT_F32X2 : AQUA_ACT_I32, 0, a, g, s));
     return AQUA_OK;
 }
 
@@ -430,14 +524,23 @@ int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_
 
     static const int kObsPlanes[5] = {AQUA_PLANE_X, AQUA_PLANE_Y, AQUA_PLANE_THETA, AQUA_PLANE_GOAL_X,
                                       AQUA_PLANE_GOAL_Y};  // aqua.py:213
+    // a failure inside the loop must not return while copies into the caller's buffers are still
+    // in flight: remember it, stop issuing, wait for every internal stream, then report
+    cudaError_t err = cudaSuccess;
+    const char* what = "";
+#define AQ_TRY(call)                                  \
+    if (err == cudaSuccess) {                         \
+        err = (call);                                 \
+        if (err != cudaSuccess) what = #call;         \
+    }
     int c = 0;
-    for (int64_t lo = 0; lo < n; lo += chunk, ++c) {
+    for (int64_t lo = 0; lo < n && err == cudaSuccess; lo += chunk, ++c) {
         const int64_t hi = std::min(n, lo + chunk);
         const int64_t len = hi - lo;
         cudaStream_t s = env->hs[c % kHostStreams];
-        AQ_CUDA(cudaMemcpyAsync(static_cast<char*>(env->d_actions) + (size_t)lo * ab,
-                                static_cast<const char*>(actions) + (size_t)lo * ab, (size_t)len * ab,
-                                cudaMemcpyHostToDevice, s));
+        AQ_TRY(cudaMemcpyAsync(static_cast<char*>(env->d_actions) + (size_t)lo * ab,
+                               static_cast<const char*>(actions) + (size_t)lo * ab, (size_t)len * ab,
+                               cudaMemcpyHostToDevice, s));
         aqua::StepArgs a = base_args(env);
         a.env_begin = lo;
         a.env_end = hi;
@@ -445,22 +548,30 @@ int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_
         a.reward = env->d_reward;
         a.flags = env->d_flags;
         aqua::LaunchGeom g;
-        if (int rc = pick_geom(env, len, false, action_dtype, &g)) return rc;
-        AQ_CUDA(aqua::launch_step(env->cfg.precision, action_dtype, a, g, s));
+        pick_geom(env, len, false, action_dtype, &g);
+        AQ_TRY(aqua::launch_step(env->cfg.precision, action_dtype, a, g, s));
         if (flags != nullptr)
-            AQ_CUDA(cudaMemcpyAsync(flags + lo, env->d_flags + lo, (size_t)len, cudaMemcpyDeviceToHost, s));
+            AQ_TRY(cudaMemcpyAsync(flags + lo, env->d_flags + lo, (size_t)len, cudaMemcpyDeviceToHost, s));
         if (reward != nullptr)
-            AQ_CUDA(cudaMemcpyAsync(static_cast<char*>(reward) + (size_t)lo * es,
-                                    static_cast<char*>(env->d_reward) + (size_t)lo * es, (size_t)len * es,
-                                    cudaMemcpyDeviceToHost, s));
+            AQ_TRY(cudaMemcpyAsync(static_cast<char*>(reward) + (size_t)lo * es,
+                                   static_cast<char*>(env->d_reward) + (size_t)lo * es, (size_t)len * es,
+                                   cudaMemcpyDeviceToHost, s));
         if (obs != nullptr)
             for (int k = 0; k < 5; ++k)
-                AQ_CUDA(cudaMemcpyAsync(static_cast<char*>(obs) + ((size_t)k * (size_t)n + (size_t)lo) * es,
-                                        static_cast<char*>(env->state) +
-                                            ((size_t)kObsPlanes[k] * (size_t)env->ld + (size_t)lo) * es,
-                                        (size_t)len * es, cudaMemcpyDeviceToHost, s));
+                AQ_TRY(cudaMemcpyAsync(static_cast<char*>(obs) + ((size_t)k * (size_t)n + (size_t)lo) * es,
+                                       static_cast<char*>(env->state) +
+                                           ((size_t)kObsPlanes[k] * (size_t)env->ld + (size_t)lo) * es,
+                                       (size_t)len * es, cudaMemcpyDeviceToHost, s));
     }
-    for (int i = 0; i < kHostStreams; ++i) AQ_CUDA(cudaStreamSynchronize(env->hs[i]));
+    for (int i = 0; i < kHostStreams; ++i) {
+        const cudaError_t e = cudaStreamSynchronize(env->hs[i]);
+        if (err == cudaSuccess && e != cudaSuccess) {
+            err = e;
+            what = "cudaStreamSynchronize(host pipeline)";
+        }
+    }
+#undef AQ_TRY
+    if (err != cudaSuccess) return fail(AQUA_ERR_CUDA, "aqua_step_host: %s failed: %s", what, cudaGetErrorString(err));
     return AQUA_OK;
 }
 
@@ -495,7 +606,7 @@ int aqua_stats_reduce(aqua_env* env, void* stream, int64_t* out_dev, int clear) 
     if (int rc = check_env(env)) return rc;
     if (out_dev == nullptr) return fail(AQUA_ERR_INVALID, "out_dev is NULL");
     DeviceGuard guard(env->device);
-    AQ_CUDA(aqua::launch_stats_reduce(env->d_slots, out_dev, clear, static_cast<cudaStream_t>(stream)));
+    AQ_CUDA(aqua::launch_stats_reduce(env->d_slots, env->d_forced, out_dev, clear, static_cast<cudaStream_t>(stream)));
     return AQUA_OK;
 }
 
@@ -504,7 +615,7 @@ int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear) {
     if (out_host == nullptr) return fail(AQUA_ERR_INVALID, "out_host is NULL");
     DeviceGuard guard(env->device);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    AQ_CUDA(aqua::launch_stats_reduce(env->d_slots, env->d_stats_out, clear, s));
+    AQ_CUDA(aqua::launch_stats_reduce(env->d_slots, env->d_forced, env->d_stats_out, clear, s));
     AQ_CUDA(cudaMemcpyAsync(out_host, env->d_stats_out, sizeof(int64_t) * AQUA_N_STATS, cudaMemcpyDeviceToHost, s));
     AQ_CUDA(cudaStreamSynchronize(s));
     return AQUA_OK;

@@ -272,9 +272,11 @@ struct ResetResult {
 
 // env.reset() for one env: aqua.py:100-126.  `ep` is the NEW episode index.  Try n of the
 // reference's `observation_space.sample()` sequence is Philox(env, ep, n, RESET).
+// A rejection loop that reaches try kResetMaxTries - 1 accepts it untested (the reference would loop
+// on: aqua.py:102-115 have no bound); every such accept is counted in *forced (AQUA_STAT_FORCED_RESETS).
 inline __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uint32_t env_id, uint32_t ep,
                                               const double* __restrict__ tab64, int k_obst,
-                                              WorldFlags wf) {
+                                              WorldFlags wf, unsigned int* forced) {
     ResetResult o;
     uint32_t n = 0;
     if (wf.random_goal) {  // aqua.py:102-105
@@ -282,7 +284,7 @@ inline __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uin
             const uint4 r = philox_env(keys, env_id, ep, n++, kStreamReset);
             o.gx = (double)draw_pos(r.z);
             o.gy = (double)draw_pos(r.w);
-            if (n >= kResetMaxTries) break;
+            if (n >= kResetMaxTries) { atomicAdd(forced, 1u); break; }
             if (!(outside_border(o.gx, o.gy) || hits_obstacle_g(tab64, k_obst, o.gx, o.gy))) break;
         }
     } else {  // aqua.py:107
@@ -295,7 +297,7 @@ inline __device__ __noinline__ ResetResult reset_env(const PhiloxKeys& keys, uin
             o.x = (double)draw_pos(r.x);
             o.y = (double)draw_pos(r.y);
             o.th = (double)draw_angle(r.z);
-            if (n >= kResetMaxTries) break;
+            if (n >= kResetMaxTries) { atomicAdd(forced, 1u); break; }
             const double dgx = o.gx - o.x, dgy = o.gy - o.y;
             const bool reached = sqrt(fma(dgx, dgx, dgy * dgy)) - 5.0 <= 0.0;  // aqua.py:421-422
             if (!(reached || outside_border(o.x, o.y) || hits_obstacle_g(tab64, k_obst, o.x, o.y))) break;
@@ -373,7 +375,7 @@ template <typename R>
 __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, const ObstacleView<R>& tab,
                                                       const double* __restrict__ tab64, int k_circ, int k_obst,
                                                       float band, WorldFlags wf, bool valid, uint32_t env_id,
-                                                      uint32_t ep) {
+                                                      uint32_t ep, unsigned int* forced) {
     const unsigned full = 0xffffffffu;
     const unsigned lane = threadIdx.x & 31u;
     const unsigned sub = lane & ~(unsigned)(kCoopLanes - 1);  // first lane of this group
@@ -398,6 +400,7 @@ __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, co
         const unsigned lg = mg ? (unsigned)(__ffs(mg) - 1) : 0u;
         const float sgx = __shfl_sync(full, cgx, sub + lg), sgy = __shfl_sync(full, cgy, sub + lg);
         if (!goal_done && mg) {
+            if (force && l == lg) atomicAdd(forced, 1u);  // the forced try is the accepted one: no try passed
             o.gx = sgx;
             o.gy = sgy;
             goal_done = true;
@@ -414,12 +417,61 @@ __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, co
         const float sbx = __shfl_sync(full, cbx, sub + lb), sby = __shfl_sync(full, cby, sub + lb);
         const float sbt = __shfl_sync(full, cbt, sub + lb);
         if (mb) {
+            if (force && l == lb && !boat_done) atomicAdd(forced, 1u);
             o.x = sbx;
             o.y = sby;
             o.th = sbt;
             boat_done = true;
         }
         n0 += kCoopLanes;
+    }
+    if (wf.waves) {  // aqua.py:124
+        draw_wave_init(keys, env_id, ep, o.wx, o.wy);
+    } else {
+        o.wx = 0.f;
+        o.wy = 0.f;
+    }
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------
+// One lane resets one env: the reference's two rejection loops in sequence (aqua.py:100-126), try n
+// = Philox(env, ep, n, RESET), exactly the result of reset_env() and coop_reset().  No warp
+// collectives: the lanes of a warp each serve another env and leave their loops when their own
+// tries pass, so a pass over 32 queued envs costs as many rounds as its unluckiest lane (about
+// 5 on the default map) where 32 envs take four coop_reset() passes of 8.  Used wherever finished
+// envs can be collected 32 at a time: the streaming / general step kernels and the stash refill of
+// the multi-step kernel.  Accept/reject decisions are float64-exact (guard band, see above).
+// ------------------------------------------------------------------------------------------
+template <typename R>
+__device__ __forceinline__ CoopResetResult reset_env_lane(const PhiloxKeys& keys, const ObstacleView<R>& tab,
+                                                          const double* __restrict__ tab64, int k_circ, int k_obst,
+                                                          float band, WorldFlags wf, uint32_t env_id, uint32_t ep,
+                                                          unsigned int* forced) {
+    CoopResetResult o;
+    o.gx = 25.f; o.gy = 80.f;            // aqua.py:107
+    o.x = 85.f; o.y = 45.f; o.th = 0.f;  // aqua.py:117
+    uint32_t n = 0;
+    if (wf.random_goal) {  // aqua.py:102-105
+        for (;;) {
+            const uint4 r = philox_env(keys, env_id, ep, n++, kStreamReset);
+            o.gx = draw_pos(r.z);
+            o.gy = draw_pos(r.w);
+            if (n >= kResetMaxTries) { atomicAdd(forced, 1u); break; }
+            if (!(outside_border_f(o.gx, o.gy) || reset_blocked<R>(tab, tab64, k_circ, k_obst, band, o.gx, o.gy))) break;
+        }
+    }
+    if (wf.random_boat) {  // aqua.py:110-115
+        for (;;) {
+            const uint4 r = philox_env(keys, env_id, ep, n++, kStreamReset);
+            o.x = draw_pos(r.x);
+            o.y = draw_pos(r.y);
+            o.th = draw_angle(r.z);
+            if (n >= kResetMaxTries) { atomicAdd(forced, 1u); break; }
+            if (!(reset_reached<R>(o.gx, o.gy, o.x, o.y) || outside_border_f(o.x, o.y) ||
+                  reset_blocked<R>(tab, tab64, k_circ, k_obst, band, o.x, o.y)))
+                break;
+        }
     }
     if (wf.waves) {  // aqua.py:124
         draw_wave_init(keys, env_id, ep, o.wx, o.wy);
@@ -440,11 +492,13 @@ template <typename R> struct EnvState {
 
 // heading wrap to [-pi, pi): aqua.py:128-133
 __device__ __forceinline__ float wrap_angle(float a) {
-    // |a| <= pi + 0.12.  No float lies strictly between pi and 3.14159274f, so the float
-    // comparisons decide exactly like the real-number ones; 2*pi is subtracted as hi + lo.
+    // |a| <= pi + 0.12.  kPiUp = 3.14159274f is the float next above pi and 3.1415925f the one next
+    // below, so "a >= pi" reads a >= kPiUp and "a < -pi" reads a <= -kPiUp (-kPiUp itself lies below
+    // -pi and wraps to just under +pi, as the reference's [-pi, pi) range wants); 2*pi is
+    // subtracted as hi + lo.
     constexpr float kPiUp = 3.14159274f, kTwoPiHi = 6.28318548f, kTwoPiLo = -1.74845553e-7f;
     if (a >= kPiUp) a = (a - kTwoPiHi) - kTwoPiLo;
-    else if (a < -kPiUp) a = (a + kTwoPiHi) + kTwoPiLo;
+    else if (a <= -kPiUp) a = (a + kTwoPiHi) + kTwoPiLo;
     return a;
 }
 __device__ __forceinline__ double wrap_angle(double a) {

@@ -6,6 +6,7 @@
 #include <cstring>
 
 #include "aqua_device.cuh"
+#include "aqua_packed.cuh"
 
 namespace aqua {
 
@@ -27,18 +28,6 @@ template <typename T, int V> __device__ __forceinline__ void st_pack(T* p, const
 #ifndef AQUA_MEMBENCH
 #define AQUA_MEMBENCH 0
 #endif
-// AQUA_SCHED_WARP=1: the streaming kernel runs one extra warp per CTA that does all tile claims and
-// feeds the worker warps through shared-memory rings (see step_stream_kernel), so that no worker
-// waits for the reply of a global atomic.  Correct (all GPU tests pass with it) and NOT faster:
-// 8.335e10 vs 8.304e10 env-steps/s on one box, 3 % slower on the 64-obstacle map
-// (profiles/r01L_scheduler_warp_ab.txt) -- the time a worker spends waiting for its claim is time
-// the other warps of its scheduler use.  Off by default.
-#ifndef AQUA_SCHED_WARP
-#define AQUA_SCHED_WARP 0
-#endif
-constexpr int kSchedThreads = AQUA_SCHED_WARP ? 32 : 0;  // added to the CTA of the streaming kernel
-constexpr int kRing = 4;                                 // tiles queued per worker warp
-constexpr uint32_t kRingEmpty = 0xffffffffu, kRingDone = 0xfffffffeu;
 // Stores of the streaming kernel.  AQUA_STORE_CS=1 makes them evict-first (st.global.cs).  Measured
 // on one B200 box (tools/tune.py, 2^24 envs): plain 8.20e10 env-steps/s, evict-first 7.97e10 -- the
 // deferred reset writes 4-byte values into lines the owner stored a few tiles earlier, and those
@@ -207,6 +196,11 @@ __device__ __forceinline__ void decode_drives(const ActVals<ACT, V>& a, Drive<R>
     }
 }
 
+// the three discrete drives (aqua.py:33-42) as a shared-memory table: one 16-byte read per env
+template <typename R> struct alignas(16) DriveSlot {
+    R phi, h, chord, pad;
+};
+
 // ------------------------------------------------------------------------------------------
 // asynchronous global -> shared copies (LDGSTS): each thread stages the 8 plane slices of ITS
 // next tile in its own shared-memory slots while it computes the current tile, so no barrier is
@@ -295,9 +289,9 @@ __device__ __forceinline__ void flush_stats(ThreadStats& t, unsigned long long* 
         if (r) atomicAdd(&s_stats[AQUA_STAT_REWARD_SUM], (unsigned long long)r);
     }
     __syncthreads();
-    if (threadIdx.x < AQUA_N_STATS) {
+    if (threadIdx.x < kSlotStats) {
         const unsigned long long v = s_stats[threadIdx.x];
-        if (v) atomicAdd(&g_slots[(blockIdx.x % kStatSlots) * AQUA_N_STATS + threadIdx.x], v);
+        if (v) atomicAdd(&g_slots[(blockIdx.x % kStatSlots) * kSlotStats + threadIdx.x], v);
     }
 }
 
@@ -333,9 +327,15 @@ __device__ __forceinline__ ObstacleView<R> stage_table(ObstacleBox<R>* s_box, un
 // straight to the state planes (aqua.py:100-126).  Both functions are warp-collective.
 // ------------------------------------------------------------------------------------------
 constexpr int kResetGroups = 32 / kCoopLanes;
+// AQUA_LANE_PASS: queued envs a lane-per-env pass waits for (reset_queue_drain_lanes); 32 = only
+// full warps.  The queue holds what is left below that plus one tile's worth of new entries.
+#ifndef AQUA_LANE_PASS
+#define AQUA_LANE_PASS 32
+#endif
+constexpr int kLanePass = AQUA_LANE_PASS;
 template <int V> struct WarpResetQueue {
-    uint32_t rel[32 * V + kResetGroups];  // env index relative to env_begin
-    uint32_t tw[32 * V + kResetGroups];   // its terminal time word (episode, length)
+    uint32_t rel[32 * V + 32];  // env index relative to env_begin
+    uint32_t tw[32 * V + 32];   // its terminal time word (episode, length)
 };
 
 // fw: flags of the lane's V envs, one byte each (0 for padding / inactive lanes); rel_base: index
@@ -380,7 +380,7 @@ __device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const Obstac
         const uint32_t ep = ((tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
         const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
         const CoopResetResult rr = coop_reset<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
-                                                 p.w.reset_band, wf, valid, env_id, ep);
+                                                 p.w.reset_band, wf, valid, env_id, ep, p.w.forced);
         if (valid && leader) {
             length_sum += tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
             plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
@@ -396,6 +396,56 @@ __device__ __forceinline__ int reset_queue_drain(const StepArgs& p, const Obstac
     }
     __syncwarp();
     return n;
+}
+
+// The same with one LANE per queued env (reset_env_lane): passes of up to 32 envs from the tail,
+// while at least `min_batch` are queued (kLanePass: full passes; 1: flush).  What the wide kernels
+// use: a warp collects 32 finished envs within a few tiles.
+template <typename R, int V>
+__device__ __forceinline__ int reset_queue_drain_lanes(const StepArgs& p, const ObstacleView<R>& tab,
+                                                       const WarpResetQueue<V>& wq, int n, int min_batch,
+                                                       uint32_t& length_sum) {
+    const int lane = (int)(threadIdx.x & 31u);
+    const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
+    uint32_t* const ptw = plane_tw<R>(p.planes, p.ld);
+    __syncwarp();  // queue entries are visible to the whole warp
+    while (n >= min_batch && n > 0) {
+        const int take = min(n, 32);
+        const int first = n - take;
+        if (lane < take) {
+            const int64_t i = p.env_begin + (int64_t)wq.rel[first + lane];
+            const uint32_t tw = wq.tw[first + lane];
+            const uint32_t ep = ((tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+            const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
+            const CoopResetResult rr = reset_env_lane<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
+                                                         p.w.reset_band, wf, env_id, ep, p.w.forced);
+            length_sum += tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
+            plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_Y)[i] = (R)rr.y;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_THETA)[i] = (R)rr.th;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_X)[i] = (R)rr.gx;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_GOAL_Y)[i] = (R)rr.gy;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_X)[i] = (R)rr.wx;
+            plane<R>(p.planes, p.ld, AQUA_PLANE_WAVE_Y)[i] = (R)rr.wy;
+            ptw[i] = ep << AQUA_TIME_BITS;
+        }
+        n = first;
+    }
+    __syncwarp();
+    return n;
+}
+
+// Terminal observation of an env that finished (aqua.py:213 returns it together with done = True;
+// under auto-reset the state planes move on to the next episode): x, y, angle, goal_x, goal_y into
+// the 5 `term` planes, by the env's owner.  `i` = absolute env index.
+template <typename R>
+__device__ __forceinline__ void store_terminal(const StepArgs& p, int64_t i, const EnvState<R>& e) {
+    R* const t = reinterpret_cast<R*>(p.term) + i;
+    t[0] = e.x;
+    t[p.ld] = e.y;
+    t[2 * p.ld] = e.th;
+    t[3 * p.ld] = e.gx;
+    t[4 * p.ld] = e.gy;
 }
 
 // the V flag bytes as one word (byte j = env j)

@@ -8,10 +8,11 @@
 // bandwidth (65 B per discrete env-step).
 //
 // The kernels live in headers by family -- aqua_step_stream.cuh (K1s, large slabs),
-// aqua_step_narrow.cuh (K1n, small slabs), aqua_step_general.cuh (K1 general step, K1r rollout),
-// helpers in aqua_kernel_util.cuh, device
-// arithmetic in aqua_device.cuh; this file holds the small kernels (K2 reset, K3 statistics, K4
-// state access) and every launcher.  Host-side tables: aqua_tables.cu.
+// aqua_step_narrow.cuh (K1n, small slabs), aqua_step_general.cuh (K1 general step),
+// aqua_step_many.cuh (K1m, K steps per launch; launched from aqua_many.cu), helpers in
+// aqua_kernel_util.cuh, device arithmetic in aqua_device.cuh and aqua_packed.cuh; this file holds
+// the small kernels (K2 reset, K3 statistics, K4 state access) and the single-step launchers.
+// Host-side tables: aqua_tables.cu.
 #include <algorithm>
 #include <cstring>
 
@@ -34,7 +35,7 @@ __global__ void __launch_bounds__(kMaxThreads) reset_kernel(const __grid_constan
     const uint32_t ep = ((ptw[i] >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
     const ResetResult rr = reset_env(p.w.keys, env_id, ep, p.w.tab64, p.w.k_obst,
-                                     WorldFlags{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0});
+                                     WorldFlags{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0}, p.w.forced);
     // the draws are float32 values: exact in either precision
     plane<R>(p.planes, p.ld, AQUA_PLANE_X)[i] = (R)rr.x;
     plane<R>(p.planes, p.ld, AQUA_PLANE_Y)[i] = (R)rr.y;
@@ -123,29 +124,34 @@ __global__ void observe_kernel(const void* planes, int64_t ld, int64_t n, float*
     for (int k = 0; k < 5; ++k) out[i * 5 + k] = v[k];
 }
 
-// K3: fold the per-CTA slots into int64[AQUA_N_STATS]
-__global__ void stats_reduce_kernel(unsigned long long* slots, int64_t* out, int clear) {
-    __shared__ unsigned long long s[AQUA_N_STATS];
-    if (threadIdx.x < AQUA_N_STATS) s[threadIdx.x] = 0ull;
+// K3: fold the per-CTA slots (kSlotStats counters each) and the forced-reset counter into
+// int64[AQUA_N_STATS]
+__global__ void stats_reduce_kernel(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear) {
+    __shared__ unsigned long long s[kSlotStats];
+    if (threadIdx.x < kSlotStats) s[threadIdx.x] = 0ull;
     __syncthreads();
-    unsigned long long acc[AQUA_N_STATS];
+    unsigned long long acc[kSlotStats];
 #pragma unroll
-    for (int k = 0; k < AQUA_N_STATS; ++k) acc[k] = 0ull;
+    for (int k = 0; k < kSlotStats; ++k) acc[k] = 0ull;
     for (int slot = threadIdx.x; slot < kStatSlots; slot += blockDim.x) {
 #pragma unroll
-        for (int k = 0; k < AQUA_N_STATS; ++k) {
-            acc[k] += slots[slot * AQUA_N_STATS + k];
-            if (clear) slots[slot * AQUA_N_STATS + k] = 0ull;
+        for (int k = 0; k < kSlotStats; ++k) {
+            acc[k] += slots[slot * kSlotStats + k];
+            if (clear) slots[slot * kSlotStats + k] = 0ull;
         }
     }
 #pragma unroll
-    for (int k = 0; k < AQUA_N_STATS; ++k) {
+    for (int k = 0; k < kSlotStats; ++k) {
         unsigned long long v = acc[k];
         for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         if ((threadIdx.x & 31) == 0 && v) atomicAdd(&s[k], v);
     }
     __syncthreads();
-    if (threadIdx.x < AQUA_N_STATS) out[threadIdx.x] = (int64_t)s[threadIdx.x];
+    if (threadIdx.x < kSlotStats) out[threadIdx.x] = (int64_t)s[threadIdx.x];
+    if (threadIdx.x == 0) {
+        out[AQUA_STAT_FORCED_RESETS] = (int64_t)*forced;
+        if (clear) *forced = 0u;
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -167,15 +173,6 @@ template <typename Op> static cudaError_t dispatch_step(int precision, int v, in
         return v == 1 ? dispatch_act<double, 1>(act, op) : dispatch_act<double, Prec<double>::V>(act, op);
     return v == 1 ? dispatch_act<float, 1>(act, op) : dispatch_act<float, Prec<float>::V>(act, op);
 }
-template <typename Op> static cudaError_t dispatch_rollout(int precision, int v, int continuous, const Op& op) {
-    if (precision == AQUA_F64) {
-        if (v == 1) return continuous ? op.template run<double, 1, true>() : op.template run<double, 1, false>();
-        return continuous ? op.template run<double, Prec<double>::V, true>() : op.template run<double, Prec<double>::V, false>();
-    }
-    if (v == 1) return continuous ? op.template run<float, 1, true>() : op.template run<float, 1, false>();
-    return continuous ? op.template run<float, Prec<float>::V, true>() : op.template run<float, Prec<float>::V, false>();
-}
-
 struct StepLaunchOp {
     const StepArgs& a;
     LaunchGeom g;
@@ -196,9 +193,8 @@ struct StreamLaunchOp {
     template <typename R, int V, int ACT> cudaError_t run() const {
         if constexpr (stream_supported<ACT, V>()) {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(a.w.use_grid);
-            const int threads = g.threads + kSchedThreads;
-            if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, threads, smem, s>>>(a);
-            else step_stream_kernel<R, V, ACT, false><<<g.blocks, threads, smem, s>>>(a);
+            if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
+            else step_stream_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
             return cudaGetLastError();
         } else {
             return cudaErrorNotSupported;
@@ -270,8 +266,10 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
     }
     const int64_t warp_envs = 32 * wide;
     int64_t n_stream = 0;
+    // (the bulk copies of the streaming kernel want every plane and the actions 16-byte aligned at
+    // env_begin: 16 envs cover the narrowest element, a uint8 action)
     if (g.v == wide && wide > 1 && a.noise_x == nullptr && n <= ((int64_t)1 << 31) &&
-        a.env_begin % wide == 0 && has_stream_kernel(precision, action_dtype))
+        a.env_begin % 16 == 0 && has_stream_kernel(precision, action_dtype))
         n_stream = n / warp_envs * warp_envs;
     if (n_stream == 0) return dispatch_step(precision, g.v, action_dtype, StepLaunchOp{a, g, s});
 
@@ -350,9 +348,9 @@ struct StreamOccupancyOp {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(use_grid);
             if (waves)
                 return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>,
-                                                                     threads + kSchedThreads, smem);
+                                                                     threads, smem);
             return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>,
-                                                                 threads + kSchedThreads, smem);
+                                                                 threads, smem);
         } else {
             *out = 0;
             return cudaSuccess;
@@ -362,29 +360,6 @@ struct StreamOccupancyOp {
 cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int use_grid, int* blocks_per_sm) {
     return dispatch_step(precision, envs_per_thread(precision), action_dtype,
                          StreamOccupancyOp{threads, waves, use_grid, blocks_per_sm});
-}
-
-struct RolloutLaunchOp {
-    const StepArgs& a;
-    LaunchGeom g;
-    cudaStream_t s;
-    template <typename R, int V, bool CONT> cudaError_t run() const {
-        rollout_kernel<R, V, CONT><<<g.blocks, g.threads, cell_bytes(a.w.use_grid), s>>>(a);
-        return cudaGetLastError();
-    }
-};
-cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s) {
-    return dispatch_rollout(precision, g.v, continuous, RolloutLaunchOp{a, g, s});
-}
-struct RolloutOccupancyOp {
-    int threads, use_grid;
-    int* out;
-    template <typename R, int V, bool CONT> cudaError_t run() const {
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, rollout_kernel<R, V, CONT>, threads, cell_bytes(use_grid));
-    }
-};
-cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int use_grid, int* blocks_per_sm) {
-    return dispatch_rollout(precision, v, continuous, RolloutOccupancyOp{threads, use_grid, blocks_per_sm});
 }
 
 static inline int blocks_for(int64_t n, int threads) { return (int)((n + threads - 1) / threads); }
@@ -442,8 +417,8 @@ cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_
     return cudaGetLastError();
 }
 
-cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s) {
-    stats_reduce_kernel<<<1, 256, 0, s>>>(slots, out, clear);
+cudaError_t launch_stats_reduce(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear, cudaStream_t s) {
+    stats_reduce_kernel<<<1, 256, 0, s>>>(slots, forced, out, clear);
     return cudaGetLastError();
 }
 

@@ -30,6 +30,8 @@ constexpr int kTilePools = 8;
 constexpr int kTilePoolStride = 32;                                   // uint32 words
 constexpr int kTileCounterWords = (kTilePools + 1) * kTilePoolStride;
 constexpr int kStatSlots = 1024;   // per-CTA statistics slots (CTA b adds into slot b % kStatSlots)
+constexpr int kSlotStats = 8;      // counters per slot: AQUA_STAT_EPISODES .. AQUA_STAT_BAD_ACTIONS; the ninth
+                                   // (AQUA_STAT_FORCED_RESETS) is one global counter, World::forced
 
 // Round keys of the draw streams, computed once on the host so that in the kernels they are
 // constant-bank operands of the rounds' XORs:
@@ -56,6 +58,7 @@ struct World {
     float reset_band;       // guard band of the float32 reset test, see reset_blocked()
     uint8_t waves, random_boat, random_goal, autoreset;
     uint8_t use_grid;       // dense map: obstacles are culled through the cell grid of the table
+    unsigned int* forced;   // device counter of forced reset accepts (AQUA_STAT_FORCED_RESETS)
 };
 
 struct StepArgs {
@@ -69,7 +72,7 @@ struct StepArgs {
     uint8_t* flags;
     const float* noise_x;   // injected wave increments (or NULL): indexed by absolute env index
     const float* noise_y;
-    unsigned long long* stats;  // [kStatSlots][AQUA_N_STATS]
+    unsigned long long* stats;  // [kStatSlots][kSlotStats]
     int64_t steps;          // rollout kernel: steps per launch
     uint64_t step0;         // rollout kernel: ACTION-stream index of the first step
     // streaming step kernel (whole warps only): everything below is filled by launch_step() so
@@ -82,6 +85,14 @@ struct StepArgs {
     uint32_t n_stream;               // envs of the launch, a multiple of 32 * (envs per thread)
     uint32_t env_id0;                // global id of env_begin
     uint32_t tile_lane_mask;         // 0 (see the tile claim in step_stream_kernel)
+    // terminal observations (aqua.py:213 returns the terminal obs with done = True; with auto-reset
+    // the planes already hold the next episode): 5 planes [ld] of the state's element type, written
+    // by the env's owner thread when an env finishes; NULL = not kept
+    void* term;
+    // multi-step kernel (step_many_kernel): rows of the action tape / reward / flags outputs are
+    // row_stride envs apart; stash = one 32-byte record per env with the pre-drawn next episode
+    int64_t row_stride;
+    uint4* stash;
 };
 
 struct LaunchGeom {
@@ -92,7 +103,11 @@ struct LaunchGeom {
 
 // every launcher returns the cudaError_t of the launch (cudaGetLastError)
 cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, LaunchGeom g, cudaStream_t s);
-cudaError_t launch_rollout(int precision, int continuous, const StepArgs& a, LaunchGeom g, cudaStream_t s);
+// K env-steps per launch (aqua_many.cu).  tape != 0: actions[K][row_stride] in, reward / flags
+// [K][row_stride] out (either may be NULL); tape == 0: the synthetic random policy (ACTION stream)
+cudaError_t launch_step_many(int precision, int action_dtype, int tape, const StepArgs& a, LaunchGeom g, cudaStream_t s);
+cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int use_grid, int* blocks_per_sm);
+cudaError_t launch_stash_init(uint4* stash, int64_t ld, cudaStream_t s);
 cudaError_t launch_reset(int precision, const StepArgs& a, const uint8_t* mask, cudaStream_t s);
 cudaError_t launch_init_state(int precision, void* planes, int64_t ld, cudaStream_t s);
 cudaError_t launch_random_actions(const World& w, int64_t n, uint64_t step_index, void* actions,
@@ -103,7 +118,7 @@ cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n,
                              cudaStream_t s);
 cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_t n, float* out, int normalized,
                            cudaStream_t s);
-cudaError_t launch_stats_reduce(unsigned long long* slots, int64_t* out, int clear, cudaStream_t s);
+cudaError_t launch_stats_reduce(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear, cudaStream_t s);
 // per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
 cudaError_t configure_kernels(int precision);
 // occupancy of the step kernel for (precision, action dtype) at `threads` per CTA; `use_grid`:
@@ -111,7 +126,6 @@ cudaError_t configure_kernels(int precision);
 cudaError_t step_occupancy(int precision, int v, int action_dtype, int threads, int use_grid, int* blocks_per_sm);
 // same for the streaming kernel; *blocks_per_sm = 0 when (precision, action dtype) has none
 cudaError_t stream_occupancy(int precision, int action_dtype, int waves, int threads, int use_grid, int* blocks_per_sm);
-cudaError_t rollout_occupancy(int precision, int v, int continuous, int threads, int use_grid, int* blocks_per_sm);
 
 int envs_per_thread(int precision);
 

@@ -1,7 +1,6 @@
-// aqua_step_general.cuh -- K1 (step_kernel) and K1r (rollout_kernel): the general form of the
-// env step.  step_kernel serves the tail of a range, narrow threads (V = 1) and injected wave
-// noise; large slabs run step_stream_kernel (aqua_step_stream.cuh), which inlines the same
-// arithmetic and agrees with it bit for bit.
+// aqua_step_general.cuh -- K1 (step_kernel): the general form of the env step.  It serves the tail
+// of a range, narrow threads (V = 1) with injected wave noise; large slabs run step_stream_kernel
+// (aqua_step_stream.cuh), which inlines the same arithmetic and agrees with it bit for bit.
 #pragma once
 
 #include "aqua_kernel_util.cuh"
@@ -15,10 +14,10 @@ namespace aqua {
 template <typename R, int V, int ACT, bool INJECT>
 __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
-    __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
-    if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
     const int64_t ld = p.ld;
@@ -145,39 +144,30 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
             decode_drives<R, ACT, V>(act_cur, dr, st.bad);
 
             EnvState<R> e[V];
-            MoveTmp<R> m[V];
-            R pxn[V], pyn[V], clr[V];
+            float nx[V], ny[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
                 e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
                 e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
                 e[j].tw = vtw.v[j];
-                float nx = 0.f, ny = 0.f;
+                nx[j] = ny[j] = 0.f;
                 if constexpr (INJECT) {
                     if (j < nvalid) {
-                        nx = __ldg(p.noise_x + base + j);
-                        ny = __ldg(p.noise_y + base + j);
+                        nx[j] = __ldg(p.noise_x + base + j);
+                        ny[j] = __ldg(p.noise_y + base + j);
                     }
                 } else {
                     const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                    if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx, ny);
+                    if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx[j], ny[j]);
                 }
-                move_env<R>(e[j], dr[j], (R)nx, (R)ny, waves, m[j]);
-                pxn[j] = e[j].x;
-                pyn[j] = e[j].y;
-                clr[j] = R(kClearFar);
             }
-            obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
-
             Pack<R, V> vrew, ox, oy, oth, owx, owy;
+            const uint32_t fw_all = step_envs<R, V>(e, dr, nx, ny, waves, tab, k_circ, k_obst, vrew.v);
             Pack<uint8_t, V> vfl;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                R reward;
-                const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
-                vrew.v[j] = reward;
-                vfl.v[j] = (uint8_t)f;
+                vfl.v[j] = (uint8_t)(fw_all >> (8 * j));
                 ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
                 owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
             }
@@ -193,6 +183,11 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
             if (!autoreset) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) st.add_length(vfl.v[j], otw.v[j] & kTimeMask);
+            }
+            if (p.term != nullptr && fw != 0u) {  // rare: keep the terminal observation (aqua.py:213)
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (vfl.v[j] & 1u) store_terminal<R>(p, base + j, e[j]);
             }
 
             // ---- stores (the goal only changes at reset: phase B writes it) ----
@@ -217,137 +212,17 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
         staged = next_staged;
         if (autoreset && __any_sync(0xffffffffu, fw != 0u)) {
             n_queued = reset_queue_push<V>(wq, n_queued, fw, (uint32_t)(base - p.env_begin), otw.v);
-            if (n_queued >= kResetGroups)
-                n_queued = reset_queue_drain<R, V>(p, tab, wq, n_queued, kResetGroups, st.length);
+            if constexpr (V == 1) {
+                if (n_queued >= kResetGroups) n_queued = reset_queue_drain<R, V>(p, tab, wq, n_queued, kResetGroups, st.length);
+            } else {
+                if (n_queued >= kLanePass) n_queued = reset_queue_drain_lanes<R, V>(p, tab, wq, n_queued, kLanePass, st.length);
+            }
         }
     }
     cp_async_wait<0>();
-    if (autoreset) reset_queue_drain<R, V>(p, tab, wq, n_queued, 1, st.length);  // flush the remainder
-    __syncthreads();
-    flush_stats(st, s_stats, p.stats);
-}
-
-// ------------------------------------------------------------------------------------------
-// K1r: `steps` env-steps per launch under the synthetic random policy (ACTION stream); the
-// state stays in registers between steps, per-step reward/flags are folded into the statistics
-// ------------------------------------------------------------------------------------------
-template <typename R, int V, bool CONTINUOUS>
-__global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) rollout_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
-    __shared__ unsigned long long s_stats[AQUA_N_STATS];
-    __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
-    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage, p.w.tab, p.w.k_obst, p.w.use_grid != 0);  // no staging buffers here
-    if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
-    __syncthreads();
-
-    const int64_t ld = p.ld;
-    const bool waves = p.w.waves != 0;
-    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
-    const int64_t tile_envs = (int64_t)blockDim.x * V;
-    const int64_t warp_off = (int64_t)(threadIdx.x & ~31u) * V;
-    uint32_t* const ptw_ = plane_tw<R>(p.planes, ld);
-
-    ThreadStats st;
-    for (int64_t tile_base = p.env_begin + (int64_t)blockIdx.x * tile_envs; tile_base + warp_off < p.env_end;
-         tile_base += (int64_t)gridDim.x * tile_envs) {
-        const int64_t base = tile_base + (int64_t)threadIdx.x * V;
-        const int nvalid = (int)max((int64_t)0, min((int64_t)V, p.env_end - base));
-        EnvState<R> e[V];
-        if (nvalid > 0) {
-            const Pack<R, V> vx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_X) + base);
-            const Pack<R, V> vy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_Y) + base);
-            const Pack<R, V> vth = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_THETA) + base);
-            const Pack<R, V> vwx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base);
-            const Pack<R, V> vwy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base);
-            const Pack<R, V> vgx = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base);
-            const Pack<R, V> vgy = ld_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base);
-            const Pack<uint32_t, V> vtw = ld_pack<uint32_t, V>(ptw_ + base);
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
-                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
-                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
-                e[j].tw = vtw.v[j];
-            }
-        }
-        for (int64_t k = 0; k < p.steps; ++k) {
-            uint32_t fw = 0u;
-            if (nvalid > 0) {
-                const uint64_t step = p.step0 + (uint64_t)k;
-                MoveTmp<R> m[V];
-                R pxn[V], pyn[V], clr[V];
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)(base + j));
-                    const uint2 ra = draw_action_words(p.w.keys, env_id, step);
-                    Drive<R> dr;
-                    if constexpr (CONTINUOUS) {
-                        uint32_t bad = 0;
-                        dr = drive_continuous<R>(draw_thrust(ra.x), draw_thrust(ra.y), bad);
-                    } else {
-                        dr = drive_from_index<R>(__umulhi(ra.x, 3u));
-                    }
-                    float nx = 0.f, ny = 0.f;
-                    if (waves) draw_wave_noise(p.w.keys, env_id, e[j].tw, nx, ny);
-                    move_env<R>(e[j], dr, (R)nx, (R)ny, waves, m[j]);
-                    pxn[j] = e[j].x;
-                    pyn[j] = e[j].y;
-                    clr[j] = R(kClearFar);
-                }
-                obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
-                Pack<uint8_t, V> vfl;
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    R reward;
-                    const uint32_t f = finish_env<R>(e[j], m[j], clr[j], reward);
-                    vfl.v[j] = (uint8_t)((j < nvalid) ? f : 0u);
-                    st.add_env<R>((j < nvalid) ? reward : R(0));
-                }
-                fw = flags_word<V>(vfl);
-                st.add_flags(fw, nvalid);
-            }
-            if (__any_sync(0xffffffffu, fw != 0u)) {
-                WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
-                uint32_t tws[V];
-#pragma unroll
-                for (int j = 0; j < V; ++j) tws[j] = (nvalid > 0) ? e[j].tw : 0u;
-                const int n_queued = reset_queue_push<V>(wq, 0, fw, (uint32_t)(base - p.env_begin), tws);
-                reset_queue_drain<R, V>(p, tab, wq, n_queued, 1, st.length);  // the next step needs the fresh state
-                if (fw != 0u) {  // pick the fresh episode up from the planes
-#pragma unroll
-                    for (int j = 0; j < V; ++j)
-                        if ((fw >> (8 * j)) & 1u) {
-                            const int64_t i = base + j;
-                            e[j].x = plane<R>(p.planes, ld, AQUA_PLANE_X)[i];
-                            e[j].y = plane<R>(p.planes, ld, AQUA_PLANE_Y)[i];
-                            e[j].th = plane<R>(p.planes, ld, AQUA_PLANE_THETA)[i];
-                            e[j].gx = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X)[i];
-                            e[j].gy = plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y)[i];
-                            e[j].wx = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X)[i];
-                            e[j].wy = plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y)[i];
-                            e[j].tw = ptw_[i];
-                        }
-                }
-            }
-        }
-        if (nvalid > 0) {
-            Pack<R, V> ox, oy, oth, owx, owy, ogx, ogy;
-            Pack<uint32_t, V> otw;
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
-                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy;
-                ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; otw.v[j] = e[j].tw;
-            }
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_X) + base, ox);
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_Y) + base, oy);
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_THETA) + base, oth);
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_X) + base, owx);
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_WAVE_Y) + base, owy);
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_X) + base, ogx);
-            st_pack<R, V>(plane<R>(p.planes, ld, AQUA_PLANE_GOAL_Y) + base, ogy);
-            st_pack<uint32_t, V>(ptw_ + base, otw);
-        }
+    if (autoreset) {  // flush the remainder
+        if constexpr (V == 1) reset_queue_drain<R, V>(p, tab, wq, n_queued, 1, st.length);
+        else reset_queue_drain_lanes<R, V>(p, tab, wq, n_queued, 1, st.length);
     }
     __syncthreads();
     flush_stats(st, s_stats, p.stats);

@@ -1,0 +1,405 @@
+// aqua_step_many.cuh -- K1m (step_many_kernel): K consecutive env.step() calls in ONE launch.
+//
+// A single-step launch moves 65 bytes per env-step through HBM / L2 and cannot take less than a few
+// microseconds, which is all a step of the BASELINE slab sizes (65,536 - 1M envs) is worth.  Here a
+// thread keeps the state of its V envs in registers for K steps: per env-step it reads the action
+// (4 bytes, from the caller's [K][row_stride] tape) and writes reward + flags (5 bytes); the state
+// planes are read once before and written once after the K steps.  What bounds the kernel is the
+// instruction issue rate, so the float32 arithmetic of env pairs is packed (aqua_packed.cuh).
+// The same kernel with TAPE = false draws the actions from the Philox ACTION stream (the synthetic
+// random policy of aqua_rollout_random) and writes no per-step outputs.
+//
+// Auto-reset without a stall: the state of an episode's first step depends only on (env id,
+// episode index), never on how the previous episode ended, so it is drawn AHEAD OF TIME.  Every env
+// has a 32-byte "stash" record in global memory = the reset state of the episode after the current
+// one, tagged with that episode's index.  When an env finishes, its owner swaps the record in (two
+// 16-byte loads) and goes on with the next step; the env is queued for a refill of its record, and
+// the warp refills 32 queued envs at a time with one LANE per env (reset_env_lane: the reference's
+// rejection loops, aqua.py:100-126, all lanes busy).  A record whose tag is not the episode wanted
+// (first launch, or the single-step kernels advanced the episode meanwhile, or the env finished
+// again before its refill ran) is refilled on the spot, so the stash is a cache: results do not
+// depend on it (test_step_many_equals_stepwise).
+#pragma once
+
+#include "aqua_kernel_util.cuh"
+
+namespace aqua {
+
+// register budget: 128-thread CTAs, 6 / 4 / 3 of them per SM at 1 / 2 / 4 envs per thread
+#ifndef AQUA_MANY_MINB
+#define AQUA_MANY_MINB(V) ((V) == 1 ? 6 : ((V) == 2 ? 4 : 3))
+#endif
+constexpr int kManyThreads = 128;  // launch bound; the launcher picks 32 .. 128 threads per CTA
+constexpr uint32_t kStashEmpty = 0xffffffffu;
+
+// what is left below a full pass (< 32) plus the entries of two steps (a waiting env's second entry)
+template <int V> struct RefillQueue {
+    uint32_t rel[64 * V + 32];  // env index relative to env_begin
+    uint32_t ep[64 * V + 32];   // episode index to draw the record for
+};
+
+// word: bit 0 of byte j set = queue env rel_base + j with episode ep[j]; returns the new length
+template <int V>
+__device__ __forceinline__ int refill_push(RefillQueue<V>& rq, int n, uint32_t word, uint32_t rel_base,
+                                           const uint32_t (&ep)[V]) {
+    const unsigned full = 0xffffffffu;
+    const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+        const bool d = ((word >> (8 * j)) & 1u) != 0u;
+        const unsigned mj = __ballot_sync(full, d);
+        if (d) {
+            const int at = n + __popc(mj & lt);
+            rq.rel[at] = rel_base + (uint32_t)j;
+            rq.ep[at] = ep[j];
+        }
+        n += __popc(mj);
+    }
+    return n;
+}
+
+__device__ __forceinline__ void stash_pack(const CoopResetResult& rr, uint32_t ep, uint4& a, uint4& b) {
+    a = make_uint4(__float_as_uint(rr.x), __float_as_uint(rr.y), __float_as_uint(rr.th), __float_as_uint(rr.gx));
+    b = make_uint4(__float_as_uint(rr.gy), __float_as_uint(rr.wx), __float_as_uint(rr.wy), ep);
+}
+
+// the record's reset state into the env, at time 0 of episode r1.w
+template <typename R> __device__ __forceinline__ void stash_unpack(const uint4& r0, const uint4& r1, EnvState<R>& e) {
+    e.x = (R)__uint_as_float(r0.x);
+    e.y = (R)__uint_as_float(r0.y);
+    e.th = (R)__uint_as_float(r0.z);
+    e.gx = (R)__uint_as_float(r0.w);
+    e.gy = (R)__uint_as_float(r1.x);
+    e.wx = (R)__uint_as_float(r1.y);
+    e.wy = (R)__uint_as_float(r1.z);
+    e.tw = r1.w << AQUA_TIME_BITS;
+}
+
+// Refills the records of queued envs, one lane per env, in passes of up to 32 from the tail while
+// at least `min_batch` are queued (kLanePass: full passes; 1: flush).  Warp-collective.
+// Not inlined: it runs once per 32 finished envs, and its registers (Philox4x32, the table tests)
+// should not count against the step loop's.
+template <typename R, int V>
+__device__ __forceinline__ int refill_drain(const StepArgs& p, const ObstacleView<R>& tab, const RefillQueue<V>& rq,
+                                         int n, int min_batch) {
+    const int lane = (int)(threadIdx.x & 31u);
+    const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
+    __syncwarp();  // queue entries are visible to the whole warp
+    while (n >= min_batch && n > 0) {
+        const int take = min(n, 32);
+        const int first = n - take;
+        if (lane < take) {
+            const int64_t i = p.env_begin + (int64_t)rq.rel[first + lane];
+            const uint32_t ep = rq.ep[first + lane];
+            const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
+            const CoopResetResult rr = reset_env_lane<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
+                                                         p.w.reset_band, wf, env_id, ep, p.w.forced);
+            uint4 a, b;
+            stash_pack(rr, ep, a, b);
+            __stcg(p.stash + 2 * i, a);  // L2 only: the owner lane reads it back with __ldcg
+            __stcg(p.stash + 2 * i + 1, b);
+        }
+        n = first;
+    }
+    __syncwarp();  // orders the record stores before the owners' loads (same warp)
+    return n;
+}
+
+// ten Philox2x32 rounds of N independent counters side by side
+template <int N>
+__device__ __forceinline__ void philox2x32_10_v(uint32_t (&c0)[N], uint32_t (&c1)[N], const uint32_t (&rk)[10],
+                                                uint32_t key_add) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t k = rk[r] + key_add;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const unsigned long long pr = (unsigned long long)0xD256D193u * c0[j];
+            const uint32_t n0 = (uint32_t)(pr >> 32) ^ c1[j] ^ k;
+            c1[j] = (uint32_t)pr;
+            c0[j] = n0;
+        }
+    }
+}
+
+template <typename R, int V, int ACT, bool TAPE>
+__global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_kernel(const __grid_constant__ StepArgs p) {
+    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
+    __shared__ unsigned long long s_stats[kSlotStats];
+    __shared__ DriveSlot<R> s_drive[3];
+    // dynamic shared memory: the culling grid of a dense map, then one refill queue per warp
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage, p.w.tab, p.w.k_obst, p.w.use_grid != 0);
+    RefillQueue<V>* const s_rq = reinterpret_cast<RefillQueue<V>*>(s_stage + cell_bytes(p.w.use_grid));
+    if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
+    if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
+        const Drive<R> d = drive_from_index<R>(threadIdx.x);
+        s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
+    }
+    __syncthreads();
+
+    const unsigned full = 0xffffffffu;
+    const uint32_t n = p.n_stream;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t warp_rel = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * (32u * V);  // the warp's first env
+    const uint32_t rel = warp_rel + lane * V;                                                      // this thread's
+    const int nvalid = rel >= n ? 0 : (int)min((uint32_t)V, n - rel);
+    const bool waves = p.w.waves != 0, autoreset = p.w.autoreset != 0;
+    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
+    uint32_t valid_mask = 0u;  // 0xff in byte j for the envs of this thread that exist
+#pragma unroll
+    for (int j = 0; j < V; ++j) valid_mask |= (j < nvalid ? 0xffu : 0u) << (8 * j);
+
+    ThreadStats st;
+    if (warp_rel < n) {  // warp-uniform
+        RefillQueue<V>& rq = s_rq[threadIdx.x >> 5];
+        int n_q = 0;           // queued refills, warp-uniform
+        int thr = kLanePass;   // queue length that triggers a refill pass; 1 = flush before the next step
+        uint32_t pend = 0u;    // bit 0 of byte j: env j finished and waits for the refill of its record
+        const uint4* const my_stash = p.stash + 2 * (p.env_begin + (int64_t)rel);
+        const uint32_t env_id = p.env_id0 + rel;
+
+        // ---- state in: the planes are padded to AQUA_TILE, full-width loads are in bounds ----
+        EnvState<R> e[V];
+        {
+            const size_t off = (size_t)rel * sizeof(R);
+            const Pack<R, V> vx = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_X] + off));
+            const Pack<R, V> vy = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_Y] + off));
+            const Pack<R, V> vth = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_THETA] + off));
+            const Pack<R, V> vgx = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_GOAL_X] + off));
+            const Pack<R, V> vgy = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_GOAL_Y] + off));
+            const Pack<R, V> vwx = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_WAVE_X] + off));
+            const Pack<R, V> vwy = ld_pack<R, V>(reinterpret_cast<const R*>(p.pl0[AQUA_PLANE_WAVE_Y] + off));
+            const Pack<uint32_t, V> vtw =
+                ld_pack<uint32_t, V>(reinterpret_cast<const uint32_t*>(p.pl0[AQUA_PLANE_TIME] + (size_t)rel * 4));
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
+                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
+                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
+                e[j].tw = vtw.v[j];
+            }
+        }
+
+        // ---- stash check: every env needs the record of its next episode; missing ones are queued and
+        // drawn by the flush that opens the step loop ----
+        if (autoreset) {
+            uint32_t want[V], word = 0u;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                want[j] = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+                if (j < nvalid) {
+                    const uint32_t tag = __ldcg(reinterpret_cast<const uint32_t*>(my_stash + 2 * j + 1) + 3);
+                    word |= (tag != want[j] ? 1u : 0u) << (8 * j);
+                }
+            }
+            if (__any_sync(full, word != 0u)) {
+                n_q = refill_push<V>(rq, n_q, word, rel, want);
+                thr = 1;
+            }
+        }
+
+        // ---- per-step I/O: row k of the tape is row_stride envs after row k - 1.  A thread without
+        // envs (behind the last one of the launch) touches no row: the rows end at row_stride, which
+        // only covers n rounded up to 16 ----
+        constexpr int kActBytes = act_bytes<ACT, V>();
+        const bool has = nvalid > 0;
+        const char* act_ptr_k = TAPE ? p.act0 + (size_t)rel * (kActBytes / V) : nullptr;
+        char* rew_ptr_k = (p.reward != nullptr && has) ? p.rew0 + (size_t)rel * sizeof(R) : nullptr;
+        uint8_t* flg_ptr_k = (p.flags != nullptr && has) ? p.flg0 + rel : nullptr;
+        ActVals<ACT, V> act_next;
+#pragma unroll
+        for (int j = 0; j < ActVals<ACT, V>::N; ++j) act_next.w[j] = 0u;
+        if (TAPE && has) act_next = fetch_actions<ACT, V>(act_ptr_k, V);
+
+        for (int64_t k = 0;; ++k) {
+            // ---- the ONE place where records are drawn: full passes while the launch runs; a flush
+            // when an env waits for its record, and after the last step ----
+            if (autoreset && (n_q >= thr || (k == p.steps && n_q > 0))) {
+                n_q = refill_drain<R, V>(p, tab, rq, n_q, k == p.steps ? 1 : thr);
+                thr = kLanePass;
+            }
+            if (__any_sync(full, pend != 0u)) {  // rare: the records of waiting envs are there now
+                uint32_t next[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+                    next[j] = (want + 1u) & kEpisodeMask;
+                    if ((pend >> (8 * j)) & 1u) {
+                        const uint4 r0 = __ldcg(my_stash + 2 * j), r1 = __ldcg(my_stash + 2 * j + 1);
+                        if (r1.w != want) __trap();  // the flush above drew exactly this record
+                        stash_unpack<R>(r0, r1, e[j]);
+                    }
+                }
+                n_q = refill_push<V>(rq, n_q, pend, rel, next);
+                pend = 0u;
+            }
+            if (k == p.steps) break;
+
+            // ---- actions: this step's were loaded during the previous one ----
+            Drive<R> dr[V];
+            float nx[V], ny[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
+            if constexpr (TAPE) {
+                const ActVals<ACT, V> act = act_next;
+                if (k + 1 < p.steps && has) {
+                    act_ptr_k += (size_t)p.row_stride * (kActBytes / V);
+                    act_next = fetch_actions<ACT, V>(act_ptr_k, V);
+                }
+                if constexpr (ACT == AQUA_ACT_F32X2) {
+                    uint32_t bad = 0u;
+                    decode_drives<R, ACT, V>(act, dr, bad);
+                    if (bad != 0u && nvalid != V) {  // the padding envs of a partial thread read what lies behind the row
+                        bad = 0u;
+#pragma unroll
+                        for (int j = 0; j < V; ++j) {
+                            const float l = __uint_as_float(act.w[2 * j]), r = __uint_as_float(act.w[2 * j + 1]);
+                            bad += (j < nvalid && !(l >= 0.2f && l <= 0.5f && r >= 0.2f && r <= 0.5f)) ? 1u : 0u;
+                        }
+                    }
+                    st.bad += bad;
+                } else {
+                    uint32_t worst = 0u;
+#pragma unroll
+                    for (int j = 0; j < V; ++j) {
+                        worst = max(worst, act.w[j]);
+                        const DriveSlot<R> d = s_drive[min(act.w[j], 2u)];  // outside {0,1,2}: full throttle
+                        dr[j].phi = d.phi;
+                        dr[j].h = d.h;
+                        dr[j].chord = d.chord;
+                    }
+                    if (worst > 2u) {  // rare
+#pragma unroll
+                        for (int j = 0; j < V; ++j) st.bad += (j < nvalid && act.w[j] > 2u) ? 1u : 0u;
+                    }
+                }
+                if (waves) {
+                    uint32_t tw[V];
+#pragma unroll
+                    for (int j = 0; j < V; ++j) tw[j] = e[j].tw;
+                    draw_wave_noise_v<V>(p.w.keys, env_id, tw, nx, ny);
+                }
+            } else {
+                // synthetic random policy (test_random.py:19-20): the ACTION and WAVE_NOISE chains of
+                // the V envs advance side by side
+                const uint64_t step = p.step0 + (uint64_t)k;
+                uint32_t a0[V], a1[V], w0[V], w1[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    a0[j] = w0[j] = env_id + (uint32_t)j;
+                    a1[j] = (uint32_t)step;
+                    w1[j] = e[j].tw;
+                }
+                philox2x32_10_v<V>(a0, a1, p.w.keys.action, (uint32_t)(step >> 32));
+                if (waves) philox2x32_10_v<V>(w0, w1, p.w.keys.noise, 0u);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if constexpr (ACT == AQUA_ACT_F32X2) {
+                        uint32_t bad = 0u;
+                        dr[j] = drive_continuous<R>(draw_thrust(a0[j]), draw_thrust(a1[j]), bad);
+                    } else {
+                        const DriveSlot<R> d = s_drive[__umulhi(a0[j], 3u)];
+                        dr[j].phi = d.phi;
+                        dr[j].h = d.h;
+                        dr[j].chord = d.chord;
+                    }
+                    if (waves) {
+                        nx[j] = draw_noise(w0[j]);
+                        ny[j] = draw_noise(w1[j]);
+                    }
+                }
+            }
+
+            // ---- the step ----
+            R reward[V];
+            uint32_t fw = step_envs<R, V>(e, dr, nx, ny, waves, tab, k_circ, k_obst, reward);
+            fw &= valid_mask;
+            if (nvalid != V) {
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if (j >= nvalid) reward[j] = R(0);
+            }
+            st.add_flags(fw, nvalid);
+#pragma unroll
+            for (int j = 0; j < V; ++j) st.add_env<R>(reward[j]);
+
+            // ---- outputs of step k (full-width: a partial thread writes into the row's padding) ----
+            if (rew_ptr_k != nullptr) {
+                Pack<R, V> vrew;
+#pragma unroll
+                for (int j = 0; j < V; ++j) vrew.v[j] = reward[j];
+                st_pack<R, V>(reinterpret_cast<R*>(rew_ptr_k), vrew);
+                rew_ptr_k += (size_t)p.row_stride * sizeof(R);
+            }
+            if (flg_ptr_k != nullptr) {
+                if constexpr (V == 4) *reinterpret_cast<uint32_t*>(flg_ptr_k) = fw;
+                else if constexpr (V == 2) *reinterpret_cast<uint16_t*>(flg_ptr_k) = (uint16_t)fw;
+                else *flg_ptr_k = (uint8_t)fw;
+                flg_ptr_k += p.row_stride;
+            }
+
+            // ---- finished envs: the next episode comes from the stash ----
+            if (!autoreset) {
+#pragma unroll
+                for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), e[j].tw & kTimeMask);
+            } else if (__any_sync(full, fw != 0u)) {
+                uint32_t ep[V], word = 0u;  // what gets queued: bit 0 of byte j, with episode ep[j]
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;  // the episode that opens now
+                    ep[j] = (want + 1u) & kEpisodeMask;                                        // the record after it
+                    if ((fw >> (8 * j)) & 1u) {
+                        st.length += e[j].tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
+                        if (p.term != nullptr) store_terminal<R>(p, p.env_begin + rel + j, e[j]);  // aqua.py:213
+                        const uint4 r0 = __ldcg(my_stash + 2 * j), r1 = __ldcg(my_stash + 2 * j + 1);
+                        word |= 1u << (8 * j);
+                        if (r1.w == want) {  // swap it in; its successor is drawn by a later pass
+                            stash_unpack<R>(r0, r1, e[j]);
+                        } else {
+                            // the env finished again before the refill of its record ran (or the record was
+                            // never drawn): queue exactly this record (a second entry for it is harmless),
+                            // flush before the next step, pick it up there
+                            ep[j] = want;
+                            pend |= 1u << (8 * j);
+                        }
+                    }
+                }
+                n_q = refill_push<V>(rq, n_q, word, rel, ep);
+                if (__any_sync(full, pend != 0u)) thr = 1;
+            }
+        }
+
+        // ---- state out (full-width: the plane padding behind the last env is scratch) ----
+        if (nvalid > 0) {
+            Pack<R, V> ox, oy, oth, owx, owy, ogx, ogy;
+            Pack<uint32_t, V> otw;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy;
+                ogx.v[j] = e[j].gx; ogy.v[j] = e[j].gy; otw.v[j] = e[j].tw;
+            }
+            const size_t off = (size_t)rel * sizeof(R);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off), ox);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_Y]) + off), oy);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_THETA]) + off), oth);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_GOAL_X]) + off), ogx);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_GOAL_Y]) + off), ogy);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_X]) + off), owx);
+            st_pack<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_WAVE_Y]) + off), owy);
+            st_pack<uint32_t, V>(reinterpret_cast<uint32_t*>(const_cast<char*>(p.pl0[AQUA_PLANE_TIME]) + (size_t)rel * 4), otw);
+        }
+    }
+    __syncthreads();
+    flush_stats(st, s_stats, p.stats);
+}
+
+// fresh stash: no record drawn yet
+__global__ void stash_init_kernel(uint4* stash, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= ld) return;
+    stash[2 * i] = make_uint4(0u, 0u, 0u, 0u);
+    stash[2 * i + 1] = make_uint4(0u, 0u, 0u, kStashEmpty);
+}
+
+}  // namespace aqua

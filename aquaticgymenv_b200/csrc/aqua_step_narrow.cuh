@@ -33,13 +33,13 @@ __device__ __forceinline__ void flush_stats_warp(ThreadStats& t, unsigned long l
     for (int off = 16; off > 0; off >>= 1) r += __shfl_xor_sync(full, r, off);
     static_assert(AQUA_STAT_EPISODES == 0 && AQUA_STAT_COLLIDED == 1 && AQUA_STAT_TIMEOUT == 2 && AQUA_STAT_SUCCESS == 3 &&
                       AQUA_STAT_LENGTH_SUM == 4 && AQUA_STAT_REWARD_SUM == 5 && AQUA_STAT_STEPS == 6 &&
-                      AQUA_STAT_BAD_ACTIONS == 7 && AQUA_N_STATS == 8,
+                      AQUA_STAT_BAD_ACTIONS == 7 && kSlotStats == 8,
                   "lane k carries counter k");
     const unsigned lane = threadIdx.x & 31u;
     unsigned long long v = (unsigned long long)r;  // lane 5: the fixed-point reward sum
     v = lane == 0 ? d : lane == 1 ? c : lane == 2 ? o : lane == 3 ? s : lane == 4 ? l : lane == 6 ? n : lane == 7 ? b : v;
     const unsigned warp = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (lane < AQUA_N_STATS && v != 0ull) atomicAdd(&g_slots[(warp % kStatSlots) * AQUA_N_STATS + lane], v);
+    if (lane < kSlotStats && v != 0ull) atomicAdd(&g_slots[(warp % kStatSlots) * kSlotStats + lane], v);
 }
 
 // AQUA_PDL=1: consecutive narrow launches overlap their launch latency (see the kernel's first lines)
@@ -98,6 +98,7 @@ __global__ void __launch_bounds__(kNarrowThreads, 8) step_narrow_kernel(const __
         st.add_env<R>(reward);
         if (!autoreset) st.add_length(fw, e[0].tw & kTimeMask);
         tw_out[0] = e[0].tw;
+        if (p.term != nullptr && (fw & 1u)) store_terminal<R>(p, p.env_begin + i, e[0]);  // aqua.py:213
 
         // ---- stores (the goal only changes at reset: phase B writes it) ----
         *reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off) = e[0].x;

@@ -48,60 +48,75 @@ template <typename T, int V> __device__ __forceinline__ Pack<T, V> lds_pack(uint
     return out;
 }
 
-// wave increments of V consecutive envs (ids env_id .. env_id + V - 1): draw_wave_noise() for
-// each, the ten rounds of the V counters interleaved
-template <int V>
-__device__ __forceinline__ void draw_wave_noise_v(const PhiloxKeys& keys, uint32_t env_id, const uint32_t (&tw)[V],
-                                                  float (&nx)[V], float (&ny)[V]) {
-    uint32_t c0[V], c1[V];
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-        c0[j] = env_id + (uint32_t)j;
-        c1[j] = tw[j];
-    }
-#pragma unroll
-    for (int r = 0; r < 10; ++r) {
-#pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const unsigned long long pr = (unsigned long long)0xD256D193u * c0[j];
-            const uint32_t n0 = (uint32_t)(pr >> 32) ^ c1[j] ^ keys.noise[r];
-            c1[j] = (uint32_t)pr;
-            c0[j] = n0;
-        }
-    }
-#pragma unroll
-    for (int j = 0; j < V; ++j) {
-        nx[j] = draw_noise(c0[j]);
-        ny[j] = draw_noise(c1[j]);
-    }
-}
-
-template <typename R> struct alignas(16) DriveSlot {
-    R phi, h, chord, pad;
-};
-
 template <int ACT, int V> constexpr bool stream_supported() {
     constexpr int b = act_bytes<ACT, V>();
     return V > 1 && (b == 4 || b == 8 || b == 16 || b == 32);
 }
 
+// ------------------------------------------------------------------------------------------
+// Bulk staging (AQUA_TMA=1, the default): the 8 plane segments + actions of a warp tile are
+// contiguous runs of 32 x 16 bytes in global memory, so ONE lane of the warp moves each with a bulk
+// asynchronous copy (cp.async.bulk.shared::cta.global, the 1-D form of the tensor memory
+// accelerator: UBLKCP in SASS) that lands in the warp's 512-byte stretch of the staging slot and
+// reports its bytes to the warp's mbarrier for that buffer.  Nine copy instructions per tile
+// instead of 9 x 32 per-lane LDGSTS and their address arithmetic; the lanes wait on the mbarrier
+// phase instead of a cp.async group.  A buffer is refilled after __syncwarp(): every lane has read
+// its slices by then.  AQUA_TMA=0 keeps the per-lane cp.async form (profiles/r02_tma_ab.txt).
+// ------------------------------------------------------------------------------------------
+#ifndef AQUA_TMA
+#define AQUA_TMA 1
+#endif
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+// bounded: a copy that never lands traps instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t spins = 0u;
+    while (!mbar_try_wait(bar, parity))
+        if (++spins > (1u << 26)) __trap();
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
 template <typename R, int V, int ACT, bool WAVES>
-__global__ void __launch_bounds__(kMaxThreads + kSchedThreads, kMinBlocks)
+__global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 step_stream_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
-    __shared__ unsigned long long s_stats[AQUA_N_STATS];
+    __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     __shared__ DriveSlot<R> s_drive[3];
-#if AQUA_SCHED_WARP
-    __shared__ uint32_t s_ring[kMaxThreads / 32][kRing];
-    if (threadIdx.x < (kMaxThreads / 32) * kRing) (&s_ring[0][0])[threadIdx.x] = kRingEmpty;
+#if AQUA_TMA
+    __shared__ __align__(8) unsigned long long s_bar[kMaxThreads / 32][2];  // [warp][buffer]
 #endif
     const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
-    if (threadIdx.x < AQUA_N_STATS) s_stats[threadIdx.x] = 0ull;
+    if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
         s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
     }
+#if AQUA_TMA
+    if ((threadIdx.x & 31u) == 0u) {
+        mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][0]), 1u);
+        mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][1]), 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+#endif
     __syncthreads();
 
     constexpr int kSlot = stage_slot<R, V>(), kPitch = stage_pitch<R, V>();
@@ -115,10 +130,33 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
     const uint32_t n = p.n_stream;
     const bool autoreset = p.w.autoreset != 0;
     const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
+    const uint32_t lane_off = (threadIdx.x & 31u) * V;
     uint32_t s_cur = smem_u32(s_stage) + threadIdx.x * kSlot, s_nxt = s_cur + kStage;
 
+#if AQUA_TMA
+    // The warp's stretch of a staging slot is the 32 slices of its lanes, kSlot bytes each.  The
+    // actions are one linear run of kActBytes per thread instead (4 to 32 bytes: the two action
+    // slots together hold kMaxThreads x 32), so thread t finds its actions act_off = t * (kActBytes -
+    // kSlot) bytes from where a kSlot-byte slice would lie (modulo 2^32: the offset may be negative).
+    const uint32_t act_off = AQUA_N_PLANES * kPitch + threadIdx.x * (uint32_t)(kActBytes - kSlot);
+    constexpr uint32_t kTxBytes = 32u * (7u * kSlot + 4u * V + kActBytes);
+    uint32_t bar_cur = smem_u32(&s_bar[threadIdx.x >> 5][0]), bar_nxt = bar_cur + 8u;
+    uint32_t par_cur = 0u, par_nxt = 0u;  // phase parity to wait for on each buffer
+    const bool issuer = (threadIdx.x & 31u) == 0u;
+    // stages the tile whose first env (for this lane) is i into the buffer s (this lane's slice base)
+    auto prefetch = [&](uint32_t s, uint32_t bar, uint32_t i) {
+        if (issuer) {  // lane 0: i is the tile's first env, s the warp's stretch
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' reads of s precede the refill
+            mbar_expect_tx(bar, kTxBytes);
+#pragma unroll
+            for (int pl = 0; pl < 7; ++pl) bulk_g2s(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R), 32u * kSlot, bar);
+            bulk_g2s(s + AQUA_PLANE_TIME * kPitch, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4, 32u * 4u * V, bar);
+            bulk_g2s(s + act_off, p.act0 + (size_t)i * (kActBytes / V), 32u * kActBytes, bar);
+        }
+    };
+#else
     // the 8 plane slices + actions of the V envs starting at (relative) env index i
-    auto prefetch = [&](uint32_t s, uint32_t i) {
+    auto prefetch = [&](uint32_t s, uint32_t, uint32_t i) {
 #pragma unroll
         for (int pl = 0; pl < 7; ++pl) cp_async_s<kSlot>(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R));
         cp_async_s<4 * V>(s + AQUA_PLANE_TIME * kPitch, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4);
@@ -126,9 +164,11 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
         for (int q = 0; q < kActPieces; ++q)
             cp_async_s<kActPiece>(s + (AQUA_N_PLANES + q) * kPitch, p.act0 + (size_t)i * (kActBytes / V) + q * kActPiece);
     };
+    const uint32_t bar_cur = 0u, bar_nxt = 0u;
+#endif
 
     ThreadStats st;
-    WarpResetQueue<V>& wq = s_wq[(threadIdx.x >> 5) % (kMaxThreads / 32)];  // (the scheduler warp queues nothing)
+    WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
     int n_queued = 0;  // warp-uniform
 
     // Work distribution: a warp tile is 32 V consecutive envs.  Every warp starts with four
@@ -144,72 +184,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
     // Two staging buffers, prefetch distance two tiles: a buffer is refilled (with the tile after
     // next) as soon as its slices have been read into registers, so every copy has two tile
     // times to land.
-    const uint32_t lane_off = (threadIdx.x & 31u) * V;
     constexpr uint32_t kWarpTile = 32u * V;
-#if AQUA_SCHED_WARP
-    // Scheduler warp: the last warp of the CTA does every tile claim, so that no worker ever waits
-    // for the reply of a global atomic (measured: 21 % of a worker's time when it claimed its own
-    // tiles).  Lane l feeds worker warp l through the ring s_ring[l]: it claims two tiles at a time
-    // (atomicAdd 2 on the worker's pool) whenever two slots are free and writes kRingDone when the
-    // pool is dry.  A worker pops one tile per tile it processes and always drains its ring up to
-    // kRingDone, so no claimed tile is lost.  All spins are bounded (trap, not hang).
-    const uint32_t n_workers = (blockDim.x >> 5) - 1u;
-    const uint32_t n_warps = gridDim.x * n_workers;  // worker warps of the launch
-    const uint32_t n_pools = min((uint32_t)kTilePools, n_workers);
-    const uint32_t n_tiles = n / kWarpTile;
-    const bool is_sched = (threadIdx.x >> 5) == n_workers;
-    constexpr uint32_t kStatic = 3u;  // statically assigned tiles per worker
-    if (is_sched) {
-        const uint32_t l = threadIdx.x & 31u;
-        if (l < n_workers) {
-            volatile uint32_t* const ring = s_ring[l];
-            const uint32_t q = l % n_pools;
-            uint32_t* const ctr = p.tile_ctr + q * kTilePoolStride;
-            uint32_t head = 0u;
-            for (;;) {
-                uint32_t spins = 0u;
-                while (ring[head % kRing] != kRingEmpty || ring[(head + 1u) % kRing] != kRingEmpty) {
-                    __nanosleep(100);
-                    if (++spins > (1u << 24)) __trap();
-                }
-                const uint32_t c = atomicAdd(ctr, 2u);  // positions c, c + 1 of pool q's tile sequence
-                const uint32_t t0 = kStatic * n_warps + c * n_pools + q, t1 = t0 + n_pools;
-                if (t0 >= n_tiles) { ring[head % kRing] = kRingDone; break; }
-                ring[head % kRing] = t0;
-                if (t1 >= n_tiles) { ring[(head + 1u) % kRing] = kRingDone; break; }
-                ring[(head + 1u) % kRing] = t1;
-                head += 2u;
-            }
-        }
-    }
-    const uint32_t warp_g = blockIdx.x * n_workers + (threadIdx.x >> 5);
-    uint32_t i = is_sched ? n : warp_g * kWarpTile + lane_off;       // this tile
-    uint32_t i1 = is_sched ? n : i + n_warps * kWarpTile;            // the next one (in flight)
-    uint32_t i2 = is_sched ? n : i1 + n_warps * kWarpTile;           // the one after (to be prefetched)
-    volatile uint32_t* const my_ring = s_ring[is_sched ? 0u : (threadIdx.x >> 5)];
-    uint32_t ring_head = 0u;
-    bool ring_done = is_sched;  // warp-uniform
-    // next tile of this worker (env index of this thread's slice), n once the pool is dry
-    auto ring_pop = [&]() -> uint32_t {
-        if (ring_done) return n;
-        uint32_t t = 0u;
-        if ((threadIdx.x & 31u) == 0u) {
-            uint32_t spins = 0u;
-            while ((t = my_ring[ring_head % kRing]) == kRingEmpty) {
-                __nanosleep(50);
-                if (++spins > (1u << 24)) __trap();
-            }
-            if (t != kRingDone) my_ring[ring_head % kRing] = kRingEmpty;  // hand the slot back
-        }
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t == kRingDone) {
-            ring_done = true;
-            return n;
-        }
-        ++ring_head;
-        return t * kWarpTile + lane_off;
-    };
-#else
     uint32_t lane_id;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(lane_id));
     const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);  // of the launch
@@ -231,21 +206,27 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
     uint32_t claim_old = 0u;      // issued during the previous tile: the successor of i3
     bool old_valid = i3 < n;      // warp-uniform
     if (old_valid) claim_tile(claim_old);
+    if (i < n) prefetch(s_cur, bar_cur, i);
+#if !AQUA_TMA
+    cp_async_commit();
 #endif
-    if (i < n) prefetch(s_cur, i);
+    if (i1 < n) prefetch(s_nxt, bar_nxt, i1);
+#if !AQUA_TMA
     cp_async_commit();
-    if (i1 < n) prefetch(s_nxt, i1);
-    cp_async_commit();
+#endif
     for (;;) {
         const bool live = i < n;  // warp-uniform: n is a multiple of 32 V
         uint32_t fw = 0u;
         Pack<uint32_t, V> otw;
-#if !AQUA_SCHED_WARP
         uint32_t claim_new = 0u;
-#endif
         const uint32_t i_done = i;
         if (live) {
+#if AQUA_TMA
+            mbar_wait(bar_cur, par_cur);  // this tile's nine copies have landed
+            par_cur ^= 1u;
+#else
             cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
+#endif
 
             const Pack<R, V> vx = lds_pack<R, V>(s_cur + AQUA_PLANE_X * kPitch);
             const Pack<R, V> vy = lds_pack<R, V>(s_cur + AQUA_PLANE_Y * kPitch);
@@ -259,28 +240,43 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
 #pragma unroll
             for (int q = 0; q < kActPieces; ++q) {
                 uint32_t w[kActPiece / 4];
+#if AQUA_TMA
+                lds_words<kActPiece>(s_cur + act_off + q * kActPiece, w);
+#else
                 lds_words<kActPiece>(s_cur + (AQUA_N_PLANES + q) * kPitch, w);
+#endif
 #pragma unroll
                 for (int k = 0; k < kActPiece / 4; ++k) araw[q * (kActPiece / 4) + k] = w[k];
             }
             const ActVals<ACT, V> act = actions_from_raw<ACT, V, kActWords>(araw);
-            if (i2 < n) prefetch(s_cur, i2);  // refill the buffer just read
+#if AQUA_TMA
+            __syncwarp();  // every lane has read its slices: the buffer may be refilled
+#endif
+            if (i2 < n) prefetch(s_cur, bar_cur, i2);  // refill the buffer just read
+#if !AQUA_TMA
             cp_async_commit();
-#if !AQUA_SCHED_WARP
+#endif
             const bool new_valid = old_valid && i3 < n;  // the pool had tiles left at the last look
             if (new_valid) claim_tile(claim_new);
-#endif
 
+            EnvState<R> e[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
+                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
+                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
+                e[j].tw = vtw.v[j];
+            }
+            Pack<R, V> vrew;
 #if AQUA_MEMBENCH
             // Measurement build only (make variant FLAGS=-DAQUA_MEMBENCH=1): the data movement of
             // this kernel -- staging pipeline, dynamic tiles, every load consumed, every store
             // issued -- without the step's arithmetic.  Flags stay 0 (no resets).  Timed next to the
             // real kernel on one box it gives the ceiling of this structure; never the shipped build.
-            Pack<R, V> vrew, ox = vx, oy = vy, oth = vth, owx = vwx, owy = vwy;
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 vrew.v[j] = vgx.v[j] + vgy.v[j];
-                otw.v[j] = vtw.v[j] + act.w[j];
+                e[j].tw = vtw.v[j] + act.w[j];
             }
             st.steps += V;
 #else
@@ -310,41 +306,26 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
             }
-
-            EnvState<R> e[V];
-            MoveTmp<R> m[V];
-            R pxn[V], pyn[V], clr[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                e[j].x = vx.v[j]; e[j].y = vy.v[j]; e[j].th = vth.v[j];
-                e[j].wx = vwx.v[j]; e[j].wy = vwy.v[j];
-                e[j].gx = vgx.v[j]; e[j].gy = vgy.v[j];
-                e[j].tw = vtw.v[j];
-                move_env<R>(e[j], dr[j], (R)nx[j], (R)ny[j], WAVES, m[j]);
-                pxn[j] = e[j].x;
-                pyn[j] = e[j].y;
-                clr[j] = R(kClearFar);
-            }
-            obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
-
-            Pack<R, V> vrew, ox, oy, oth, owx, owy;
-#pragma unroll
-            for (int j = 0; j < V; ++j) {  // the flags word (byte j = env j) is built in 32-bit arithmetic
-                R reward;
-                fw |= finish_env<R>(e[j], m[j], clr[j], reward) << (8 * j);
-                vrew.v[j] = reward;
-                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
-                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
-            }
+            fw = step_envs<R, V>(e, dr, nx, ny, WAVES, tab, k_circ, k_obst, vrew.v);
             st.add_flags(fw, V);
 #pragma unroll
             for (int j = 0; j < V; ++j) st.add_env<R>(vrew.v[j]);
             if (!autoreset) {
 #pragma unroll
-                for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), otw.v[j] & kTimeMask);
+                for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), e[j].tw & kTimeMask);
             }
-
+            if (p.term != nullptr && fw != 0u) {  // rare: keep the terminal observation (aqua.py:213)
+#pragma unroll
+                for (int j = 0; j < V; ++j)
+                    if ((fw >> (8 * j)) & 1u) store_terminal<R>(p, p.env_begin + i + j, e[j]);
+            }
 #endif
+            Pack<R, V> ox, oy, oth, owx, owy;
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                ox.v[j] = e[j].x; oy.v[j] = e[j].y; oth.v[j] = e[j].th;
+                owx.v[j] = e[j].wx; owy.v[j] = e[j].wy; otw.v[j] = e[j].tw;
+            }
             // ---- stores (the goal only changes at reset: phase B writes it) ----
             const size_t off = (size_t)i * sizeof(R);
             st_pack_cs<R, V>(reinterpret_cast<R*>(const_cast<char*>(p.pl0[AQUA_PLANE_X]) + off), ox);
@@ -360,11 +341,13 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
             const uint32_t t = s_cur;
             s_cur = s_nxt;
             s_nxt = t;
-#if AQUA_SCHED_WARP
-            i = i1;
-            i1 = i2;
-            i2 = ring_pop();
-#else
+#if AQUA_TMA
+            const uint32_t tb = bar_cur, tp = par_cur;
+            bar_cur = bar_nxt;
+            par_cur = par_nxt;
+            bar_nxt = tb;
+            par_nxt = tp;
+#endif
             // the claim of the previous tile is consumed here, after this tile's stores
             asm volatile("" : "+r"(claim_old) : : "memory");
             const uint32_t i4 =
@@ -375,21 +358,23 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
             i3 = i4;
             claim_old = claim_new;
             old_valid = new_valid;
-#endif
         }
         if (autoreset) {  // phase B, warp-collective
             if (live && __any_sync(0xffffffffu, fw != 0u)) n_queued = reset_queue_push<V>(wq, n_queued, fw, i_done, otw.v);
-            const int need = live ? kResetGroups : 1;  // full passes only; the rest is flushed at the end
-            if (n_queued >= need) n_queued = reset_queue_drain<R, V>(p, tab, wq, n_queued, need, st.length);
+            const int need = live ? kLanePass : 1;  // full passes only; the rest is flushed at the end
+            if (n_queued >= need) n_queued = reset_queue_drain_lanes<R, V>(p, tab, wq, n_queued, need, st.length);
         }
         if (!live) break;
     }
+#if !AQUA_TMA
     cp_async_wait<0>();
+#endif
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
     if (threadIdx.x == 0) {  // the last CTA to finish rearms the tile counter for the next launch
         __threadfence();
         if (atomicAdd(p.tile_ctr + kTilePools * kTilePoolStride, 1u) == gridDim.x - 1u) {
+            __threadfence();  // every other CTA's claims precede the re-zeroing
             for (int k = 0; k <= kTilePools; ++k) p.tile_ctr[k * kTilePoolStride] = 0u;
             __threadfence();
         }

@@ -64,12 +64,18 @@ def table_to_reference_list(tab):
 
 class LazyInfo(dict):
     """``info`` of a batched step: the reference's three keys (aqua.py:194-198) as bool tensors,
-    materialised from the flags byte on first access."""
+    materialised from the flags byte on first access.  With ``keep_terminal`` it also carries
+    ``terminal_observation`` ``[N, 5]``: for the envs that finished in this step, the observation the
+    reference returns together with ``done=True`` (aqua.py:213) -- the ``obs`` of an auto-resetting
+    env already shows the next episode (rows of envs that did not finish hold their last terminal
+    observation)."""
     _BITS = {"Termination.collided": N.FLAG_COLLIDED, "Termination.time": N.FLAG_TIME,
              "Termination.success": N.FLAG_SUCCESS}
 
-    def __init__(self, flags):
+    def __init__(self, flags, terminal=None):
         super().__init__(flags=flags)
+        if terminal is not None:
+            self["terminal_observation"] = terminal
 
     def __missing__(self, key):
         bit = self._BITS[key]
@@ -95,12 +101,14 @@ class AquaVecEnv(object):
       (parity-grade pose);
     * ``autoreset``: finished envs are reset inside the step kernel (vector-env semantics);
     * ``geometry``: ``"auto"`` (default), or force the ``"wide"`` / ``"narrow"`` kernel family
-      (tests and tuning; results are identical).
+      (tests and tuning; results are identical);
+    * ``keep_terminal``: keep the observation a finished env returned with ``done=True``
+      (``terminal_obs`` ``[N, 5]``, ``info["terminal_observation"]``).
     """
 
     def __init__(self, num_envs, continuous=False, obstacles=False, waves=True, random_boat=True,
                  random_goal=True, seed=0, env_id_base=0, device=None, precision="float32",
-                 autoreset=True, geometry="auto"):
+                 autoreset=True, geometry="auto", keep_terminal=False):
         self._h = None
         self.lib = N.load()
         if device is None:
@@ -139,12 +147,17 @@ class AquaVecEnv(object):
         tab = np.ascontiguousarray(self.table)
         cfg.obstacles = tab.ctypes.data_as(C.POINTER(C.c_double)) if tab.size else None
         cfg.seed, cfg.env_id_base = self.seed, self.env_id_base
+        cfg.keep_terminal = int(bool(keep_terminal))
+        self._terminal = None
         if self.num_envs >= 1 and torch.cuda.is_available():
             # caller-owned state: the planes are a torch tensor, observations are views of it
             self._state = torch.zeros(N.N_PLANES * self.ld, dtype=self.dtype, device=device)
             torch.cuda.current_stream(device).synchronize()  # aqua_create initialises it on stream 0
             cfg.state = self._state.data_ptr()
             cfg.ld = self.ld
+            if keep_terminal:  # caller-owned as well: the terminal observations are views of it
+                self._terminal = torch.zeros(5 * self.ld, dtype=self.dtype, device=device)
+                cfg.terminal = self._terminal.data_ptr()
         else:
             self._state = None
         h = C.c_void_p()
@@ -159,6 +172,10 @@ class AquaVecEnv(object):
         self.reward = torch.zeros(self.ld, dtype=self.dtype, device=device)[:self.num_envs]
         self.flags = torch.zeros(self.ld, dtype=torch.uint8, device=device)[:self.num_envs]
         self._stats_dev = torch.zeros(N.N_STATS, dtype=torch.int64, device=device)
+        self.terminal_obs_planes = self.terminal_obs = None
+        if keep_terminal:
+            self.terminal_obs_planes = self._terminal.view(5, self.ld)[:, :self.num_envs]  # [5, N]
+            self.terminal_obs = self.terminal_obs_planes.t()                                # [N, 5]
         self._step_index = 0
         # constants of the per-step call (the wrapper used to cost more than the launch itself on
         # small slabs: 11 us per call against 5 us through the bare ABI, tools/small_slab_probe.py)
@@ -228,7 +245,7 @@ class AquaVecEnv(object):
         ``autoreset`` the observation of a finished env is the first one of its next episode.
         The returned tensors are reused by the next call."""
         flags = self.step_flags(actions, noise)
-        return self.obs, self.reward, flags != 0, LazyInfo(flags)
+        return self.obs, self.reward, flags != 0, LazyInfo(flags, self.terminal_obs)
 
     def step_flags(self, actions, noise=None):
         """The launch only: updates ``obs``/``reward``/``flags`` in place and returns ``flags``
@@ -288,6 +305,12 @@ class AquaVecEnv(object):
         self._step_index += 1
         return obs_out, reward_out, flags_out
 
+    def host_d2h_bytes_per_env(self):
+        """Bytes per env-step that :meth:`step_host` copies device -> host when all three outputs are
+        requested (obs planes that changed, reward, flags)."""
+        es = 8 if self.precision == N.F64 else 4
+        return 5 * es + es + 1
+
     def render(self, mode="human"):
         """aqua.py:215-365 draws a pyglet window; the batched env has no viewer (out of scope)."""
         return None
@@ -306,6 +329,41 @@ class AquaVecEnv(object):
         N.check(self.lib.aqua_random_actions(self._h, self._stream(), int(step_index),
                                              C.c_void_p(out.data_ptr()), adt))
         return out
+
+    def step_many(self, actions, reward_out=None, flags_out=None):
+        """``K`` consecutive ``env.step`` calls in ONE launch (``aqua_step_many``): ``actions`` is the
+        tape ``[K, N]`` (discrete, integer dtype) or ``[K, N, 2]`` (continuous float32) on the env's
+        device.  Returns ``(reward [K, N], flags [K, N] uint8)``; bit for bit what ``K`` calls of
+        :meth:`step` give.  The state planes (``obs``) hold the observation after the last step.
+        Rows must be 16 envs aligned: for ``N % 16 != 0`` pass (and get) tensors ``[K, N16]`` with
+        ``N16 = N`` rounded up to 16 and use the first ``N`` columns."""
+        self._check_open()
+        if not (type(actions) is torch.Tensor and actions.is_cuda and actions.is_contiguous()):
+            raise TypeError("step_many takes a contiguous CUDA tensor [K, N] (or [K, N, 2])")
+        if self.continuous:
+            if actions.dtype != torch.float32 or actions.dim() != 3 or actions.shape[2] != 2:
+                raise ValueError("continuous tape must be float32 [K, N, 2]")
+            adt = N.ACT_F32X2
+        else:
+            if actions.dim() != 2 or actions.dtype not in _ACT_DTYPES:
+                raise ValueError("discrete tape must be int32 / int64 / uint8 [K, N]")
+            adt = _ACT_DTYPES[actions.dtype]
+        K, stride = int(actions.shape[0]), int(actions.shape[1])
+        if stride < self.num_envs or stride % 16:
+            raise ValueError("tape rows must have >= %d columns, a multiple of 16; got %d" % (self.num_envs, stride))
+        if reward_out is None:
+            reward_out = torch.empty(K, stride, dtype=self.dtype, device=self.device)
+        if flags_out is None:
+            flags_out = torch.empty(K, stride, dtype=torch.uint8, device=self.device)
+        for name, t, dt in (("reward_out", reward_out, self.dtype), ("flags_out", flags_out, torch.uint8)):
+            if t is not False and (t.shape != (K, stride) or t.dtype != dt or not t.is_contiguous()):
+                raise ValueError("%s must be a contiguous %s [%d, %d] tensor" % (name, dt, K, stride))
+        N.check(self.lib.aqua_step_many(
+            self._h, self._stream(), K, C.c_void_p(actions.data_ptr()), adt,
+            None if reward_out is False else C.c_void_p(reward_out.data_ptr()),
+            None if flags_out is False else C.c_void_p(flags_out.data_ptr()), stride))
+        self._step_index += K
+        return reward_out, flags_out
 
     def rollout_random(self, steps, first_step_index=None):
         """``steps`` env-steps in one launch under the synthetic random policy (always auto-resets);

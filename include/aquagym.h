@@ -13,7 +13,11 @@
  *     failure on the calling thread is returned by aqua_last_error().
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  All launches
  *     are asynchronous on that stream; only aqua_get_stats() and aqua_step_host() synchronise.
- *   - A handle is owned by one host thread at a time; distinct handles are independent.
+ *   - A handle is owned by one host thread at a time (calls on it are not thread safe); distinct
+ *     handles are independent.  At most 64 step launches of one handle may be in flight at once on
+ *     DIFFERENT streams (each takes one of 64 tile-counter sets, handed out round robin; launches on
+ *     one stream serialise and never collide); a CUDA graph that captured steps of a handle must not
+ *     be replayed concurrently with other steps of that handle.
  *   - There is no CPU fallback: without a CUDA device aqua_create() fails.
  *
  * State layout (structure of arrays, one "plane" per quantity, `ld` elements apart):
@@ -32,7 +36,7 @@
 extern "C" {
 #endif
 
-#define AQUAGYM_ABI_VERSION 1
+#define AQUAGYM_ABI_VERSION 2
 
 typedef struct aqua_env aqua_env;
 
@@ -85,7 +89,10 @@ enum {
     AQUA_STAT_REWARD_SUM = 5, /* sum of ALL step rewards, fixed point: value * 2^20 */
     AQUA_STAT_STEPS = 6,      /* env-steps executed */
     AQUA_STAT_BAD_ACTIONS = 7, /* discrete index outside {0,1,2} or thrust outside [0.2,0.5] */
-    AQUA_N_STATS = 8
+    AQUA_STAT_FORCED_RESETS = 8, /* reset rejection loops (aqua.py:102-115) cut off after 4096 tries: the
+                                    last try was accepted untested.  The reference would loop on; a
+                                    non-zero count means the map leaves (almost) no free space */
+    AQUA_N_STATS = 9
 };
 #define AQUA_REWARD_FIXED_POINT 1048576.0
 
@@ -116,6 +123,12 @@ typedef struct {
     void* state;
     int64_t ld;            /* plane stride in elements, multiple of AQUA_TILE, >= n_envs;
                               0 -> n_envs rounded up to AQUA_TILE */
+    int32_t keep_terminal; /* 1: the observation a finished env returned with done = True (aqua.py:213)
+                              is kept in 5 extra planes (aqua_state_view.terminal) -- under autoreset
+                              the state planes already hold the next episode's first observation */
+    int32_t _reserved;
+    void* terminal;        /* optional caller-owned DEVICE buffer for them, 5 * ld elements of the
+                              state's element type; NULL -> the library allocates it */
 } aqua_config;
 
 typedef struct {
@@ -124,6 +137,9 @@ typedef struct {
     int64_t n_envs;
     int32_t precision;
     int32_t _pad;
+    /* keep_terminal: x, y, theta, goal_x, goal_y of the last finished episode of each env, `ld` apart,
+     * same element type as the state; valid for env i once it has reported done; else NULL */
+    void* terminal[5];
 } aqua_state_view;
 
 /* ---- life cycle ---------------------------------------------------------------------- */
@@ -163,9 +179,24 @@ int aqua_step_ex(aqua_env* env, void* stream, const void* actions, int action_dt
 int aqua_random_actions(aqua_env* env, void* stream, uint64_t step_index, void* actions,
                         int action_dtype);
 
-/* `steps` env-steps fused in ONE launch with the synthetic random policy above (state stays in
- * registers; per-step reward/flags are not materialised, statistics are).  first_step_index is
- * the ACTION-stream index of the first step. */
+/* `steps` consecutive env.step() calls (aqua.py:135-213) in ONE launch: the state stays in registers
+ * between the steps, per env-step only the action is read and reward + flags are written.
+ *   actions : device [steps][row_stride] of `action_dtype` (continuous: float[steps][row_stride][2]);
+ *             row k holds the actions of step k, env i at column i
+ *   reward  : device float / double [steps][row_stride], or NULL
+ *   flags   : device uint8 [steps][row_stride], or NULL
+ *   row_stride : columns per row, >= n_envs and a multiple of 16 (columns >= n_envs are padding: never
+ *             read as actions that count, but the outputs' padding may be written)
+ * Identical, bit for bit, to `steps` calls of aqua_step on the rows.  With autoreset the next
+ * episode of a finished env starts in the same launch (its first observation is NOT materialised
+ * per step: the state planes hold the observation after the last step; keep_terminal keeps the
+ * terminal one).  The first call allocates 32 bytes per env for the pre-drawn next episodes (so it
+ * cannot be captured in a CUDA graph; later calls can). */
+int aqua_step_many(aqua_env* env, void* stream, int64_t steps, const void* actions, int action_dtype,
+                   void* reward, uint8_t* flags, int64_t row_stride);
+
+/* The same under the synthetic random policy above (aqua_random_actions keyed by first_step_index,
+ * first_step_index + 1, ...): no tape, no per-step outputs, the statistics count everything. */
 int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t first_step_index);
 
 /* Host-buffer step: the call a host-side gym user makes.  Copies `actions` (HOST, preferably

@@ -398,6 +398,173 @@ def test_rollout_kernel_equals_stepwise(name, precision, geometry):
     b.close()
 
 
+def _tape(env, K, first=0):
+    """K rows of the synthetic random policy as a step_many tape (rows padded to 16 columns)."""
+    torch = _torch()
+    n16 = (env.num_envs + 15) // 16 * 16
+    if env.continuous:
+        tape = torch.full((K, n16, 2), 0.35, dtype=torch.float32, device="cuda")
+        for k in range(K):
+            tape[k, :env.num_envs] = env.random_actions(first + k)
+    else:
+        tape = torch.full((K, n16), 2, dtype=torch.int32, device="cuda")
+        for k in range(K):
+            tape[k, :env.num_envs] = env.random_actions(first + k)
+    return tape
+
+
+@pytest.mark.parametrize("many_v", ["1", "2", "wide"])
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+@pytest.mark.parametrize("name,n,K", [("v1_discrete", 10003, 150), ("dense64_continuous", 4100, 120),
+                                      ("v1_discrete", 77, 40), ("v2_continuous", 1, 300)])
+def test_step_many_equals_stepwise(name, n, K, precision, many_v, monkeypatch):
+    """aqua_step_many (K steps in one launch, state in registers, next episodes from the stash) ==
+    K aqua_step launches on the same tape: rewards, flags, final state and statistics, bit for bit,
+    for every envs-per-thread instantiation and sizes that leave partial threads and padded rows."""
+    torch = _torch()
+    if many_v == "wide":
+        monkeypatch.delenv("AQUA_MANY_V", raising=False)
+    else:
+        monkeypatch.setenv("AQUA_MANY_V", many_v)
+    cfg = _cfg(name, seed=41, base=2000)
+    a = _make_gpu(cfg, n, precision, autoreset=True)
+    b = _make_gpu(cfg, n, precision, autoreset=True, geometry="wide" if many_v == "wide" else "auto")
+    a.reset()
+    b.reset()
+    tape = _tape(a, K)
+    rew = torch.zeros(K, tape.shape[1], dtype=a.dtype, device="cuda")
+    flg = torch.zeros(K, tape.shape[1], dtype=torch.uint8, device="cuda")
+    for k in range(K):
+        a.step_flags(tape[k, :n].contiguous())
+        rew[k, :n] = a.reward
+        flg[k, :n] = a.flags
+    # two launches (the second finds the stash of the first), the second with another tape dtype
+    K1 = K // 3
+    r1, f1 = b.step_many(tape[:K1].contiguous())
+    t2 = tape[K1:].contiguous() if b.continuous else tape[K1:].to(torch.uint8).contiguous()
+    r2, f2 = b.step_many(t2)
+    got_r, got_f = torch.cat([r1, r2])[:, :n], torch.cat([f1, f2])[:, :n]
+    assert torch.equal(got_f, flg[:, :n])
+    assert torch.equal(got_r, rew[:, :n])
+    assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy())
+    assert a.stats() == b.stats()
+    assert int((flg & 1).sum()) > 0 or n == 1
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_step_many_interleaved_with_single_steps(precision):
+    """Single-step launches advance episodes without touching the stash: the next step_many finds
+    stale records and redraws them.  Any interleaving gives the stepwise trajectory."""
+    torch = _torch()
+    cfg = _cfg("v1_discrete", seed=43, base=7)
+    n = 3000
+    a = _make_gpu(cfg, n, precision, autoreset=True)
+    b = _make_gpu(cfg, n, precision, autoreset=True)
+    a.reset()
+    b.reset()
+    t = 0
+    for block, K in enumerate([30, 25, 40, 1, 60]):
+        tape = _tape(a, K, first=t)
+        for k in range(K):
+            a.step_flags(tape[k, :n].contiguous())
+        if block % 2 == 0:
+            b.step_many(tape, reward_out=False, flags_out=False)
+        else:
+            for k in range(K):
+                b.step_flags(tape[k, :n].contiguous())
+        t += K
+        assert torch.equal(a.get_state(), b.get_state()), block
+    b.set_state(a.get_state())       # a restored checkpoint: episodes jump, the records are stale again
+    tape = _tape(a, 50, first=t)
+    for k in range(50):
+        a.step_flags(tape[k, :n].contiguous())
+    b.step_many(tape)
+    assert torch.equal(a.get_state(), b.get_state())
+    a.close()
+    b.close()
+
+
+def test_step_many_without_autoreset_and_argument_checks():
+    torch = _torch()
+    cfg = _cfg("v1_discrete", seed=44)
+    n = 2048
+    a = _make_gpu(cfg, n, "float64", autoreset=False)
+    b = _make_gpu(cfg, n, "float64", autoreset=False)
+    a.reset()
+    b.reset()
+    tape = _tape(a, 30)
+    for k in range(30):
+        a.step_flags(tape[k])
+    r, f = b.step_many(tape)
+    assert torch.equal(a.get_state(), b.get_state()) and torch.equal(f[-1], a.flags) and a.stats() == b.stats()
+    with pytest.raises(ValueError):
+        b.step_many(tape[:, :n - 16].contiguous())           # rows shorter than the slab
+    with pytest.raises(ValueError):
+        b.step_many(tape.float())
+    a.close()
+    b.close()
+
+
+@pytest.mark.parametrize("geometry", ["wide", "narrow"])
+@pytest.mark.parametrize("many", [False, True])
+def test_terminal_observation_is_kept(geometry, many):
+    """aqua.py:213 returns the terminal observation together with done = True; under auto-reset the
+    planes already show the next episode, keep_terminal keeps it (info['terminal_observation'])."""
+    torch = _torch()
+    from aquaticgymenv_b200 import AquaVecEnv
+    cfg = _cfg("v1_discrete", seed=45)
+    n, T = 5000, 60
+    env = AquaVecEnv(n, obstacles=cfg["table"], seed=45, precision="float64", geometry=geometry, keep_terminal=True)
+    ref = _make_oracle(cfg, n)
+    env.reset()
+    ref.reset()
+    want = np.zeros((n, 5))
+    seen = np.zeros(n, bool)
+    tape = _tape(env, T)
+    for t in range(T):
+        act = tape[t, :n].contiguous()
+        if not many:
+            _, _, done, info = env.step(act)
+            assert info["terminal_observation"].shape == (n, 5)
+        _, _, f_ref, _ = ref.step(act.cpu().numpy(), autoreset=False)
+        d = (f_ref & 1) != 0
+        want[d] = ref.obs()[d]
+        seen |= d
+        ref.reset(mask=d.astype(np.uint8))
+    if many:
+        env.step_many(tape)
+    got = env.terminal_obs.cpu().numpy()
+    assert seen.sum() > 100
+    assert np.abs(got[seen] - want[seen]).max() < 1e-6
+    assert np.array_equal(got[seen][:, 3:], want[seen][:, 3:])       # the finished episode's goal, exactly
+    assert np.array_equal(got[~seen], np.zeros((int((~seen).sum()), 5)))
+    env.close()
+
+
+def test_forced_reset_accepts_are_counted():
+    """A map without free space: the reference's rejection loops (aqua.py:102-115) would never end;
+    the kernels accept try 4095 untested and count it (AQUA_STAT_FORCED_RESETS), as the oracle does."""
+    torch = _torch()
+    from aquaticgymenv_b200 import AquaVecEnv
+    wall = np.array([[50.0, 50.0, 1.0, 300.0, 300.0]])
+    n = 96
+    env = AquaVecEnv(n, obstacles=wall, seed=3, precision="float32")
+    env.reset()
+    s = env.stats()
+    assert s["forced_resets"] == 2 * n, s                        # goal loop and boat loop of every env
+    env.step_flags(torch.zeros(n, dtype=torch.int32, device="cuda"))   # all collide; auto-reset forces again
+    s = env.stats()
+    assert s["collided"] == n and s["forced_resets"] == 4 * n, s
+    free = AquaVecEnv(n, obstacles=True, seed=3)
+    free.reset()
+    free.rollout_random(50)
+    assert free.stats()["forced_resets"] == 0
+    env.close()
+    free.close()
+
+
 @pytest.mark.parametrize("precision", ["float64", "float32"])
 def test_step_host_equals_device_step(precision):
     cfg = _cfg("v1_discrete", seed=8)

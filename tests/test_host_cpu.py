@@ -180,13 +180,13 @@ from aquaticgymenv_b200 import sharding
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=int(sys.argv[1]), world_size=2)
 rank = dist.get_rank()
 base, n = sharding.slab(1001, rank, 2)
-stats = torch.tensor([n, rank, 0, 1, 10 * n, -5 * (rank + 1), 7 * n, 0], dtype=torch.int64)
+stats = torch.tensor([n, rank, 0, 1, 10 * n, -5 * (rank + 1), 7 * n, 0, rank], dtype=torch.int64)
 sharding.all_reduce_stats(stats)
-assert stats.tolist() == [1001, 1, 0, 2, 10010, -15, 7007, 0], stats
-w = sharding.all_reduce_stats(torch.ones(8, dtype=torch.int64), async_op=True)
+assert stats.tolist() == [1001, 1, 0, 2, 10010, -15, 7007, 0, 1], stats
+w = sharding.all_reduce_stats(torch.ones(9, dtype=torch.int64), async_op=True)
 w.wait()
 try:
-    sharding.all_reduce_stats(torch.ones(8))
+    sharding.all_reduce_stats(torch.ones(9))
     raise SystemExit("float stats accepted")
 except ValueError:
     pass

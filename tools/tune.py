@@ -1,8 +1,8 @@
 #!/usr/bin/env python
 """Time the build variants of libaquagym.so (make -C aquaticgymenv_b200/csrc variant NAME=.. FLAGS=..)
-on ONE box, one subprocess per variant and workload: the bench headline (AquaEnv-v1, default
-obstacles) and the 64-obstacle stress map.  Boxes differ by a few per cent, so variants are only
-comparable within one call.  usage (GPU box): python tools/tune.py [envs] [steps]"""
+on ONE box, one subprocess per variant and workload (tools/config_rate.py: single-step launches,
+actions resident).  Boxes differ by a few per cent, so variants are only comparable within one
+call.  usage (GPU box): python tools/tune.py"""
 import glob
 import json
 import os
@@ -10,25 +10,21 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-envs = sys.argv[1] if len(sys.argv) > 1 else str(1 << 24)
-steps = sys.argv[2] if len(sys.argv) > 2 else "200"
+WORKLOADS = [("AquaEnv-v1", 1 << 24, "float32", "-", 200), ("AquaEnv-v1", 1 << 20, "float32", "-", 400),
+             ("AquaEnv-v0", 1 << 22, "float32", "dense64", 100), ("AquaContinuousEnv-v1", 1 << 24, "float32", "-", 100),
+             ("AquaEnv-v1", 1 << 23, "float64", "-", 100)]
 libs = sorted(glob.glob(os.path.join(ROOT, "aquaticgymenv_b200", "variants", "*.so")))
-for lib in libs:
-    env = dict(os.environ, AQUAGYM_LIB=lib)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--no-extras", "--e2e-steps", "0",
-                          "--steps", steps, "--warmup", "20", "--envs-per-gpu", envs],
-                         env=env, capture_output=True, text=True)
-    try:
-        j = json.loads(out.stdout.strip().splitlines()[-1])
-        print("%-34s %.4g env-steps/s  roofline %.3f  %.4f ms/step" % (
-            os.path.basename(lib), j["value"], j["roofline"]["frac"], j["ms_per_step"]), flush=True)
-    except Exception:
-        print(os.path.basename(lib), "FAILED", out.stdout[-300:], out.stderr[-600:], flush=True)
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config_rate.py"), "AquaEnv-v0", str(1 << 22),
-                          "float32", "dense64", "100"], env=env, capture_output=True, text=True)
-    try:
-        j = json.loads(out.stdout.strip().splitlines()[-1])
-        print("%-34s %.4g env-steps/s  dense64 map, 2^22 envs, %.1f us/step" % (
-            "", j["env_steps_per_s"], j["us_per_step"]), flush=True)
-    except Exception:
-        print(os.path.basename(lib), "dense64 FAILED", out.stdout[-300:], out.stderr[-600:], flush=True)
+for rep in range(2):  # twice, interleaved: shows the run-to-run spread on this box
+    for lib in libs:
+        env = dict(os.environ, AQUAGYM_LIB=lib)
+        row = []
+        for env_id, n, prec, tab, steps in WORKLOADS:
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "config_rate.py"), env_id, str(n), prec,
+                                  tab, str(steps)], env=env, capture_output=True, text=True)
+            try:
+                j = json.loads(out.stdout.strip().splitlines()[-1])
+                row.append("%.4g" % j["env_steps_per_s"])
+            except Exception:
+                row.append("FAILED " + out.stderr[-300:].replace("\n", " | "))
+        print("%-32s v1@2^24 %s | v1@2^20 %s | dense64@2^22 %s | cont@2^24 %s | f64@2^23 %s" % (
+            (os.path.basename(lib),) + tuple(row)), flush=True)
