@@ -55,38 +55,48 @@ class GreedyQPolicy(Policy):
 
 @torch.no_grad()
 def evaluate(env, policy, episodes, max_steps=None):
-    """Runs the policy until at least ``episodes`` episodes have finished (all envs in parallel,
-    auto-reset) and returns the statistics of dqn_test_plotter.py:23-35: success rate, mean and
-    standard deviation of the episode reward, mean length, and the termination counts."""
+    """The statistics of dqn_test_plotter.py:23-35 (success rate, mean and standard deviation of
+    the episode reward, mean length, termination counts) over at least ``episodes`` episodes, all
+    envs in parallel with auto-reset.
+
+    Which episodes count is fixed up front: the FIRST ``ceil(episodes / num_envs)`` episodes of
+    every env.  (Counting whichever episodes finish first would favour short ones -- early
+    collisions -- over long and timed-out ones.)  Every episode ends within 1001 steps
+    (aqua.py:203), so the default step limit lets every env complete its quota: no truncation.
+    With an explicit smaller ``max_steps`` the unfinished quota is reported in ``truncated``.
+    The loop does not wait for the device: counters live there and are read every 64 steps."""
     if not env.autoreset:
         raise ValueError("evaluate() needs an auto-resetting AquaVecEnv")
     env.reset()
-    n = env.num_envs
-    ret = torch.zeros(n, dtype=torch.float64, device=env.device)
-    rewards, lengths = [], []
-    counts = torch.zeros(3, dtype=torch.int64, device=env.device)  # collided, time, success
-    steps_in_ep = torch.zeros(n, dtype=torch.int64, device=env.device)
-    done_total, t = 0, 0
-    limit = max_steps if max_steps is not None else 1002 * (episodes // n + 2)
-    while done_total < episodes and t < limit:
-        obs = env.obs  # [N, 5] view: after auto-reset it already holds the next episode's first obs
-        flags = env.step_flags(policy.get_action(obs))
+    n, dev = env.num_envs, env.device
+    quota = -(-int(episodes) // n)
+    limit = max_steps if max_steps is not None else 1001 * quota + 1
+    ret = torch.zeros(n, dtype=torch.float64, device=dev)
+    length = torch.zeros(n, dtype=torch.int64, device=dev)
+    count = torch.zeros(n, dtype=torch.int64, device=dev)
+    acc = torch.zeros(7, dtype=torch.float64, device=dev)  # episodes, collided, time, success, sum r, sum r^2, sum len
+    t = 0
+    while t < limit:
+        flags = env.step_flags(policy.get_action(env.obs))  # env.obs: after auto-reset the next episode's first obs
         ret += env.reward.double()
-        steps_in_ep += 1
+        length += 1
         done = (flags & 1) != 0
-        if bool(done.any()):
-            rewards.append(ret[done].clone())
-            lengths.append(steps_in_ep[done].clone())
-            counts += torch.stack([((flags & 2) != 0).sum(), ((flags & 4) != 0).sum(), ((flags & 8) != 0).sum()])
-            done_total += int(done.sum())
-            ret[done] = 0.0
-            steps_in_ep[done] = 0
+        counted = done & (count < quota)
+        c = counted.double()
+        acc += torch.stack([c.sum(), (c * ((flags & 2) != 0)).sum(), (c * ((flags & 4) != 0)).sum(),
+                            (c * ((flags & 8) != 0)).sum(), (c * ret).sum(), (c * ret * ret).sum(),
+                            (c * length).sum()])
+        count += counted
+        ret.masked_fill_(done, 0.0)
+        length.masked_fill_(done, 0)
         t += 1
-    rewards = torch.cat(rewards) if rewards else torch.zeros(0, dtype=torch.float64)
-    lengths = torch.cat(lengths) if lengths else torch.zeros(0, dtype=torch.int64)
-    c = counts.tolist()
-    total = max(len(rewards), 1)
-    return {"episodes": len(rewards), "success_rate": c[2] / total, "collided": c[0], "time": c[1],
-            "success": c[2], "reward_mean": float(rewards.mean()) if len(rewards) else 0.0,
-            "reward_std": float(rewards.std()) if len(rewards) > 1 else 0.0,
-            "length_mean": float(lengths.double().mean()) if len(lengths) else 0.0, "steps": t}
+        if t % 64 == 0 and bool((count >= quota).all()):
+            break
+    k, coll, tim, succ, sr, sr2, sl = acc.tolist()
+    k = int(k)
+    mean = sr / max(k, 1)
+    var = max(sr2 - k * mean * mean, 0.0) / max(k - 1, 1)
+    return {"episodes": k, "success_rate": succ / max(k, 1), "collided": int(coll), "time": int(tim),
+            "success": int(succ), "reward_mean": mean, "reward_std": var ** 0.5,
+            "length_mean": sl / max(k, 1), "steps": t, "episodes_per_env": quota,
+            "truncated": int(n * quota - k)}

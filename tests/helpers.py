@@ -39,3 +39,46 @@ def table_to_reference_list(tab):
     for cx, cy, typ, a, b in np.asarray(tab, np.float64).reshape(-1, 5):
         out.append((np.array([cx, cy]), "c", a) if typ == 0.0 else (np.array([cx, cy]), "r", (a, b)))
     return out
+
+
+def reference_main():
+    """The reference's own caller code (`main/impl`, `main/testing`) made importable next to the
+    drop-in env: its root is baseline/_ref (shipped to the GPU box by __graft_entry__.build()) or
+    /root/reference.  `gym` resolves to the stand-in of oracle/gym_standin with the DROP-IN's six
+    ids registered, `gym_aqua` (imported by main/testing/__init__.py:2) to the drop-in package,
+    and `tensorflow` (imported by main/impl/dqn.py:9 at module level, absent here) to an empty
+    stub.  Returns (gym, root) or skips the calling test when no reference copy is around."""
+    import sys
+    import types
+
+    import pytest
+    root = None
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for cand in (os.path.join(here, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(cand, "main", "testing")):
+            root = cand
+            break
+    if root is None:
+        pytest.skip("no copy of the reference's main/ package (baseline/_ref is made by __graft_entry__.build())")
+    for p in (os.path.join(root, "main"), os.path.join(here, "oracle", "gym_standin")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    import gym
+    from aquaticgymenv_b200 import gym_aqua as dropin
+    sys.modules["gym_aqua"] = dropin
+    dropin._register_with_gym()
+    if "impl.dqn" not in sys.modules:  # import it once under the stub, then take the stub away again
+        stub = "tensorflow" not in sys.modules
+        if stub:
+            tf = types.ModuleType("tensorflow")
+            tf.config = types.SimpleNamespace(list_physical_devices=lambda kind=None: [],
+                                              experimental=types.SimpleNamespace(set_memory_growth=lambda *a: None))
+            tf.keras = types.SimpleNamespace()
+            sys.modules["tensorflow"] = tf
+        try:
+            import impl.dqn  # noqa: F401
+            import impl.utils  # noqa: F401
+        finally:
+            if stub:
+                del sys.modules["tensorflow"]
+    return gym, root

@@ -6,7 +6,8 @@ import os
 import numpy as np
 import torch
 
-from aquaticgymenv_b200 import dqn, policies, spaces, utils
+from aquaticgymenv_b200 import dqn, policies, spaces
+from tests.helpers import reference_main
 
 
 def _ref_optimal_action(state):
@@ -36,7 +37,11 @@ class _Env:
                                    dtype=np.float64)
 
 
-def test_state_normalizer_matches_reference_formula():
+def test_reference_normalizer_accepts_the_dropin_spaces():
+    """The reference's own AquaStateNormalizer (main/impl/utils.py:15-33, imported unmodified) on the
+    drop-in's observation space: the attributes it reads (.high, .low) behave like gym's."""
+    reference_main()
+    from impl import utils
     nz = utils.AquaStateNormalizer(_Env())
     s = np.array([50.0, 25.0, -np.pi / 2, 100.0, 0.0])
     out = nz(s)
@@ -127,3 +132,54 @@ def test_replay_buffer_ring():
     assert sorted(set(b.r.tolist())) == [1.0, 2.0, 3.0]           # the oldest rows were overwritten
     b.push(torch.ones(25, 5), torch.zeros(25), torch.arange(25.0), torch.zeros(25, 5), torch.zeros(25, dtype=torch.bool))
     assert b.size == 10 and sorted(b.r.tolist()) == list(map(float, range(15, 25)))
+
+
+def test_savedmodel_reader_and_policy_fixtures():
+    """The tensor-bundle reader (aquaticgymenv_b200/savedmodel.py) against the committed fixtures:
+    shapes of the 5 -> 64 -> 64 -> 3 network (dqn.py:301-314), and -- where the reference tree is at
+    hand -- the fixtures are exactly what the reader extracts from the shipped SavedModels."""
+    from aquaticgymenv_b200 import savedmodel
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    for name, model in (("no_obs", "example_no_obs/models/model-00030"), ("with_obs", "example_with_obs/models/model-00032")):
+        w = savedmodel.load_weights(os.path.join(golden, "policy_%s.npz" % name))
+        assert [k.shape for k, _ in w] == [(5, 64), (64, 64), (64, 3)] and [b.shape for _, b in w] == [(64,), (64,), (3,)]
+        assert all(k.dtype == np.float32 and np.isfinite(k).all() for k, _ in w)
+        net = savedmodel.load_q_network(os.path.join(golden, "policy_%s.npz" % name))
+        x = torch.rand(7, 5)
+        h = torch.relu(x @ torch.as_tensor(w[0][0]) + torch.as_tensor(w[0][1]))
+        h = torch.relu(h @ torch.as_tensor(w[1][0]) + torch.as_tensor(w[1][1]))
+        want = h @ torch.as_tensor(w[2][0]) + torch.as_tensor(w[2][1])
+        assert torch.allclose(net(x), want, atol=1e-5)
+        src = os.path.join("/root/reference/example_policies", model)
+        if os.path.isdir(src):
+            for (k0, b0), (k1, b1) in zip(w, savedmodel.load_weights(src)):
+                assert np.array_equal(k0, k1) and np.array_equal(b0, b1)
+
+
+def test_evaluate_counts_a_fixed_quota_of_episodes_per_env():
+    """evaluate() keeps the first ceil(episodes / N) episodes of EVERY env: an env with short
+    episodes must not crowd out one with long episodes."""
+    class TwoSpeedEnv(FakeVecEnv):
+        # even envs finish in 2 steps (collision), odd envs in 10 (success)
+        @property
+        def obs(self):
+            return self.observe()
+
+        def step_flags(self, action):
+            self.t += 1
+            period = torch.where(torch.arange(self.num_envs) % 2 == 0, 2, 10)
+            done = self.t >= period
+            odd = torch.arange(self.num_envs) % 2 == 1
+            self.flags = torch.where(done, torch.where(odd, 9, 3), 0).to(torch.uint8)
+            self.reward = torch.where(done, torch.where(odd, 10.0, -10.0), 0.0)
+            self.t[done] = 0
+            return self.flags
+
+    class Zero(policies.Policy):
+        def get_action(self, state):
+            return torch.zeros(state.shape[0], dtype=torch.int64)
+
+    res = policies.evaluate(TwoSpeedEnv(8), Zero(), episodes=40)
+    assert res["episodes"] == 40 and res["episodes_per_env"] == 5 and res["truncated"] == 0
+    assert res["success"] == 20 and res["collided"] == 20          # not 5x more short episodes than long ones
+    assert abs(res["length_mean"] - 6.0) < 1e-9 and abs(res["reward_mean"]) < 1e-9

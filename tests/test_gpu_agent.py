@@ -9,7 +9,10 @@ pytestmark = pytest.mark.gpu
 
 def test_observe_and_normaliser_match_reference_formula():
     import torch
-    from aquaticgymenv_b200 import gym_aqua, utils
+    from aquaticgymenv_b200 import gym_aqua
+    from tests.helpers import reference_main
+    reference_main()
+    from impl import utils                                        # the reference's own, unmodified
     for precision in ("float32", "float64"):
         env = gym_aqua.make("AquaEnv-v1", num_envs=5000, seed=3, precision=precision)
         env.reset()
@@ -96,3 +99,63 @@ def test_dqn_graph_mode_reproduces_the_eager_run():
     assert len(r0) > 1000 and r0 == r1 and s0 == s1
     assert all(torch.equal(a, b) for a, b in zip(w0, w1)) and all(torch.equal(a, b) for a, b in zip(t0, t1))
     assert torch.equal(b0, b1) and st0 == st1
+
+
+@pytest.mark.parametrize("name,env_id,published,published_reward", [
+    ("no_obs", "AquaEnv-v0", 0.938, 38.83), ("with_obs", "AquaEnv-v1", 0.667, 25.52)])
+def test_shipped_policies_reproduce_the_published_success_rates(name, env_id, published, published_reward):
+    """The reference's only published numbers (example_policies/test_results.pickle, report section
+    2.3): its two trained policies reach the goal in 93.8 % (no obstacles) and 66.7 % (default
+    obstacles) of 1000 test episodes, mean reward 38.83 / 25.52.  Their weights, read from the
+    SavedModels (tests/golden/policy_*.npz, tools/make_policy_fixtures.py), replayed greedily
+    (main/testing/test_dqn.py:14-22) on the GPU env must land on the same rates: an end-to-end check
+    of dynamics, observation, normaliser and termination logic.  The published rates carry
+    sqrt(p (1 - p) / 1000) = 0.8 % / 1.5 % of sampling error; 32,768 episodes here."""
+    import os
+    from aquaticgymenv_b200 import gym_aqua, policies, savedmodel
+    from tests.conftest import GOLDEN
+    env = gym_aqua.make(env_id, num_envs=8192, seed=11)
+    q = savedmodel.load_q_network(os.path.join(GOLDEN, "policy_%s.npz" % name), device=env.device)
+    res = policies.evaluate(env, policies.GreedyQPolicy(env, q), episodes=32768)
+    assert res["episodes"] == 32768 and res["truncated"] == 0
+    assert abs(res["success_rate"] - published) < 0.04, res
+    assert abs(res["reward_mean"] - published_reward) < 2.0, res
+    env.close()
+
+
+def test_reference_callers_run_on_the_dropin_env():
+    """The reference's own caller code, imported unmodified from its main/ package, against the
+    drop-in: Policy.test (main/testing/__init__.py:17-36) with OptimalAquaPolicy
+    (test_optimal.py:8-28) and RandomAquaPolicy (test_random.py:7-38), env made through
+    gym.make(...) as test_optimal.py:34 / test_random.py:44 do, and aqua_term_string
+    (main/impl/utils.py:4-12) on the returned info."""
+    from tests.helpers import reference_main
+    gym, _ = reference_main()
+    from impl.utils import aqua_term_string
+    from testing.test_optimal import OptimalAquaPolicy
+    from testing.test_random import RandomAquaPolicy
+    env = gym.make("AquaEnv-v0", obstacles=False)
+    assert type(env).__module__.startswith("aquaticgymenv_b200")
+    assert env.reward_goal() == 10 and env.reward_collision() == -10 and env.reward_max_steps() == -10  # aqua.py:86-88
+    wins = 0
+    for _ in range(12):
+        tot_rew, info, tot_steps = OptimalAquaPolicy().test(env, render=True)   # render(): no-op shim
+        msg = aqua_term_string(info, tot_rew, tot_steps)
+        assert sum(info.values()) == 1 and 1 <= tot_steps <= 1001
+        wins += info['Termination.success']
+        assert ("REACHED GOAL" in msg) == bool(info['Termination.success'])
+        if info['Termination.success']:
+            assert tot_rew > 10 - 1e-9          # +10 at the goal plus a positive shaping sum
+    assert wins >= 9                            # the bearing controller on an obstacle-free map
+    tot_rew, info, tot_steps = RandomAquaPolicy(strategy=0, env_action_space=env.action_space).test(env, render=False)
+    assert sum(info.values()) == 1
+    obs = env.reset()
+    o2, r, d, i = env.step(2)
+    assert abs(env.reward_step() - r) < 1e-9 or d                                 # aqua.py:89-90
+    # two envs made alike are independent (the reference is unseeded); an explicit seed replays
+    other = gym.make("AquaEnv-v0", obstacles=False)
+    assert not np.array_equal(other.reset(), env.reset())
+    a, b = gym.make("AquaEnv-v0", seed=5), gym.make("AquaEnv-v0", seed=5)
+    assert np.array_equal(a.reset(), b.reset()) and np.array_equal(a.step(0)[0], b.step(0)[0])
+    for e in (env, other, a, b):
+        e.close()
