@@ -124,6 +124,27 @@ __global__ void observe_kernel(const void* planes, int64_t ld, int64_t n, float*
     for (int k = 0; k < 5; ++k) out[i * 5 + k] = v[k];
 }
 
+// Host-buffer step: the goal planes of the caller's host observation only change for envs whose
+// episode changed.  Lists (env index, new goal) of the finished envs of a chunk: the position comes
+// from a device counter, the entry goes straight to the mapped pinned host list (a few thousand
+// 12-byte posted writes per million envs).  Entries beyond `cap` are dropped (the host then copies
+// the chunk's goal planes whole).
+template <typename R>
+__global__ void goal_updates_kernel(const void* planes, int64_t ld, const uint8_t* __restrict__ flags, int64_t lo,
+                                    int64_t len, uint32_t cap, unsigned int* __restrict__ d_count,
+                                    uint32_t* __restrict__ h_idx, R* __restrict__ h_goal) {
+    const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= len) return;
+    const int64_t i = lo + k;
+    if ((flags[i] & AQUA_FLAG_DONE) == 0) return;
+    const unsigned int pos = atomicAdd(d_count, 1u);
+    if (pos >= cap) return;
+    void* pl = const_cast<void*>(planes);
+    h_idx[pos] = (uint32_t)i;
+    h_goal[2 * (size_t)pos] = plane<R>(pl, ld, AQUA_PLANE_GOAL_X)[i];
+    h_goal[2 * (size_t)pos + 1] = plane<R>(pl, ld, AQUA_PLANE_GOAL_Y)[i];
+}
+
 // K3: fold the per-CTA slots (kSlotStats counters each) and the forced-reset counter into
 // int64[AQUA_N_STATS]
 __global__ void stats_reduce_kernel(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear) {
@@ -414,6 +435,19 @@ cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_
     const int threads = 256;
     if (precision == AQUA_F64) observe_kernel<double><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, out, normalized);
     else observe_kernel<float><<<blocks_for(n, threads), threads, 0, s>>>(planes, ld, n, out, normalized);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, const uint8_t* flags, int64_t lo,
+                                int64_t len, uint32_t cap, unsigned int* d_count, uint32_t* h_idx, void* h_goal,
+                                cudaStream_t s) {
+    const int threads = 256;
+    if (precision == AQUA_F64)
+        goal_updates_kernel<double><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len, cap, d_count, h_idx,
+                                                                                static_cast<double*>(h_goal));
+    else
+        goal_updates_kernel<float><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len, cap, d_count, h_idx,
+                                                                               static_cast<float*>(h_goal));
     return cudaGetLastError();
 }
 

@@ -29,12 +29,17 @@ template <typename Op> static cudaError_t many_dispatch(int precision, int v, in
     return cudaErrorInvalidValue;
 }
 
+// dynamic shared memory of a launch: culling grid, refill queues, stash records
+template <int V> static size_t many_smem(int threads, int use_grid) {
+    return cell_bytes(use_grid) + (size_t)(threads / 32) * sizeof(RefillQueue<V>) + (size_t)threads * V * 32;
+}
+
 struct ManyLaunchOp {
     const StepArgs& a;
     LaunchGeom g;
     cudaStream_t s;
     template <typename R, int V, int ACT, bool TAPE> cudaError_t run() const {
-        const size_t smem = cell_bytes(a.w.use_grid) + (size_t)(g.threads / 32) * sizeof(RefillQueue<V>);
+        const size_t smem = many_smem<V>(g.threads, a.w.use_grid);
         step_many_kernel<R, V, ACT, TAPE><<<g.blocks, g.threads, smem, s>>>(a);
         return cudaGetLastError();
     }
@@ -68,7 +73,7 @@ struct ManyOccupancyOp {
     int* out;
     template <typename R, int V, int ACT, bool TAPE> cudaError_t run() const {
         return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_many_kernel<R, V, ACT, TAPE>, threads,
-                                                             cell_bytes(use_grid) + (size_t)(threads / 32) * sizeof(RefillQueue<V>));
+                                                             many_smem<V>(threads, use_grid));
     }
 };
 cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int use_grid, int* blocks_per_sm) {

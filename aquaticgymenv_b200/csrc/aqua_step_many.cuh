@@ -11,9 +11,11 @@
 //
 // Auto-reset without a stall: the state of an episode's first step depends only on (env id,
 // episode index), never on how the previous episode ended, so it is drawn AHEAD OF TIME.  Every env
-// has a 32-byte "stash" record in global memory = the reset state of the episode after the current
-// one, tagged with that episode's index.  When an env finishes, its owner swaps the record in (two
-// 16-byte loads) and goes on with the next step; the env is queued for a refill of its record, and
+// has a 32-byte "stash" record = the reset state of the episode after the current one, tagged with
+// that episode's index: in global memory between launches, in shared memory while a launch runs
+// (read once before and written back once after the K steps, coalesced).  When an env finishes, its
+// owner swaps the record in (two 16-byte shared-memory loads) and goes on with the next step; the
+// env is queued for a refill of its record, and
 // the warp refills 32 queued envs at a time with one LANE per env (reset_env_lane: the reference's
 // rejection loops, aqua.py:100-126, all lanes busy).  A record whose tag is not the episode wanted
 // (first launch, or the single-step kernels advanced the episode meanwhile, or the env finished
@@ -77,11 +79,10 @@ template <typename R> __device__ __forceinline__ void stash_unpack(const uint4& 
 
 // Refills the records of queued envs, one lane per env, in passes of up to 32 from the tail while
 // at least `min_batch` are queued (kLanePass: full passes; 1: flush).  Warp-collective.
-// Not inlined: it runs once per 32 finished envs, and its registers (Philox4x32, the table tests)
-// should not count against the step loop's.
+// `s_rec`: the warp's records in shared memory, two uint4 per env, env warp_rel first.
 template <typename R, int V>
 __device__ __forceinline__ int refill_drain(const StepArgs& p, const ObstacleView<R>& tab, const RefillQueue<V>& rq,
-                                         int n, int min_batch) {
+                                            int n, int min_batch, uint4* s_rec, uint32_t warp_rel) {
     const int lane = (int)(threadIdx.x & 31u);
     const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
     __syncwarp();  // queue entries are visible to the whole warp
@@ -89,15 +90,14 @@ __device__ __forceinline__ int refill_drain(const StepArgs& p, const ObstacleVie
         const int take = min(n, 32);
         const int first = n - take;
         if (lane < take) {
-            const int64_t i = p.env_begin + (int64_t)rq.rel[first + lane];
+            const uint32_t rel = rq.rel[first + lane];
             const uint32_t ep = rq.ep[first + lane];
-            const uint32_t env_id = (uint32_t)(p.w.env_id_base + (uint64_t)i);
             const CoopResetResult rr = reset_env_lane<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
-                                                         p.w.reset_band, wf, env_id, ep, p.w.forced);
+                                                         p.w.reset_band, wf, p.env_id0 + rel, ep, p.w.forced);
             uint4 a, b;
             stash_pack(rr, ep, a, b);
-            __stcg(p.stash + 2 * i, a);  // L2 only: the owner lane reads it back with __ldcg
-            __stcg(p.stash + 2 * i + 1, b);
+            s_rec[2 * (rel - warp_rel)] = a;
+            s_rec[2 * (rel - warp_rel) + 1] = b;
         }
         n = first;
     }
@@ -127,9 +127,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
     __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ DriveSlot<R> s_drive[3];
-    // dynamic shared memory: the culling grid of a dense map, then one refill queue per warp
+    // dynamic shared memory: the culling grid of a dense map, one refill queue per warp, the stash
+    // records of the CTA's envs (2 x 16 bytes each)
     const ObstacleView<R> tab = stage_table<R>(s_box, s_stage, p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     RefillQueue<V>* const s_rq = reinterpret_cast<RefillQueue<V>*>(s_stage + cell_bytes(p.w.use_grid));
+    uint4* const s_rec_cta = reinterpret_cast<uint4*>(s_rq + (blockDim.x >> 5));
     if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
@@ -155,7 +157,9 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
         int n_q = 0;           // queued refills, warp-uniform
         int thr = kLanePass;   // queue length that triggers a refill pass; 1 = flush before the next step
         uint32_t pend = 0u;    // bit 0 of byte j: env j finished and waits for the refill of its record
-        const uint4* const my_stash = p.stash + 2 * (p.env_begin + (int64_t)rel);
+        uint4* const g_rec = p.stash + 2 * (p.env_begin + (int64_t)rel);             // this thread's, global
+        uint4* const s_rec = s_rec_cta + 2 * (size_t)(threadIdx.x & ~31u) * V;         // the warp's, shared
+        uint4* const my_rec = s_rec + 2 * (size_t)lane * V;                            // this thread's, shared
         const uint32_t env_id = p.env_id0 + rel;
 
         // ---- state in: the planes are padded to AQUA_TILE, full-width loads are in bounds ----
@@ -187,9 +191,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
 #pragma unroll
             for (int j = 0; j < V; ++j) {
                 want[j] = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
-                if (j < nvalid) {
-                    const uint32_t tag = __ldcg(reinterpret_cast<const uint32_t*>(my_stash + 2 * j + 1) + 3);
-                    word |= (tag != want[j] ? 1u : 0u) << (8 * j);
+                if (j < nvalid) {  // global -> shared, 32 V contiguous bytes per thread
+                    const uint4 r0 = __ldcg(g_rec + 2 * j), r1 = __ldcg(g_rec + 2 * j + 1);
+                    my_rec[2 * j] = r0;
+                    my_rec[2 * j + 1] = r1;
+                    word |= (r1.w != want[j] ? 1u : 0u) << (8 * j);
                 }
             }
             if (__any_sync(full, word != 0u)) {
@@ -206,16 +212,22 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
         const char* act_ptr_k = TAPE ? p.act0 + (size_t)rel * (kActBytes / V) : nullptr;
         char* rew_ptr_k = (p.reward != nullptr && has) ? p.rew0 + (size_t)rel * sizeof(R) : nullptr;
         uint8_t* flg_ptr_k = (p.flags != nullptr && has) ? p.flg0 + rel : nullptr;
-        ActVals<ACT, V> act_next;
+        // the actions of a step are loaded two steps ahead (a row of the tape comes from DRAM)
+        const size_t act_row = (size_t)p.row_stride * (kActBytes / V);
+        ActVals<ACT, V> act_next, act_next2;
 #pragma unroll
-        for (int j = 0; j < ActVals<ACT, V>::N; ++j) act_next.w[j] = 0u;
-        if (TAPE && has) act_next = fetch_actions<ACT, V>(act_ptr_k, V);
+        for (int j = 0; j < ActVals<ACT, V>::N; ++j) act_next.w[j] = act_next2.w[j] = 0u;
+        if (TAPE && has) {
+            act_next = fetch_actions<ACT, V>(act_ptr_k, V);
+            if (p.steps > 1) act_next2 = fetch_actions<ACT, V>(act_ptr_k + act_row, V);
+            act_ptr_k += 2 * act_row;  // the row of step k + 2
+        }
 
         for (int64_t k = 0;; ++k) {
             // ---- the ONE place where records are drawn: full passes while the launch runs; a flush
             // when an env waits for its record, and after the last step ----
             if (autoreset && (n_q >= thr || (k == p.steps && n_q > 0))) {
-                n_q = refill_drain<R, V>(p, tab, rq, n_q, k == p.steps ? 1 : thr);
+                n_q = refill_drain<R, V>(p, tab, rq, n_q, k == p.steps ? 1 : thr, s_rec, warp_rel);
                 thr = kLanePass;
             }
             if (__any_sync(full, pend != 0u)) {  // rare: the records of waiting envs are there now
@@ -225,7 +237,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
                     const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
                     next[j] = (want + 1u) & kEpisodeMask;
                     if ((pend >> (8 * j)) & 1u) {
-                        const uint4 r0 = __ldcg(my_stash + 2 * j), r1 = __ldcg(my_stash + 2 * j + 1);
+                        const uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
                         if (r1.w != want) __trap();  // the flush above drew exactly this record
                         stash_unpack<R>(r0, r1, e[j]);
                     }
@@ -242,9 +254,10 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
             for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
             if constexpr (TAPE) {
                 const ActVals<ACT, V> act = act_next;
-                if (k + 1 < p.steps && has) {
-                    act_ptr_k += (size_t)p.row_stride * (kActBytes / V);
-                    act_next = fetch_actions<ACT, V>(act_ptr_k, V);
+                act_next = act_next2;
+                if (k + 2 < p.steps && has) {
+                    act_next2 = fetch_actions<ACT, V>(act_ptr_k, V);
+                    act_ptr_k += act_row;
                 }
                 if constexpr (ACT == AQUA_ACT_F32X2) {
                     uint32_t bad = 0u;
@@ -351,7 +364,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
                     if ((fw >> (8 * j)) & 1u) {
                         st.length += e[j].tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
                         if (p.term != nullptr) store_terminal<R>(p, p.env_begin + rel + j, e[j]);  // aqua.py:213
-                        const uint4 r0 = __ldcg(my_stash + 2 * j), r1 = __ldcg(my_stash + 2 * j + 1);
+                        const uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
                         word |= 1u << (8 * j);
                         if (r1.w == want) {  // swap it in; its successor is drawn by a later pass
                             stash_unpack<R>(r0, r1, e[j]);
@@ -367,6 +380,16 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
                 n_q = refill_push<V>(rq, n_q, word, rel, ep);
                 if (__any_sync(full, pend != 0u)) thr = 1;
             }
+        }
+
+        // ---- stash out: every record is current (the flush after the last step drew what was pending) ----
+        if (autoreset) {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (j < nvalid) {
+                    __stcg(g_rec + 2 * j, my_rec[2 * j]);
+                    __stcg(g_rec + 2 * j + 1, my_rec[2 * j + 1]);
+                }
         }
 
         // ---- state out (full-width: the plane padding behind the last env is scratch) ----

@@ -139,6 +139,9 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
     // slots together hold kMaxThreads x 32), so thread t finds its actions act_off = t * (kActBytes -
     // kSlot) bytes from where a kSlot-byte slice would lie (modulo 2^32: the offset may be negative).
     const uint32_t act_off = AQUA_N_PLANES * kPitch + threadIdx.x * (uint32_t)(kActBytes - kSlot);
+    // the same for the time plane, whose elements are 4 bytes whatever the state's (double: 8-byte
+    // slices in 16-byte slots)
+    const uint32_t tw_off = AQUA_PLANE_TIME * kPitch + threadIdx.x * (uint32_t)(4 * V - kSlot);
     constexpr uint32_t kTxBytes = 32u * (7u * kSlot + 4u * V + kActBytes);
     uint32_t bar_cur = smem_u32(&s_bar[threadIdx.x >> 5][0]), bar_nxt = bar_cur + 8u;
     uint32_t par_cur = 0u, par_nxt = 0u;  // phase parity to wait for on each buffer
@@ -150,7 +153,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
             mbar_expect_tx(bar, kTxBytes);
 #pragma unroll
             for (int pl = 0; pl < 7; ++pl) bulk_g2s(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R), 32u * kSlot, bar);
-            bulk_g2s(s + AQUA_PLANE_TIME * kPitch, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4, 32u * 4u * V, bar);
+            bulk_g2s(s + tw_off, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4, 32u * 4u * V, bar);
             bulk_g2s(s + act_off, p.act0 + (size_t)i * (kActBytes / V), 32u * kActBytes, bar);
         }
     };
@@ -165,6 +168,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
             cp_async_s<kActPiece>(s + (AQUA_N_PLANES + q) * kPitch, p.act0 + (size_t)i * (kActBytes / V) + q * kActPiece);
     };
     const uint32_t bar_cur = 0u, bar_nxt = 0u;
+    constexpr uint32_t tw_off = AQUA_PLANE_TIME * kPitch;
 #endif
 
     ThreadStats st;
@@ -235,7 +239,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
             const Pack<R, V> vgy = lds_pack<R, V>(s_cur + AQUA_PLANE_GOAL_Y * kPitch);
             const Pack<R, V> vwx = lds_pack<R, V>(s_cur + AQUA_PLANE_WAVE_X * kPitch);
             const Pack<R, V> vwy = lds_pack<R, V>(s_cur + AQUA_PLANE_WAVE_Y * kPitch);
-            const Pack<uint32_t, V> vtw = lds_pack<uint32_t, V>(s_cur + AQUA_PLANE_TIME * kPitch);
+            const Pack<uint32_t, V> vtw = lds_pack<uint32_t, V>(s_cur + tw_off);
             uint32_t araw[kActWords];
 #pragma unroll
             for (int q = 0; q < kActPieces; ++q) {

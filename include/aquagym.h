@@ -208,6 +208,15 @@ int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t fir
 int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
                    void* reward, uint8_t* flags);
 
+/* Same; persistent_obs != 0 promises that `obs` is the very buffer of the previous aqua_step_host(_ex)
+ * call on this handle and has not been written since.  Its goal planes (2 of the 5) are then brought
+ * up to date by a list of (env, goal) entries for the envs whose episode changed instead of being
+ * copied whole: 17 instead of 25 bytes per env-step come back over PCIe (float32).  Any other call that
+ * changes the state (aqua_step, aqua_step_many, aqua_reset, aqua_set_state, ...) makes the next host
+ * step send the planes whole again, whatever the promise. */
+int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
+                      void* reward, uint8_t* flags, int persistent_obs);
+
 /* Observation rows for a policy network: device float[N][5] = (x, y, angle, goal_x, goal_y)
  * gathered from the state planes (aqua.py:126,213).  normalized != 0 applies the scaling of
  * AquaStateNormalizer.__call__ (main/impl/utils.py:23-27): obs / (high - low), angle + 0.5, so

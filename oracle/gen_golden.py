@@ -14,6 +14,7 @@ Injection points:
     `np.random.uniform` (aqua.py:188) returns the wave increment of the step.
 
     python oracle/gen_golden.py            # (re)writes tests/golden/*.npz
+    python oracle/gen_golden.py wide       # only the 256-env x 1000-step fixtures (wide_*.npz)
 """
 import contextlib
 import io
@@ -228,6 +229,58 @@ def gen_rollout(name, env_id, kwargs, policy, n_envs, steps, seed, env_id_base, 
         int(((flags & 8) > 0).sum()), margin.min()))
 
 
+# ---------------------------------------------------------------- wide rollout fixtures
+def gen_wide(name, env_id, kwargs, n_envs, steps, seed, env_id_base, table, every=25):
+    """256 envs x 1000 steps per layout in compact form: the flags of EVERY
+    step, every reset (state, episode, samples drawn), and full snapshots (state after auto-reset,
+    reward) every `every` steps.  A free-running rollout (own Philox draws, own resets) can only
+    reproduce these if every step and every reset in between was right.  Actions: the synthetic
+    random policy (draws.action_discrete / action_continuous keyed by (seed, env id, step)); the
+    discrete ones are stored, the continuous ones are regenerated by the tests."""
+    continuous = "Continuous" in env_id
+    envs = [RefEnv(env_id, kwargs, seed, env_id_base + i) for i in range(n_envs)]
+    T, N = steps, n_envs
+    actions = np.zeros((T, N), np.int8)
+    flags = np.zeros((T, N), np.uint8)
+    snaps = np.zeros((T // every, 8, N), np.float64)   # x, y, theta, wx, wy, time, episode, reward of that step
+    init_state = np.zeros((9, N), np.float64)
+    resets = []
+    min_margin = np.inf
+    for i, e in enumerate(envs):
+        obs, n = e.reset()
+        init_state[:, i] = [obs[0], obs[1], obs[2], e.env._wave_speed[0], e.env._wave_speed[1],
+                            obs[3], obs[4], e.env.time, e.episode]
+    for t in range(T):
+        for i, e in enumerate(envs):
+            if continuous:
+                a = draws.action_continuous(seed, e.gid, t)
+                act = np.array(a, dtype=np.float64)
+            else:
+                a = int(draws.action_discrete(seed, e.gid, t))
+                actions[t, i] = a
+                act = a
+            obs, r, f, _ = e.step(act)
+            flags[t, i] = f
+            min_margin = min(min_margin, e.margin())
+            if f & 1:
+                obs, n = e.reset()
+                resets.append([t, i, obs[0], obs[1], obs[2], e.env._wave_speed[0], e.env._wave_speed[1],
+                               obs[3], obs[4], e.episode, n])
+            if (t + 1) % every == 0:
+                snaps[t // every, :, i] = [obs[0], obs[1], obs[2], e.env._wave_speed[0], e.env._wave_speed[1],
+                                           e.env.time, e.episode, r]
+    goals = np.array([[e.env._goal_state[0], e.env._goal_state[1]] for e in envs]).T
+    np.savez_compressed(
+        os.path.join(OUT, name + ".npz"),
+        kind="wide", env_id=env_id, continuous=continuous, policy="random", every=every,
+        waves=bool(kwargs.get("waves", True)), random_boat=True, random_goal=True, seed=np.uint64(seed),
+        env_id_base=np.uint64(env_id_base), table=table, init_state=init_state, actions=actions, flags=flags,
+        snaps=snaps, final_goal=goals, resets=np.array(resets, dtype=np.float64), min_margin=min_margin)
+    print("%-34s T=%d N=%d done=%d collided=%d time=%d success=%d min-margin=%.3g" % (
+        name, T, N, int((flags & 1).sum()), int(((flags & 2) > 0).sum()), int(((flags & 4) > 0).sum()),
+        int(((flags & 8) > 0).sum()), min_margin), flush=True)
+
+
 # ---------------------------------------------------------------- single-step known-answer fixtures
 def gen_single_step(name, env_id, kwargs, n_cases, seed, table):
     """Random (and deliberately edgy) states pushed straight into the reference's
@@ -307,6 +360,24 @@ def gen_single_step(name, env_id, kwargs, n_cases, seed, table):
         int(((flags & 4) > 0).sum()), int(((flags & 8) > 0).sum())))
 
 
+def main_wide():
+    dense = dense64_table()
+    dense_list = table_to_reference_list(dense)
+    none = np.zeros((0, 5))
+    v1 = reference_list_to_table(gym.make("AquaEnv-v1").obstacles)
+    v2 = reference_list_to_table(gym.make("AquaEnv-v2").obstacles)
+    W = gen_wide
+    W("wide_v0_discrete", "AquaEnv-v0", {}, 256, 1000, 31, 0, none)
+    W("wide_v1_discrete", "AquaEnv-v1", {}, 256, 1000, 32, 70000, v1)
+    W("wide_v2_discrete", "AquaEnv-v2", {}, 256, 1000, 33, 0, v2)
+    W("wide_dense64_discrete", "AquaEnv-v0", {"obstacles": dense_list}, 256, 1000, 34, 1 << 20, dense)
+    W("wide_v0_continuous", "AquaContinuousEnv-v0", {}, 256, 1000, 35, 0, none)
+    W("wide_v1_continuous", "AquaContinuousEnv-v1", {}, 256, 1000, 36, 5, v1)
+    W("wide_v2_continuous", "AquaContinuousEnv-v2", {}, 256, 1000, 37, 0, v2)
+    W("wide_dense64_continuous", "AquaContinuousEnv-v0", {"obstacles": dense_list}, 256, 1000, 38, 3000000000, dense)
+    W("wide_v1_discrete_nowaves", "AquaEnv-v1", {"waves": False}, 256, 1000, 39, 0, v1)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     dense = dense64_table()
@@ -347,4 +418,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "wide":   # only the 256-env fixtures (about 10 minutes)
+        main_wide()
+    else:
+        main()
+        main_wide()

@@ -82,3 +82,22 @@ def reference_main():
             if stub:
                 del sys.modules["tensorflow"]
     return gym, root
+
+
+def wide_actions(g, t0, t1):
+    """Rows t0..t1-1 of the golden's action tape: stored for the discrete envs, regenerated from the
+    ACTION stream (oracle draws, pinned in test_philox.py) for the continuous ones."""
+    if not bool(g["continuous"]):
+        return np.ascontiguousarray(g["actions"][t0:t1]).astype(np.int32)
+    import ctypes as C
+    from oracle import aqua_oracle as ao
+    L = ao.lib()
+    n = g["flags"].shape[1]
+    out = np.zeros((t1 - t0, n, 2), np.float32)
+    buf = (C.c_float * 2)()
+    seed, base = int(g["seed"]), int(g["env_id_base"])
+    for t in range(t0, t1):
+        for i in range(n):
+            L.aqo_draw_action_continuous(seed, base + i, t, buf)
+            out[t - t0, i] = (buf[0], buf[1])
+    return out

@@ -15,7 +15,7 @@ import pytest
 
 from tests.conftest import GOLDEN
 from tests.helpers import (SCALE_POS, SCALE_REWARD, SCALE_WAVE, err_angle, err_scaled, golden_names,
-                           load_golden)
+                           load_golden, wide_actions)
 
 pytestmark = pytest.mark.gpu
 
@@ -131,6 +131,81 @@ def test_rollout_golden_f64_free_running(name, geometry):
             for i in np.nonzero(done)[0]:
                 r = resets[(t, int(i))]
                 assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 8], i], r[2:10]), (name, t, i)
+    env.close()
+
+
+# ------------------------------------------------------------------ 256-env golden rollouts
+@pytest.mark.parametrize("mode", ["single", "many"])
+@pytest.mark.parametrize("name", golden_names(GOLDEN, "wide_"))
+def test_wide_golden_f64_free_running(name, mode):
+    """256 envs x 1000 steps per layout, recorded by executing the reference (oracle/gen_golden.py
+    wide): the float64 env, free-running with in-kernel auto-reset, must give the reference's flags at
+    EVERY step, its state at every 25th (after hundreds of resets in between) and its final goals.
+    Once with one launch per step, once with 25 steps per launch (aqua_step_many)."""
+    torch = _torch()
+    g = load_golden(GOLDEN, name)
+    T, n = g["flags"].shape
+    every = int(g["every"])
+    env = _make_gpu(g, n, "float64", autoreset=True)
+    env.reset()
+    assert np.array_equal(env.get_state().cpu().numpy(), g["init_state"])
+    cont = bool(g["continuous"])
+    n16 = (n + 15) // 16 * 16
+    for c in range(T // every):
+        acts = wide_actions(g, c * every, (c + 1) * every)
+        if mode == "many":
+            shape = (every, n16, 2) if cont else (every, n16)
+            tape = torch.zeros(shape, dtype=torch.float32 if cont else torch.int32, device="cuda")
+            tape[:, :n] = torch.as_tensor(acts).cuda()
+            rew, flg = env.step_many(tape)
+            flags, reward = flg[:, :n].cpu().numpy(), rew[-1, :n].cpu().numpy()
+        else:
+            rows = []
+            for k in range(every):
+                rows.append(env.step_flags(_actions_tensor(acts[k], cont)).cpu().numpy().copy())
+            flags, reward = np.stack(rows), env.reward.cpu().numpy()
+        assert np.array_equal(flags, g["flags"][c * every:(c + 1) * every]), (name, c)
+        st = env.get_state().cpu().numpy()
+        snap = g["snaps"][c]
+        e = max(err_scaled(st[0], snap[0], SCALE_POS).max(), err_scaled(st[1], snap[1], SCALE_POS).max(),
+                err_angle(st[2], snap[2]).max(), err_scaled(st[3:5], snap[3:5], SCALE_WAVE).max(),
+                err_scaled(reward, snap[7], SCALE_REWARD).max())
+        assert e < 1e-7, (name, c, e)
+        assert np.array_equal(st[7], snap[5]) and np.array_equal(st[8], snap[6])      # time, episode
+    assert np.array_equal(env.get_state().cpu().numpy()[5:7], g["final_goal"])
+    assert env.stats()["episodes"] == int((g["flags"] & 1).sum())
+    env.close()
+
+
+@pytest.mark.parametrize("name", golden_names(GOLDEN, "wide_"))
+def test_wide_golden_f32(name):
+    """The float32 layout (what the throughput numbers run) on the same 256,000 env-steps per layout,
+    free-running: an env whose flags ever differ from the reference's has left the recorded
+    trajectory (a decision within float32 round-off of a rim; measured rate ~1e-7 per env-step) and
+    is dropped from the comparison -- at most 3 of the 256 may; all the others match the reference's
+    flags at every step and its state within 1e-5 (scaled) at every 25th."""
+    g = load_golden(GOLDEN, name)
+    T, n = g["flags"].shape
+    every = int(g["every"])
+    env = _make_gpu(g, n, "float32", autoreset=True)
+    env.reset()
+    cont = bool(g["continuous"])
+    alive = np.ones(n, bool)
+    for c in range(T // every):
+        acts = wide_actions(g, c * every, (c + 1) * every)
+        rows = []
+        for k in range(every):
+            rows.append(env.step_flags(_actions_tensor(acts[k], cont)).cpu().numpy().copy())
+        alive &= ~(np.stack(rows) != g["flags"][c * every:(c + 1) * every]).any(axis=0)
+        st = env.get_state().cpu().numpy()
+        snap = g["snaps"][c]
+        e = max(err_scaled(st[0, alive], snap[0, alive], SCALE_POS).max(),
+                err_scaled(st[1, alive], snap[1, alive], SCALE_POS).max(),
+                err_angle(st[2, alive], snap[2, alive]).max(),
+                err_scaled(st[3:5, alive], snap[3:5, alive], SCALE_WAVE).max())
+        assert e < TOL_F32, (name, c, e)
+        assert np.array_equal(st[7, alive], snap[5, alive]) and np.array_equal(st[8, alive], snap[6, alive])
+    assert (~alive).sum() <= 3, (~alive).sum()
     env.close()
 
 
@@ -567,23 +642,56 @@ def test_forced_reset_accepts_are_counted():
 
 @pytest.mark.parametrize("precision", ["float64", "float32"])
 def test_step_host_equals_device_step(precision):
+    """aqua_step_host(_ex): host buffers in and out, several pipeline chunks.  With the same obs
+    buffer call after call the goal planes arrive as per-env updates; a fresh buffer, or a device
+    step in between, gets them whole again.  Every variant must equal the device step."""
     cfg = _cfg("v1_discrete", seed=8)
     n = 300000  # several pipeline chunks
     a = _make_gpu(cfg, n, precision, autoreset=True)
     b = _make_gpu(cfg, n, precision, autoreset=True)
     a.reset()
     b.reset()
-    for t in range(5):
+    np_real = np.float64 if precision == "float64" else np.float32
+    obs_h = np.full((5, n), -1.0, np_real)      # garbage goals: the first call must overwrite them
+    rew_h, fl_h = np.empty(n, np_real), np.empty(n, np.uint8)
+    for t in range(40):
         act = a.random_actions(t)
         flags = a.step_flags(act).cpu().numpy()
-        obs_h, rew_h, fl_h = b.step_host(act.cpu().numpy())
-        assert np.array_equal(fl_h, flags)
-        assert np.array_equal(rew_h, a.reward.cpu().numpy())
-        assert np.array_equal(obs_h, a.obs_planes.cpu().numpy())
+        if t == 20:      # another fresh buffer
+            obs_h = np.full((5, n), -2.0, np_real)
+        if t == 30:      # a device-side step between two host steps: the host copy of the goals is stale
+            b.step_flags(act)
+            obs_h[3:] = -3.0
+            assert np.array_equal(b.flags.cpu().numpy(), flags)
+            continue
+        b.step_host(act.cpu().numpy(), obs_h, rew_h, fl_h)
+        assert np.array_equal(fl_h, flags), t
+        assert np.array_equal(rew_h, a.reward.cpu().numpy()), t
+        assert np.array_equal(obs_h, a.obs_planes.cpu().numpy()), t
+    o2, r2, f2 = b.step_host(a.random_actions(40).cpu().numpy())     # buffers made by the wrapper
+    a.step_flags(a.random_actions(40))
+    assert np.array_equal(o2, a.obs_planes.cpu().numpy())
     assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy())
     assert a.stats() == b.stats()
     a.close()
     b.close()
+
+
+def test_step_host_goal_update_list_overflow():
+    """More finished envs than the update list holds (a quarter of a chunk): the chunk's goal planes
+    are copied whole.  A map without free space finishes every env at every step."""
+    from aquaticgymenv_b200 import AquaVecEnv
+    wall = np.array([[50.0, 50.0, 1.0, 300.0, 300.0]])
+    n = 70000
+    env = AquaVecEnv(n, obstacles=wall, seed=3, precision="float32")
+    env.reset()
+    obs_h = np.zeros((5, n), np.float32)
+    act = np.zeros(n, np.int32)
+    for t in range(3):
+        _, _, fl = env.step_host(act, obs_h)
+        assert (fl & 1).all()
+        assert np.array_equal(obs_h, env.obs_planes.cpu().numpy()), t
+    env.close()
 
 
 @pytest.mark.parametrize("precision", ["float32", "float64"])

@@ -7,7 +7,7 @@ import pytest
 
 from oracle import aqua_oracle as ao
 from tests.helpers import (SCALE_POS, SCALE_REWARD, SCALE_WAVE, err_angle, err_scaled,
-                           golden_names, load_golden)
+                           golden_names, load_golden, wide_actions)
 from tests.conftest import GOLDEN
 
 TOL = 1e-7  # scaled-relative; flags must be identical
@@ -81,3 +81,26 @@ def test_rollout_golden_free_running(name):
                 r = resets[(t, int(i))]
                 assert np.array_equal(st[[0, 1, 2, 3, 4, 5, 6, 8], i], r[2:10]), (name, t, i)
     assert worst < TOL
+
+
+@pytest.mark.parametrize("name", golden_names(GOLDEN, "wide_"))
+def test_oracle_reproduces_wide_golden(name):
+    """256 envs x 1000 steps per layout recorded from the executed reference: the C oracle,
+    free-running with its own draws and resets, gives the same flags at every step, the same state
+    at every 25th step (to the reference's own round-off) and the same final goals."""
+    g = load_golden(GOLDEN, name)
+    T, n = g["flags"].shape
+    every = int(g["every"])
+    ref = ao.OracleVecEnv(n, continuous=bool(g["continuous"]), obstacles=np.asarray(g["table"], np.float64),
+                          waves=bool(g["waves"]), seed=int(g["seed"]), env_id_base=int(g["env_id_base"]))
+    ref.reset()
+    assert np.array_equal(ref.get_state(), g["init_state"])
+    for c in range(T // every):
+        acts = wide_actions(g, c * every, (c + 1) * every)
+        for k in range(every):
+            _, r, f, _ = ref.step(acts[k], autoreset=True)
+            assert np.array_equal(f, g["flags"][c * every + k]), (name, c, k)
+        st, snap = ref.get_state(), g["snaps"][c]
+        assert np.abs(st[:5] - snap[:5]).max() < 1e-7 and np.abs(r - snap[7]).max() < 1e-7
+        assert np.array_equal(st[7], snap[5]) and np.array_equal(st[8], snap[6])
+    assert np.array_equal(ref.get_state()[5:7], g["final_goal"])
