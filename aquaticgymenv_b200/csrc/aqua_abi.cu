@@ -46,7 +46,7 @@ struct DeviceGuard {
 
 constexpr int kHostStreams = 4;       // host-step pipeline depth
 constexpr int kTileCounters = 64;     // launches that may be in flight at once on one handle
-constexpr int64_t kHostChunkMin = 64 * 1024;
+constexpr int64_t kHostChunkMin = 256 * 1024;  // a copy below ~1 MB costs more to issue than to move
 constexpr int kHostMaxChunks = kHostStreams * 4;
 constexpr int kGoalCapDiv = 4;        // goal-update list: room for a quarter of a chunk's envs
 

@@ -185,25 +185,32 @@ constexpr double kRectR2 = 6.25;  // (boat or goal radius 2.5)^2, aqua.py:72,75
 template <typename R, int V>
 __device__ __forceinline__ void obstacle_clearance(const ObstacleView<R>& tab, int k_circ, int k_obst,
                                                    const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
-    // one obstacle per iteration (the body already carries V independent chains): with runtime
-    // counts an unrolled loop spends more on its remainder handling than it saves
+    // Four circles / two rectangles per trip.  The counts are runtime values; a trip that runs past the
+    // last entry tests that entry again instead (clamped index): min() is idempotent, so the result
+    // is the same bit for bit, and no remainder loop is needed.
 #pragma unroll 1
-    for (int k = 0; k < k_circ; ++k) {
-        const ObstacleBox<R> o = tab.box[k];
+    for (int k = 0; k < k_circ; k += 4) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const R ddx = px[j] - o.cx, ddy = py[j] - o.cy;
-            clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, -o.a)));
+        for (int u = 0; u < 4; ++u) {
+            const ObstacleBox<R> o = tab.box[min(k + u, k_circ - 1)];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const R ddx = px[j] - o.cx, ddy = py[j] - o.cy;
+                clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, -o.a)));
+            }
         }
     }
 #pragma unroll 1
-    for (int k = k_circ; k < k_obst; ++k) {
-        const ObstacleBox<R> o = tab.box[k];
+    for (int k = k_circ; k < k_obst; k += 2) {
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            const R ddx = fmax(fabs(px[j] - o.cx) - o.a, R(0));
-            const R ddy = fmax(fabs(py[j] - o.cy) - o.b, R(0));
-            clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, R(-kRectR2))));
+        for (int u = 0; u < 2; ++u) {
+            const ObstacleBox<R> o = tab.box[min(k + u, k_obst - 1)];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const R ddx = fmax(fabs(px[j] - o.cx) - o.a, R(0));
+                const R ddy = fmax(fabs(py[j] - o.cy) - o.b, R(0));
+                clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, R(-kRectR2))));
+            }
         }
     }
 }

@@ -214,8 +214,15 @@ struct StreamLaunchOp {
     template <typename R, int V, int ACT> cudaError_t run() const {
         if constexpr (stream_supported<ACT, V>()) {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(a.w.use_grid);
-            if (a.w.waves) step_stream_kernel<R, V, ACT, true><<<g.blocks, g.threads, smem, s>>>(a);
-            else step_stream_kernel<R, V, ACT, false><<<g.blocks, g.threads, smem, s>>>(a);
+            // bulk (TMA) staging for launches large enough to stream from HBM, per-lane cp.async below
+            const bool tma = AQUA_TMA == 2 || (AQUA_TMA == 1 && (int64_t)a.n_stream >= kTmaMinEnvs);
+            if (a.w.waves) {
+                if (tma) step_stream_kernel<R, V, ACT, true, true><<<g.blocks, g.threads, smem, s>>>(a);
+                else step_stream_kernel<R, V, ACT, true, false><<<g.blocks, g.threads, smem, s>>>(a);
+            } else {
+                if (tma) step_stream_kernel<R, V, ACT, false, true><<<g.blocks, g.threads, smem, s>>>(a);
+                else step_stream_kernel<R, V, ACT, false, false><<<g.blocks, g.threads, smem, s>>>(a);
+            }
             return cudaGetLastError();
         } else {
             return cudaErrorNotSupported;
@@ -323,18 +330,16 @@ struct StepConfigureOp {  // dynamic shared memory above the 48 KiB default limi
             e = cudaFuncSetAttribute(step_kernel<R, V, ACT, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                      cudaSharedmemCarveoutMaxShared);
         if constexpr (stream_supported<ACT, V>()) {
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, false>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, false>,
-                                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e == cudaSuccess)
-                e = cudaFuncSetAttribute(step_stream_kernel<R, V, ACT, true>,
-                                         cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            auto opt_in = [&](auto* kernel) {
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDyn);
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared);
+            };
+            opt_in(step_stream_kernel<R, V, ACT, false, false>);
+            opt_in(step_stream_kernel<R, V, ACT, true, false>);
+            opt_in(step_stream_kernel<R, V, ACT, false, true>);
+            opt_in(step_stream_kernel<R, V, ACT, true, true>);
         }
         return e;
     }
@@ -368,9 +373,9 @@ struct StreamOccupancyOp {
         if constexpr (stream_supported<ACT, V>()) {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(use_grid);
             if (waves)
-                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true>,
+                return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, true, true>,
                                                                      threads, smem);
-            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false>,
+            return cudaOccupancyMaxActiveBlocksPerMultiprocessor(out, step_stream_kernel<R, V, ACT, false, true>,
                                                                  threads, smem);
         } else {
             *out = 0;

@@ -39,9 +39,17 @@ struct ManyLaunchOp {
     LaunchGeom g;
     cudaStream_t s;
     template <typename R, int V, int ACT, bool TAPE> cudaError_t run() const {
-        const size_t smem = many_smem<V>(g.threads, a.w.use_grid);
-        step_many_kernel<R, V, ACT, TAPE><<<g.blocks, g.threads, smem, s>>>(a);
-        return cudaGetLastError();
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)g.blocks);
+        cfg.blockDim = dim3((unsigned)g.threads);
+        cfg.dynamicSmemBytes = many_smem<V>(g.threads, a.w.use_grid);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[1];  // consecutive launches overlap their launch latency and prologue
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, step_many_kernel<R, V, ACT, TAPE>, a);
     }
 };
 

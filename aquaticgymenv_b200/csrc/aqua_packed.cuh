@@ -126,30 +126,37 @@ __device__ __forceinline__ void obstacle_clearance_pairs(const ObstacleView<floa
         x2[q] = f2(px[2 * q], px[2 * q + 1]);
         y2[q] = f2(py[2 * q], py[2 * q + 1]);
     }
+    // four circles / two rectangles per trip, clamped index (see obstacle_clearance)
 #pragma unroll 1
-    for (int k = 0; k < k_circ; ++k) {
-        const ObstacleBox<float> o = tab.box[k];
+    for (int k = 0; k < k_circ; k += 4) {
 #pragma unroll
-        for (int q = 0; q < V / 2; ++q) {
-            const F2 ddx = x2[q] - f2(o.cx), ddy = y2[q] - f2(o.cy);
-            const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(-o.a)));
-            clr[2 * q] = fminf(clr[2 * q], lo(d));
-            clr[2 * q + 1] = fminf(clr[2 * q + 1], hi(d));
+        for (int u = 0; u < 4; ++u) {
+            const ObstacleBox<float> o = tab.box[min(k + u, k_circ - 1)];
+#pragma unroll
+            for (int q = 0; q < V / 2; ++q) {
+                const F2 ddx = x2[q] - f2(o.cx), ddy = y2[q] - f2(o.cy);
+                const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(-o.a)));
+                clr[2 * q] = fminf(clr[2 * q], lo(d));
+                clr[2 * q + 1] = fminf(clr[2 * q + 1], hi(d));
+            }
         }
     }
 #pragma unroll 1
-    for (int k = k_circ; k < k_obst; ++k) {
-        const ObstacleBox<float> o = tab.box[k];
+    for (int k = k_circ; k < k_obst; k += 2) {
 #pragma unroll
-        for (int q = 0; q < V / 2; ++q) {
-            const F2 ex = x2[q] - f2(o.cx), ey = y2[q] - f2(o.cy);
-            const F2 ux = f2(fabsf(lo(ex)), fabsf(hi(ex))) - f2(o.a);
-            const F2 uy = f2(fabsf(lo(ey)), fabsf(hi(ey))) - f2(o.b);
-            const F2 ddx = f2(fmaxf(lo(ux), 0.f), fmaxf(hi(ux), 0.f));
-            const F2 ddy = f2(fmaxf(lo(uy), 0.f), fmaxf(hi(uy), 0.f));
-            const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(-(float)kRectR2)));
-            clr[2 * q] = fminf(clr[2 * q], lo(d));
-            clr[2 * q + 1] = fminf(clr[2 * q + 1], hi(d));
+        for (int u = 0; u < 2; ++u) {
+            const ObstacleBox<float> o = tab.box[min(k + u, k_obst - 1)];
+#pragma unroll
+            for (int q = 0; q < V / 2; ++q) {
+                const F2 ex = x2[q] - f2(o.cx), ey = y2[q] - f2(o.cy);
+                const F2 ux = f2(fabsf(lo(ex)), fabsf(hi(ex))) - f2(o.a);
+                const F2 uy = f2(fabsf(lo(ey)), fabsf(hi(ey))) - f2(o.b);
+                const F2 ddx = f2(fmaxf(lo(ux), 0.f), fmaxf(hi(ux), 0.f));
+                const F2 ddy = f2(fmaxf(lo(uy), 0.f), fmaxf(hi(uy), 0.f));
+                const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(-(float)kRectR2)));
+                clr[2 * q] = fminf(clr[2 * q], lo(d));
+                clr[2 * q + 1] = fminf(clr[2 * q + 1], hi(d));
+            }
         }
     }
 }

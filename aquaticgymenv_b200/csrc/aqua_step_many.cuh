@@ -19,17 +19,20 @@
 // the warp refills 32 queued envs at a time with one LANE per env (reset_env_lane: the reference's
 // rejection loops, aqua.py:100-126, all lanes busy).  A record whose tag is not the episode wanted
 // (first launch, or the single-step kernels advanced the episode meanwhile, or the env finished
-// again before its refill ran) is refilled on the spot, so the stash is a cache: results do not
-// depend on it (test_step_many_equals_stepwise).
+// again before its refill ran) is queued for a refill like any other and drawn at once when its env
+// finishes first, so the stash is a cache: results do not depend on it
+// (test_step_many_equals_stepwise, test_step_many_interleaved_with_single_steps).
 #pragma once
 
 #include "aqua_kernel_util.cuh"
 
 namespace aqua {
 
-// register budget: 128-thread CTAs, 6 / 4 / 3 of them per SM at 1 / 2 / 4 envs per thread
+// register budget: 128-thread CTAs, 4 / 4 / 3 of them per SM at 1 / 2 / 4 envs per thread (128 / 128 / 168
+// registers: the narrow instantiations serve slabs too small to fill more warps anyway, and a tighter
+// cap makes the compiler recompute the loop's constants in every step)
 #ifndef AQUA_MANY_MINB
-#define AQUA_MANY_MINB(V) ((V) == 1 ? 6 : ((V) == 2 ? 4 : 3))
+#define AQUA_MANY_MINB(V) ((V) == 4 ? 3 : 4)
 #endif
 constexpr int kManyThreads = 128;  // launch bound; the launcher picks 32 .. 128 threads per CTA
 constexpr uint32_t kStashEmpty = 0xffffffffu;
@@ -138,6 +141,12 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
         s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
     }
     __syncthreads();
+    // Programmatic dependent launch (the launcher sets the attribute): this CTA may have been made
+    // resident, and have staged the obstacle table above, while the previous kernel of the stream was
+    // still running; it waits here, before its first read of the state, until that kernel has
+    // completed and flushed.  The trigger right behind lets the next launch do the same.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     const unsigned full = 0xffffffffu;
     const uint32_t n = p.n_stream;
@@ -184,8 +193,10 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
             }
         }
 
-        // ---- stash check: every env needs the record of its next episode; missing ones are queued and
-        // drawn by the flush that opens the step loop ----
+        // ---- stash in: global -> shared.  A record that is not the one of the env's next episode (never
+        // drawn; or the previous launch ended before its refill ran; or a single-step launch moved the
+        // episode on) is queued like any other refill: it is drawn by the next full pass, or at once
+        // when its env finishes first ----
         if (autoreset) {
             uint32_t want[V], word = 0u;
 #pragma unroll
@@ -198,10 +209,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
                     word |= (r1.w != want[j] ? 1u : 0u) << (8 * j);
                 }
             }
-            if (__any_sync(full, word != 0u)) {
-                n_q = refill_push<V>(rq, n_q, word, rel, want);
-                thr = 1;
-            }
+            if (__any_sync(full, word != 0u)) n_q = refill_push<V>(rq, n_q, word, rel, want);
         }
 
         // ---- per-step I/O: row k of the tape is row_stride envs after row k - 1.  A thread without
@@ -224,10 +232,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
         }
 
         for (int64_t k = 0;; ++k) {
-            // ---- the ONE place where records are drawn: full passes while the launch runs; a flush
-            // when an env waits for its record, and after the last step ----
-            if (autoreset && (n_q >= thr || (k == p.steps && n_q > 0))) {
-                n_q = refill_drain<R, V>(p, tab, rq, n_q, k == p.steps ? 1 : thr, s_rec, warp_rel);
+            // ---- the ONE place where records are drawn: in full passes, all lanes busy; a flush only
+            // when an env waits for its record.  What is still queued after the last step stays
+            // undrawn (its record keeps a stale tag): the next launch queues it again ----
+            if (autoreset && n_q >= thr) {
+                n_q = refill_drain<R, V>(p, tab, rq, n_q, thr, s_rec, warp_rel);
                 thr = kLanePass;
             }
             if (__any_sync(full, pend != 0u)) {  // rare: the records of waiting envs are there now
@@ -382,7 +391,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
             }
         }
 
-        // ---- stash out: every record is current (the flush after the last step drew what was pending) ----
+        // ---- stash out (records whose refill is still queued go back with their old tag) ----
         if (autoreset) {
 #pragma unroll
             for (int j = 0; j < V; ++j)

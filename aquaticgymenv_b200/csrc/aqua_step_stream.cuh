@@ -61,11 +61,15 @@ template <int ACT, int V> constexpr bool stream_supported() {
 // reports its bytes to the warp's mbarrier for that buffer.  Nine copy instructions per tile
 // instead of 9 x 32 per-lane LDGSTS and their address arithmetic; the lanes wait on the mbarrier
 // phase instead of a cp.async group.  A buffer is refilled after __syncwarp(): every lane has read
-// its slices by then.  AQUA_TMA=0 keeps the per-lane cp.async form (profiles/r02_tma_ab.txt).
+// its slices by then.  Both forms are compiled (template parameter TMA).  Measured on one box
+// (profiles/r02a_variants_ab.txt): equal at 2^24 envs (7.89e10 both), per-lane cp.async 4.6 % faster at
+// 2^20 envs, where a warp sees three tiles and the start-up of the copy pipeline counts.  launch_step
+// therefore takes the bulk form from kTmaMinEnvs envs per launch (AQUA_TMA: 0 never, 1 by size, 2 always).
 // ------------------------------------------------------------------------------------------
 #ifndef AQUA_TMA
 #define AQUA_TMA 1
 #endif
+constexpr int64_t kTmaMinEnvs = (int64_t)1 << 22;
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
@@ -93,30 +97,28 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  : "memory");
 }
 
-template <typename R, int V, int ACT, bool WAVES>
+template <typename R, int V, int ACT, bool WAVES, bool TMA>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 step_stream_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     __shared__ DriveSlot<R> s_drive[3];
-#if AQUA_TMA
-    __shared__ __align__(8) unsigned long long s_bar[kMaxThreads / 32][2];  // [warp][buffer]
-#endif
+    __shared__ __align__(8) unsigned long long s_bar[TMA ? kMaxThreads / 32 : 1][2];  // [warp][buffer]
     const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
         s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
     }
-#if AQUA_TMA
-    if ((threadIdx.x & 31u) == 0u) {
-        mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][0]), 1u);
-        mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][1]), 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if constexpr (TMA) {
+        if ((threadIdx.x & 31u) == 0u) {
+            mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][0]), 1u);
+            mbar_init(smem_u32(&s_bar[threadIdx.x >> 5][1]), 1u);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        }
     }
-#endif
     __syncthreads();
 
     constexpr int kSlot = stage_slot<R, V>(), kPitch = stage_pitch<R, V>();
@@ -133,43 +135,38 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
     const uint32_t lane_off = (threadIdx.x & 31u) * V;
     uint32_t s_cur = smem_u32(s_stage) + threadIdx.x * kSlot, s_nxt = s_cur + kStage;
 
-#if AQUA_TMA
-    // The warp's stretch of a staging slot is the 32 slices of its lanes, kSlot bytes each.  The
-    // actions are one linear run of kActBytes per thread instead (4 to 32 bytes: the two action
-    // slots together hold kMaxThreads x 32), so thread t finds its actions act_off = t * (kActBytes -
-    // kSlot) bytes from where a kSlot-byte slice would lie (modulo 2^32: the offset may be negative).
-    const uint32_t act_off = AQUA_N_PLANES * kPitch + threadIdx.x * (uint32_t)(kActBytes - kSlot);
-    // the same for the time plane, whose elements are 4 bytes whatever the state's (double: 8-byte
-    // slices in 16-byte slots)
-    const uint32_t tw_off = AQUA_PLANE_TIME * kPitch + threadIdx.x * (uint32_t)(4 * V - kSlot);
+    // The warp's stretch of a staging slot is the 32 slices of its lanes, kSlot bytes each.  With bulk
+    // copies the actions are one linear run of kActBytes per thread instead (4 to 32 bytes: the two
+    // action slots together hold kMaxThreads x 32), so thread t finds its actions act_off = t *
+    // (kActBytes - kSlot) bytes from where a kSlot-byte slice would lie (modulo 2^32: the offset may be
+    // negative); the same for the time plane, whose elements are 4 bytes whatever the state's.
+    const uint32_t act_off = AQUA_N_PLANES * kPitch + (TMA ? threadIdx.x * (uint32_t)(kActBytes - kSlot) : 0u);
+    const uint32_t tw_off = AQUA_PLANE_TIME * kPitch + (TMA ? threadIdx.x * (uint32_t)(4 * V - kSlot) : 0u);
     constexpr uint32_t kTxBytes = 32u * (7u * kSlot + 4u * V + kActBytes);
-    uint32_t bar_cur = smem_u32(&s_bar[threadIdx.x >> 5][0]), bar_nxt = bar_cur + 8u;
+    uint32_t bar_cur = smem_u32(&s_bar[TMA ? threadIdx.x >> 5 : 0][0]), bar_nxt = bar_cur + 8u;
     uint32_t par_cur = 0u, par_nxt = 0u;  // phase parity to wait for on each buffer
     const bool issuer = (threadIdx.x & 31u) == 0u;
     // stages the tile whose first env (for this lane) is i into the buffer s (this lane's slice base)
     auto prefetch = [&](uint32_t s, uint32_t bar, uint32_t i) {
-        if (issuer) {  // lane 0: i is the tile's first env, s the warp's stretch
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' reads of s precede the refill
-            mbar_expect_tx(bar, kTxBytes);
+        if constexpr (TMA) {
+            if (issuer) {  // lane 0: i is the tile's first env, s the warp's stretch
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the lanes' reads of s precede the refill
+                mbar_expect_tx(bar, kTxBytes);
 #pragma unroll
-            for (int pl = 0; pl < 7; ++pl) bulk_g2s(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R), 32u * kSlot, bar);
-            bulk_g2s(s + tw_off, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4, 32u * 4u * V, bar);
-            bulk_g2s(s + act_off, p.act0 + (size_t)i * (kActBytes / V), 32u * kActBytes, bar);
+                for (int pl = 0; pl < 7; ++pl) bulk_g2s(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R), 32u * kSlot, bar);
+                bulk_g2s(s + tw_off, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4, 32u * 4u * V, bar);
+                bulk_g2s(s + act_off, p.act0 + (size_t)i * (kActBytes / V), 32u * kActBytes, bar);
+            }
+        } else {  // the 8 plane slices + actions of the V envs starting at (relative) env index i, per lane
+#pragma unroll
+            for (int pl = 0; pl < 7; ++pl) cp_async_s<kSlot>(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R));
+            cp_async_s<4 * V>(s + AQUA_PLANE_TIME * kPitch, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4);
+#pragma unroll
+            for (int q = 0; q < kActPieces; ++q)
+                cp_async_s<kActPiece>(s + (AQUA_N_PLANES + q) * kPitch, p.act0 + (size_t)i * (kActBytes / V) + q * kActPiece);
+            cp_async_commit();
         }
     };
-#else
-    // the 8 plane slices + actions of the V envs starting at (relative) env index i
-    auto prefetch = [&](uint32_t s, uint32_t, uint32_t i) {
-#pragma unroll
-        for (int pl = 0; pl < 7; ++pl) cp_async_s<kSlot>(s + pl * kPitch, p.pl0[pl] + (size_t)i * sizeof(R));
-        cp_async_s<4 * V>(s + AQUA_PLANE_TIME * kPitch, p.pl0[AQUA_PLANE_TIME] + (size_t)i * 4);
-#pragma unroll
-        for (int q = 0; q < kActPieces; ++q)
-            cp_async_s<kActPiece>(s + (AQUA_N_PLANES + q) * kPitch, p.act0 + (size_t)i * (kActBytes / V) + q * kActPiece);
-    };
-    const uint32_t bar_cur = 0u, bar_nxt = 0u;
-    constexpr uint32_t tw_off = AQUA_PLANE_TIME * kPitch;
-#endif
 
     ThreadStats st;
     WarpResetQueue<V>& wq = s_wq[threadIdx.x >> 5];
@@ -210,14 +207,11 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
     uint32_t claim_old = 0u;      // issued during the previous tile: the successor of i3
     bool old_valid = i3 < n;      // warp-uniform
     if (old_valid) claim_tile(claim_old);
+    // (the per-lane form commits one cp.async group per tile slot, empty when there is no tile)
     if (i < n) prefetch(s_cur, bar_cur, i);
-#if !AQUA_TMA
-    cp_async_commit();
-#endif
+    else if (!TMA) cp_async_commit();
     if (i1 < n) prefetch(s_nxt, bar_nxt, i1);
-#if !AQUA_TMA
-    cp_async_commit();
-#endif
+    else if (!TMA) cp_async_commit();
     for (;;) {
         const bool live = i < n;  // warp-uniform: n is a multiple of 32 V
         uint32_t fw = 0u;
@@ -225,12 +219,12 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
         uint32_t claim_new = 0u;
         const uint32_t i_done = i;
         if (live) {
-#if AQUA_TMA
-            mbar_wait(bar_cur, par_cur);  // this tile's nine copies have landed
-            par_cur ^= 1u;
-#else
-            cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
-#endif
+            if constexpr (TMA) {
+                mbar_wait(bar_cur, par_cur);  // this tile's nine copies have landed
+                par_cur ^= 1u;
+            } else {
+                cp_async_wait<1>();  // everything but the newest group has landed: this tile's slices
+            }
 
             const Pack<R, V> vx = lds_pack<R, V>(s_cur + AQUA_PLANE_X * kPitch);
             const Pack<R, V> vy = lds_pack<R, V>(s_cur + AQUA_PLANE_Y * kPitch);
@@ -244,22 +238,14 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
 #pragma unroll
             for (int q = 0; q < kActPieces; ++q) {
                 uint32_t w[kActPiece / 4];
-#if AQUA_TMA
-                lds_words<kActPiece>(s_cur + act_off + q * kActPiece, w);
-#else
-                lds_words<kActPiece>(s_cur + (AQUA_N_PLANES + q) * kPitch, w);
-#endif
+                lds_words<kActPiece>(s_cur + (TMA ? act_off + q * kActPiece : (AQUA_N_PLANES + q) * kPitch), w);
 #pragma unroll
                 for (int k = 0; k < kActPiece / 4; ++k) araw[q * (kActPiece / 4) + k] = w[k];
             }
             const ActVals<ACT, V> act = actions_from_raw<ACT, V, kActWords>(araw);
-#if AQUA_TMA
-            __syncwarp();  // every lane has read its slices: the buffer may be refilled
-#endif
+            if constexpr (TMA) __syncwarp();  // every lane has read its slices: the buffer may be refilled
             if (i2 < n) prefetch(s_cur, bar_cur, i2);  // refill the buffer just read
-#if !AQUA_TMA
-            cp_async_commit();
-#endif
+            else if (!TMA) cp_async_commit();
             const bool new_valid = old_valid && i3 < n;  // the pool had tiles left at the last look
             if (new_valid) claim_tile(claim_new);
 
@@ -345,13 +331,13 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
             const uint32_t t = s_cur;
             s_cur = s_nxt;
             s_nxt = t;
-#if AQUA_TMA
-            const uint32_t tb = bar_cur, tp = par_cur;
-            bar_cur = bar_nxt;
-            par_cur = par_nxt;
-            bar_nxt = tb;
-            par_nxt = tp;
-#endif
+            if constexpr (TMA) {
+                const uint32_t tb = bar_cur, tp = par_cur;
+                bar_cur = bar_nxt;
+                par_cur = par_nxt;
+                bar_nxt = tb;
+                par_nxt = tp;
+            }
             // the claim of the previous tile is consumed here, after this tile's stores
             asm volatile("" : "+r"(claim_old) : : "memory");
             const uint32_t i4 =
@@ -370,9 +356,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
         }
         if (!live) break;
     }
-#if !AQUA_TMA
-    cp_async_wait<0>();
-#endif
+    if constexpr (!TMA) cp_async_wait<0>();
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
     if (threadIdx.x == 0) {  // the last CTA to finish rearms the tile counter for the next launch
