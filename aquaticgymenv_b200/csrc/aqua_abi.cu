@@ -46,9 +46,7 @@ struct DeviceGuard {
 
 constexpr int kHostStreams = 4;       // host-step pipeline depth
 constexpr int kTileCounters = 64;     // launches that may be in flight at once on one handle
-constexpr int64_t kHostChunkMin = 256 * 1024;  // a copy below ~1 MB costs more to issue than to move
-constexpr int kHostMaxChunks = kHostStreams * 4;
-constexpr int kGoalCapDiv = 4;        // goal-update list: room for a quarter of a chunk's envs
+constexpr int64_t kHostChunkMin = 256 * 1024;  // every copy costs several us to issue and start: few, large ones
 
 size_t elem_size(int precision) { return precision == AQUA_F64 ? 8 : 4; }
 
@@ -96,10 +94,6 @@ struct aqua_env {
     // goal planes of the caller's host observation buffer: sent whole once, then only the entries of
     // envs whose episode changed (see aqua_step_host)
     const void* host_obs_last = nullptr;  // the obs buffer whose goal planes are current, or NULL
-    unsigned int* d_goal_count = nullptr;  // per chunk
-    unsigned int* h_goal_count = nullptr;  // pinned
-    uint32_t* h_goal_idx = nullptr;        // pinned, mapped: ld / 4 entries
-    void* h_goal_val = nullptr;            // pinned, mapped: 2 values per entry
 };
 
 namespace {
@@ -160,11 +154,6 @@ int ensure_host_pipeline(aqua_env* env, int action_dtype) {
         AQ_CUDA(cudaEventCreateWithFlags(&env->ev_in, cudaEventDisableTiming));
         AQ_CUDA(cudaMalloc(&env->d_reward, (size_t)env->ld * elem_size(env->cfg.precision)));
         AQ_CUDA(cudaMalloc(&env->d_flags, (size_t)env->ld));
-        AQ_CUDA(cudaMalloc(&env->d_goal_count, sizeof(unsigned int) * kHostMaxChunks));
-        AQ_CUDA(cudaHostAlloc(&env->h_goal_count, sizeof(unsigned int) * kHostMaxChunks, cudaHostAllocDefault));
-        const size_t cap = (size_t)env->ld / kGoalCapDiv + kHostMaxChunks;
-        AQ_CUDA(cudaHostAlloc(&env->h_goal_idx, cap * sizeof(uint32_t), cudaHostAllocMapped));
-        AQ_CUDA(cudaHostAlloc(&env->h_goal_val, cap * 2 * elem_size(env->cfg.precision), cudaHostAllocMapped));
         env->host_ready = true;
     }
     const size_t need = (size_t)env->ld * action_bytes(action_dtype);
@@ -355,10 +344,6 @@ int aqua_destroy(aqua_env* env) {
     if (env->d_actions) keep(cudaFree(env->d_actions));
     if (env->d_reward) keep(cudaFree(env->d_reward));
     if (env->d_flags) keep(cudaFree(env->d_flags));
-    if (env->d_goal_count) keep(cudaFree(env->d_goal_count));
-    if (env->h_goal_count) keep(cudaFreeHost(env->h_goal_count));
-    if (env->h_goal_idx) keep(cudaFreeHost(env->h_goal_idx));
-    if (env->h_goal_val) keep(cudaFreeHost(env->h_goal_val));
     if (env->owns_state && env->state) keep(cudaFree(env->state));
     if (env->d_tab) keep(cudaFree(env->d_tab));
     if (env->d_tab64) keep(cudaFree(env->d_tab64));
@@ -562,15 +547,18 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
     }
     // The goal planes (2 of the 5 observation planes) only change for envs whose episode changed:
     // they travel whole when the caller's obs buffer is new to this handle (or anything else touched
-    // the state in between) and as a list of (env, goal) updates otherwise -- 17 instead of 25 bytes
-    // per env-step come back over PCIe.
-    const bool sparse_goals = persistent_obs != 0 && obs != nullptr && env->host_obs_last == obs;
-    const int n_obs_planes = sparse_goals ? 3 : 5;
-    if (sparse_goals) AQ_TRY(cudaMemsetAsync(env->d_goal_count, 0, sizeof(unsigned int) * kHostMaxChunks, env->hs[0]));
-    if (sparse_goals) {  // the other streams' kernels count into it: after the memset
-        AQ_TRY(cudaEventRecord(env->ev_in, env->hs[0]));
-        for (int i = 1; i < kHostStreams; ++i) AQ_TRY(cudaStreamWaitEvent(env->hs[i], env->ev_in, 0));
+    // the state in between, or the buffer is pageable) and as per-env writes of a small kernel straight
+    // into the caller's pinned planes otherwise -- 17 instead of 25 bytes per env-step come back.
+    char* obs_dev = nullptr;  // the caller's obs buffer as the device sees it (pinned memory only)
+    if (persistent_obs != 0 && obs != nullptr && env->host_obs_last == obs) {
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, obs) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
+            obs_dev = static_cast<char*>(pa.devicePointer);
+        else
+            cudaGetLastError();  // pageable memory: not an error, just no shortcut
     }
+    const bool sparse_goals = obs_dev != nullptr;
+    const int n_obs_planes = sparse_goals ? 3 : 5;
     int c = 0;
     for (int64_t lo = 0; lo < n && err == cudaSuccess; lo += chunk, ++c) {
         const int64_t hi = std::min(n, lo + chunk);
@@ -600,44 +588,15 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
                                        static_cast<char*>(env->state) +
                                            ((size_t)kObsPlanes[k] * (size_t)env->ld + (size_t)lo) * es,
                                        (size_t)len * es, cudaMemcpyDeviceToHost, s));
-        if (sparse_goals) {
-            const size_t off = (size_t)lo / kGoalCapDiv + (size_t)c;  // this chunk's stretch of the lists
+        if (sparse_goals)
             AQ_TRY(aqua::launch_goal_updates(env->cfg.precision, env->state, env->ld, env->d_flags, lo, len,
-                                             (uint32_t)(len / kGoalCapDiv), env->d_goal_count + c, env->h_goal_idx + off,
-                                             static_cast<char*>(env->h_goal_val) + off * 2 * es, s));
-            AQ_TRY(cudaMemcpyAsync(env->h_goal_count + c, env->d_goal_count + c, sizeof(unsigned int),
-                                   cudaMemcpyDeviceToHost, s));
-        }
+                                             obs_dev + (size_t)3 * (size_t)n * es, obs_dev + (size_t)4 * (size_t)n * es, s));
     }
     for (int i = 0; i < kHostStreams; ++i) {
         const cudaError_t e = cudaStreamSynchronize(env->hs[i]);
         if (err == cudaSuccess && e != cudaSuccess) {
             err = e;
             what = "cudaStreamSynchronize(host pipeline)";
-        }
-    }
-    if (sparse_goals && err == cudaSuccess) {  // apply the updates (a few per cent of the envs)
-        char* const gx = static_cast<char*>(obs) + (size_t)3 * (size_t)n * es;
-        char* const gy = static_cast<char*>(obs) + (size_t)4 * (size_t)n * es;
-        int cc = 0;
-        for (int64_t lo = 0; lo < n && err == cudaSuccess; lo += chunk, ++cc) {
-            const int64_t len = std::min(n, lo + chunk) - lo;
-            const size_t off = (size_t)lo / kGoalCapDiv + (size_t)cc;
-            const unsigned int cnt = env->h_goal_count[cc];
-            if (cnt > (unsigned int)(len / kGoalCapDiv)) {  // more than the list holds: this chunk's planes whole
-                for (int k = 3; k < 5; ++k)
-                    AQ_TRY(cudaMemcpy(static_cast<char*>(obs) + ((size_t)k * (size_t)n + (size_t)lo) * es,
-                                      static_cast<char*>(env->state) +
-                                          ((size_t)kObsPlanes[k] * (size_t)env->ld + (size_t)lo) * es,
-                                      (size_t)len * es, cudaMemcpyDeviceToHost));
-                continue;
-            }
-            const uint32_t* idx = env->h_goal_idx + off;
-            const char* val = static_cast<const char*>(env->h_goal_val) + off * 2 * es;
-            for (unsigned int k = 0; k < cnt; ++k) {
-                memcpy(gx + (size_t)idx[k] * es, val + (size_t)(2 * k) * es, es);
-                memcpy(gy + (size_t)idx[k] * es, val + (size_t)(2 * k + 1) * es, es);
-            }
         }
     }
 #undef AQ_TRY

@@ -125,24 +125,19 @@ __global__ void observe_kernel(const void* planes, int64_t ld, int64_t n, float*
 }
 
 // Host-buffer step: the goal planes of the caller's host observation only change for envs whose
-// episode changed.  Lists (env index, new goal) of the finished envs of a chunk: the position comes
-// from a device counter, the entry goes straight to the mapped pinned host list (a few thousand
-// 12-byte posted writes per million envs).  Entries beyond `cap` are dropped (the host then copies
-// the chunk's goal planes whole).
+// episode changed.  When that buffer is pinned (hence mapped into the device's address space) the
+// new goals of the finished envs of a chunk go straight to it: a few thousand 4-byte posted writes
+// over PCIe per million envs instead of two whole planes.
 template <typename R>
 __global__ void goal_updates_kernel(const void* planes, int64_t ld, const uint8_t* __restrict__ flags, int64_t lo,
-                                    int64_t len, uint32_t cap, unsigned int* __restrict__ d_count,
-                                    uint32_t* __restrict__ h_idx, R* __restrict__ h_goal) {
+                                    int64_t len, R* __restrict__ h_gx, R* __restrict__ h_gy) {
     const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= len) return;
     const int64_t i = lo + k;
     if ((flags[i] & AQUA_FLAG_DONE) == 0) return;
-    const unsigned int pos = atomicAdd(d_count, 1u);
-    if (pos >= cap) return;
     void* pl = const_cast<void*>(planes);
-    h_idx[pos] = (uint32_t)i;
-    h_goal[2 * (size_t)pos] = plane<R>(pl, ld, AQUA_PLANE_GOAL_X)[i];
-    h_goal[2 * (size_t)pos + 1] = plane<R>(pl, ld, AQUA_PLANE_GOAL_Y)[i];
+    h_gx[i] = plane<R>(pl, ld, AQUA_PLANE_GOAL_X)[i];
+    h_gy[i] = plane<R>(pl, ld, AQUA_PLANE_GOAL_Y)[i];
 }
 
 // K3: fold the per-CTA slots (kSlotStats counters each) and the forced-reset counter into
@@ -444,15 +439,14 @@ cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_
 }
 
 cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, const uint8_t* flags, int64_t lo,
-                                int64_t len, uint32_t cap, unsigned int* d_count, uint32_t* h_idx, void* h_goal,
-                                cudaStream_t s) {
+                                int64_t len, void* h_gx, void* h_gy, cudaStream_t s) {
     const int threads = 256;
     if (precision == AQUA_F64)
-        goal_updates_kernel<double><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len, cap, d_count, h_idx,
-                                                                                static_cast<double*>(h_goal));
+        goal_updates_kernel<double><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len,
+                                                                                static_cast<double*>(h_gx), static_cast<double*>(h_gy));
     else
-        goal_updates_kernel<float><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len, cap, d_count, h_idx,
-                                                                               static_cast<float*>(h_goal));
+        goal_updates_kernel<float><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len,
+                                                                               static_cast<float*>(h_gx), static_cast<float*>(h_gy));
     return cudaGetLastError();
 }
 

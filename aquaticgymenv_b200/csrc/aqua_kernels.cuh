@@ -118,10 +118,9 @@ cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n,
                              cudaStream_t s);
 cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_t n, float* out, int normalized,
                            cudaStream_t s);
-// lists the finished envs of [lo, lo + len) with their (new) goals into mapped host memory
+// writes the goals of the finished envs of [lo, lo + len) into the caller's (device-mapped) host planes
 cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, const uint8_t* flags, int64_t lo,
-                                int64_t len, uint32_t cap, unsigned int* d_count, uint32_t* h_idx, void* h_goal,
-                                cudaStream_t s);
+                                int64_t len, void* h_gx, void* h_gy, cudaStream_t s);
 cudaError_t launch_stats_reduce(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear, cudaStream_t s);
 // per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
 cudaError_t configure_kernels(int precision);

@@ -15,7 +15,7 @@ Workloads (BASELINE.json):
   c3        AquaContinuousEnv-v1, thrust pairs, 1,048,576 envs in total sharded over the N GPUs
   c4        the 64-obstacle stress map, discrete, 4,194,304 envs in total sharded over the N GPUs
   stream    AquaEnv-v1, 2^24 envs per GPU, ONE launch per step (the HBM-streaming kernel)
-By default the steps run `--steps-per-launch` (32) at a time through aqua_step_many: the action
+By default the steps run `--steps-per-launch` (64) at a time through aqua_step_many: the action
 tape [K][N] is read and reward + flags [K][N] are written per step (tape + outputs exceed the
 126 MB L2 at the headline size), the state stays in registers between the steps of a launch.
 `--mode single` runs one aqua_step launch per step instead (what a policy in the loop uses); at the
@@ -64,13 +64,13 @@ CONFIGS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
-    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=64)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default=None, choices=["many", "single"])
     ap.add_argument("--envs-per-gpu", type=int, default=None, help="override the config's slab size")
-    ap.add_argument("--steps-per-launch", type=int, default=32)
+    ap.add_argument("--steps-per-launch", type=int, default=64)
     ap.add_argument("--precision", default="float32", choices=["float32", "float64"])
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=12)
@@ -588,7 +588,7 @@ def run_b200(args):
         extras = {}
         try:
             def one(nm, **kw):
-                mm = measure(torch, nm, world, rank, args, dist_on=dist_on, steps=64, warmup=32, **kw)
+                mm = measure(torch, nm, world, rank, args, dist_on=dist_on, steps=128, warmup=64, **kw)
                 ss = summarise(torch, mm, world, dist_on)
                 mm["env"].close()
                 return brief(ss, mm, world)

@@ -209,9 +209,10 @@ int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_
                    void* reward, uint8_t* flags);
 
 /* Same; persistent_obs != 0 promises that `obs` is the very buffer of the previous aqua_step_host(_ex)
- * call on this handle and has not been written since.  Its goal planes (2 of the 5) are then brought
- * up to date by a list of (env, goal) entries for the envs whose episode changed instead of being
- * copied whole: 17 instead of 25 bytes per env-step come back over PCIe (float32).  Any other call that
+ * call on this handle and has not been written since.  If it is pinned memory (cudaHostAlloc /
+ * cudaHostRegister / torch pin_memory), its goal planes (2 of the 5) are then brought up to date by
+ * per-env writes for the envs whose episode changed instead of being copied whole: 17 instead of 25
+ * bytes per env-step come back over PCIe (float32).  Any other call that
  * changes the state (aqua_step, aqua_step_many, aqua_reset, aqua_set_state, ...) makes the next host
  * step send the planes whole again, whatever the promise. */
 int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,

@@ -677,21 +677,28 @@ def test_step_host_equals_device_step(precision):
     b.close()
 
 
-def test_step_host_goal_update_list_overflow():
-    """More finished envs than the update list holds (a quarter of a chunk): the chunk's goal planes
-    are copied whole.  A map without free space finishes every env at every step."""
+def test_step_host_with_pinned_buffers_updates_goals_in_place():
+    """Pinned host buffers (what bench.py's e2e leg uses): the goals of finished envs are written
+    straight into the caller's planes by a small kernel.  Also the extreme case: a map without free
+    space finishes every env at every step."""
+    torch = _torch()
     from aquaticgymenv_b200 import AquaVecEnv
-    wall = np.array([[50.0, 50.0, 1.0, 300.0, 300.0]])
-    n = 70000
-    env = AquaVecEnv(n, obstacles=wall, seed=3, precision="float32")
-    env.reset()
-    obs_h = np.zeros((5, n), np.float32)
-    act = np.zeros(n, np.int32)
-    for t in range(3):
-        _, _, fl = env.step_host(act, obs_h)
-        assert (fl & 1).all()
-        assert np.array_equal(obs_h, env.obs_planes.cpu().numpy()), t
-    env.close()
+    for table, n in ((np.load("%s/v1_table.npy" % GOLDEN), 300000), (np.array([[50.0, 50.0, 1.0, 300.0, 300.0]]), 70000)):
+        env = AquaVecEnv(n, obstacles=table, seed=3, precision="float32")
+        ref = AquaVecEnv(n, obstacles=table, seed=3, precision="float32")
+        env.reset()
+        ref.reset()
+        obs_h = torch.full((5, n), -1.0, dtype=torch.float32).pin_memory().numpy()
+        rew_h = torch.empty(n, dtype=torch.float32).pin_memory().numpy()
+        fl_h = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+        for t in range(12):
+            act = ref.random_actions(t)
+            ref.step_flags(act)
+            env.step_host(act.cpu().numpy(), obs_h, rew_h, fl_h)
+            assert np.array_equal(fl_h, ref.flags.cpu().numpy()), t
+            assert np.array_equal(obs_h, ref.obs_planes.cpu().numpy()), t
+        env.close()
+        ref.close()
 
 
 @pytest.mark.parametrize("precision", ["float32", "float64"])
