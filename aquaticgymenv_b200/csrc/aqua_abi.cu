@@ -46,7 +46,8 @@ struct DeviceGuard {
 
 constexpr int kHostStreams = 4;       // host-step pipeline depth
 constexpr int kTileCounters = 64;     // launches that may be in flight at once on one handle
-constexpr int64_t kHostChunkMin = 256 * 1024;  // every copy costs several us to issue and start: few, large ones
+constexpr int64_t kHostChunkMin = 1024 * 1024;  // every copy costs several us to issue and start: few, large
+                                                // ones (tools/e2e_probe.py: 1 chunk at 2^20 envs, 16 at 2^24)
 
 size_t elem_size(int precision) { return precision == AQUA_F64 ? 8 : 4; }
 
@@ -529,13 +530,17 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
     // chunking: whole AQUA_TILEs, at least kHostChunkMin envs, at most 4 chunks per stream
     int64_t chunk = (n + kHostStreams * 4 - 1) / (kHostStreams * 4);
     chunk = std::max(chunk, kHostChunkMin);
+    if (const char* e = getenv("AQUA_HOST_CHUNKS")) {  // tuning only: that many chunks (1 .. 16)
+        const int64_t k = std::min<int64_t>(std::max<int64_t>(atoll(e), 1), kHostStreams * 4);
+        chunk = (n + k - 1) / k;
+    }
     chunk = (chunk + AQUA_TILE - 1) / AQUA_TILE * AQUA_TILE;
 
     AQ_CUDA(cudaEventRecord(env->ev_in, static_cast<cudaStream_t>(stream)));
     for (int i = 0; i < kHostStreams; ++i) AQ_CUDA(cudaStreamWaitEvent(env->hs[i], env->ev_in, 0));
 
-    static const int kObsPlanes[5] = {AQUA_PLANE_X, AQUA_PLANE_Y, AQUA_PLANE_THETA, AQUA_PLANE_GOAL_X,
-                                      AQUA_PLANE_GOAL_Y};  // aqua.py:213
+    static_assert(AQUA_PLANE_X == 0 && AQUA_PLANE_Y == 1 && AQUA_PLANE_THETA == 2 && AQUA_PLANE_GOAL_X == 3 &&
+                      AQUA_PLANE_GOAL_Y == 4, "the observation (aqua.py:213) is planes 0..4 in order");
     // a failure inside the loop must not return while copies into the caller's buffers are still
     // in flight: remember it, stop issuing, wait for every internal stream, then report
     cudaError_t err = cudaSuccess;
@@ -582,12 +587,10 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
             AQ_TRY(cudaMemcpyAsync(static_cast<char*>(reward) + (size_t)lo * es,
                                    static_cast<char*>(env->d_reward) + (size_t)lo * es, (size_t)len * es,
                                    cudaMemcpyDeviceToHost, s));
-        if (obs != nullptr)
-            for (int k = 0; k < n_obs_planes; ++k)
-                AQ_TRY(cudaMemcpyAsync(static_cast<char*>(obs) + ((size_t)k * (size_t)n + (size_t)lo) * es,
-                                       static_cast<char*>(env->state) +
-                                           ((size_t)kObsPlanes[k] * (size_t)env->ld + (size_t)lo) * es,
-                                       (size_t)len * es, cudaMemcpyDeviceToHost, s));
+        if (obs != nullptr)  // planes x, y, angle (, goal_x, goal_y) are rows 0.. of both sides: ONE strided copy
+            AQ_TRY(cudaMemcpy2DAsync(static_cast<char*>(obs) + (size_t)lo * es, (size_t)n * es,
+                                     static_cast<char*>(env->state) + (size_t)lo * es, (size_t)env->ld * es,
+                                     (size_t)len * es, (size_t)n_obs_planes, cudaMemcpyDeviceToHost, s));
         if (sparse_goals)
             AQ_TRY(aqua::launch_goal_updates(env->cfg.precision, env->state, env->ld, env->d_flags, lo, len,
                                              obs_dev + (size_t)3 * (size_t)n * es, obs_dev + (size_t)4 * (size_t)n * es, s));

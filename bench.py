@@ -487,15 +487,15 @@ def brief(s, m, world):
 
 
 def e2e_leg(torch, env, args, world, dist_on):
-    """The host-buffer C-ABI call (aqua_step_host): pinned int32 actions in, obs + reward + flags out,
+    """The host-buffer C-ABI call (aqua_step_host): pinned uint8 actions in, obs + reward + flags out,
     copies inside the timed region.  Also a plain pinned device-to-host copy of the same bytes, as the
     ceiling of the link on this box."""
     import torch.distributed as dist
     n = env.num_envs
     tdt = torch.float32 if env.precision == 0 else torch.float64
     es = 4 if env.precision == 0 else 8
-    h_act = torch.empty(n, dtype=torch.int32, pin_memory=True)
-    h_act.copy_(env.random_actions(0).cpu())
+    h_act = torch.empty(n, dtype=torch.uint8, pin_memory=True)   # the action index fits a byte (AQUA_ACT_U8)
+    h_act.copy_(env.random_actions(0).cpu().to(torch.uint8))
     h_obs = torch.empty(5, n, dtype=tdt, pin_memory=True)
     h_rew = torch.empty(n, dtype=tdt, pin_memory=True)
     h_flg = torch.empty(n, dtype=torch.uint8, pin_memory=True)
@@ -532,11 +532,12 @@ def e2e_leg(torch, env, args, world, dist_on):
     if dist_on:
         dist.all_reduce(cd, op=dist.ReduceOp.MAX)
     return {"value": n * world * args.e2e_steps / float(ed.item()), "unit": "env-steps/s",
-            "h2d_bytes_per_step": 4 * n * world, "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
+            "h2d_bytes_per_step": 1 * n * world, "d2h_bytes_per_step": d2h * world, "steps": args.e2e_steps,
             "d2h_gbs_per_gpu": d2h * args.e2e_steps / float(ed.item()) / 1e9,
             "plain_pinned_d2h_copy_gbs_per_gpu": d2h * args.e2e_steps / float(cd.item()) / 1e9,
-            "api": "aqua_step_host (AquaVecEnv.step_host): int32 actions in; x, y, angle + reward + flags out every step, "
-                   "goal planes only for the envs whose episode changed; pinned host buffers"}
+            "api": "aqua_step_host (AquaVecEnv.step_host): uint8 actions in; x, y, angle + reward + flags out every step, "
+                   "goals only for the envs whose episode changed (written straight into the pinned planes); "
+                   "pinned host buffers"}
 
 
 def run_b200(args):

@@ -764,6 +764,60 @@ def test_sharding_invariance():
     whole.close()
 
 
+# ------------------------------------------------------------------ soak at BASELINE's size
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+def test_soak_one_million_envs_against_the_oracle(precision):
+    """BASELINE's own size: 2^20 envs of AquaEnv-v1 x 100 steps = 1.05e8 env-steps, lock-step against
+    the C oracle (all host threads), every flag and reward of every step compared, the state every
+    20 steps; half of the steps through aqua_step_many.  float64: a flag may only differ where the
+    reference's own decision margin is below 1e-7 px (its round-off; measured 2 in 1.05e9).
+    float32: at most 2e-6 flips per env-step, every one at a margin below 1e-3 px; a flipped env is
+    put back on the oracle's trajectory."""
+    import os
+    torch = _torch()
+    cfg = _cfg("v1_discrete", seed=17)
+    n, T = 1 << 20, 100
+    threads = len(os.sched_getaffinity(0))
+    env = _make_gpu(cfg, n, precision, autoreset=True)
+    ref = _make_oracle(cfg, n)
+    env.reset()
+    ref.reset()
+    f64 = precision == "float64"
+    tol = TOL_F64 if f64 else TOL_F32
+    flips = 0
+    t = 0
+    while t < T:
+        K = 1 if (t // 10) % 2 == 0 else 10         # ten single steps, then ten steps in one launch, ...
+        tape = torch.stack([env.random_actions(t + k) for k in range(K)])
+        if K == 1:
+            flags = env.step_flags(tape[0]).unsqueeze(0)
+            reward = env.reward.unsqueeze(0)
+        else:
+            reward, flags = env.step_many(tape)
+        flags, reward, acts = flags.cpu().numpy(), reward.cpu().numpy().astype(np.float64), tape.cpu().numpy()
+        resync = False
+        for k in range(K):
+            _, r_ref, f_ref, margin = ref.step(acts[k], autoreset=True, want_margin=True, nthreads=threads)
+            differ = flags[k] != f_ref
+            if differ.any():
+                assert (margin[differ] < (1e-7 if f64 else TAU_F32)).all(), (t + k, margin[differ])
+                flips += int(differ.sum())
+                resync = True
+                break                                # the rest of this launch ran on a diverged env: drop it
+            assert err_scaled(reward[k], r_ref, SCALE_REWARD).max() < tol, t + k
+        if resync:
+            env.set_state(torch.as_tensor(ref.get_state()))
+            t += k + 1
+            continue
+        t += K
+        if t % 20 == 0:
+            got, want = env.get_state().cpu().numpy(), ref.get_state()
+            assert _state_err(got, want) < tol, t
+            assert np.array_equal(got[5:], want[5:])
+    assert flips <= (2 if f64 else int(2e-6 * n * T)), flips
+    env.close()
+
+
 # ------------------------------------------------------------------ full-size properties
 @pytest.mark.parametrize("name,n", [("v1_discrete", 1 << 20), ("v2_continuous", 1 << 20),
                                     ("dense64_discrete", 1 << 19)])

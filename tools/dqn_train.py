@@ -16,9 +16,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 from aquaticgymenv_b200 import dqn, gym_aqua, policies  # noqa: E402
 
-steps = int(sys.argv[1]) if len(sys.argv) > 1 else 24000
-n = int(sys.argv[2]) if len(sys.argv) > 2 else 512
-batch = int(sys.argv[3]) if len(sys.argv) > 3 else 512
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 48000
+n = int(sys.argv[2]) if len(sys.argv) > 2 else 1024
+batch = int(sys.argv[3]) if len(sys.argv) > 3 else 1024
 HP = {"EPSILON_DECAY": 15000, "BUFFER_SIZE": 300000, "MINIBATCH_SIZE": batch, "UPDATES_PER_STEP": 1,
       "LEARNING_RATE": 1e-3}   # GAMMA 0.98, TAU 0.005, EPSILON 1.0 -> 0.05, double DQN: the reference's
 
