@@ -5,8 +5,12 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-A "step" = every env of the job advances by one env.step() (aqua.py:135-213) including the
-auto-reset, on synthetic random actions that are resident in HBM before the timed region.
+A bench "step" = one pass of the hot path over one batch of synthetic input = ONE launch: with
+aqua_step_many (the default) every env of the job advances by `--steps-per-launch` (64) env.step()
+calls (aqua.py:135-213, auto-reset included) on a tape of random actions that is resident in HBM
+before the timed region; with `--mode single` by one.  `value` counts env-steps (envs x env.step()
+calls) per second; `ms_per_step` is per launch; `config.env_steps_per_step` says how many env-steps
+one bench step is.
 
 Workloads (BASELINE.json):
   headline  the metric's own config: AquaEnv-v1 (discrete actions, default 5-obstacle layout, waves,
@@ -15,9 +19,9 @@ Workloads (BASELINE.json):
   c3        AquaContinuousEnv-v1, thrust pairs, 1,048,576 envs in total sharded over the N GPUs
   c4        the 64-obstacle stress map, discrete, 4,194,304 envs in total sharded over the N GPUs
   stream    AquaEnv-v1, 2^24 envs per GPU, ONE launch per step (the HBM-streaming kernel)
-By default the steps run `--steps-per-launch` (64) at a time through aqua_step_many: the action
-tape [K][N] is read and reward + flags [K][N] are written per step (tape + outputs exceed the
-126 MB L2 at the headline size), the state stays in registers between the steps of a launch.
+aqua_step_many reads the action tape [K][N] and writes reward + flags [K][N] per env-step (tape +
+outputs exceed the 126 MB L2 at the headline size); the state stays in registers between the
+env-steps of a launch.
 `--mode single` runs one aqua_step launch per step instead (what a policy in the loop uses); at the
 L2-resident sizes it is captured in a CUDA graph.  Both figures of the headline workload are in
 the line (`extras.single_step`).  Envs shard as independent slabs; the only collective is the
@@ -64,8 +68,8 @@ CONFIGS = {
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=20, help="timed launches")
+    ap.add_argument("--warmup", type=int, default=5, help="untimed launches before (at least 3)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="headline", choices=sorted(CONFIGS))
     ap.add_argument("--mode", default=None, choices=["many", "single"])
@@ -112,6 +116,7 @@ def workload_config(name, cfg, n_local, world, mode, spl, precision, l2_note):
         "mode": ("aqua_step_many: %d steps per launch, action tape in, reward+flags out per step" % spl) if mode == "many"
                 else "aqua_step: one launch per step",
         "steps_per_launch": spl if mode == "many" else 1,
+        "env_steps_per_step": n_local * world * (spl if mode == "many" else 1),
         "bytes_per_env_step": BYTES_PER_STEP[cont],
         "parallelism": "env slabs x%d, no data-path collective" % world,
         "l2": l2_note,
@@ -313,13 +318,12 @@ class ManyRunner(object):
         self.bytes_resident = self.tape.numel() * self.tape.element_size() + self.rew.numel() * self.rew.element_size() + self.flg.numel()
         self.launches = 0
 
-    def run(self, steps):
-        done = 0
-        while done < steps:
-            k = min(self.spl, steps - done)
-            self.env.step_many(self.tape[:k], self.rew[:k], self.flg[:k])
-            done += k
-            self.launches += 1
+    per_launch = property(lambda self: self.spl)   # env-steps per env and launch
+
+    def run(self, launches):
+        for _ in range(launches):
+            self.env.step_many(self.tape, self.rew, self.flg)
+        self.launches += launches
 
     def l2_note(self):
         mb = self.bytes_resident / 1e6
@@ -345,6 +349,8 @@ class SingleRunner(object):
             with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
                 for k in range(graph_chunk):
                     env.step_flags(self.pool[k % 4])
+
+    per_launch = 1
 
     def run(self, steps):
         done = 0
@@ -402,11 +408,8 @@ def measure(torch, name, world, rank, args, mode=None, n_local=None, steps=None,
         runner = ManyRunner(torch, env, spl)
     else:
         runner = SingleRunner(torch, env, graph_chunk=32 if n_local * 65 < 126e6 else 0)
-    # warm-up: W steps, at least three launches (stash allocation, lazy initialisation, clocks)
-    l0 = runner.launches
+    # warm-up: W launches, at least three (stash allocation, lazy initialisation, clocks)
     runner.run(max(warmup, 3))
-    while runner.launches - l0 < 3:
-        runner.run(max(warmup, 3))
     torch.cuda.synchronize()
     env.stats(clear=True)
     elapsed, t0, t1, launches = timed(torch, runner, steps, dist_on)
@@ -419,7 +422,8 @@ def measure(torch, name, world, rank, args, mode=None, n_local=None, steps=None,
         t2 = time.perf_counter()
     return {"name": name, "cfg": cfg, "mode": mode, "n_local": n_local, "steps": steps, "elapsed": elapsed,
             "launches": launches, "t": (t0, t1, t2), "stats_t": stats_t, "continuous": env.continuous,
-            "precision": precision, "l2": runner.l2_note(), "spl": spl, "env": env, "runner": runner}
+            "precision": precision, "l2": runner.l2_note(), "spl": spl, "env": env, "runner": runner,
+            "per_launch": runner.per_launch}
 
 
 def summarise(torch, m, world, dist_on):
@@ -433,24 +437,24 @@ def summarise(torch, m, world, dist_on):
     elapsed_max = float(el.item())
     sharding.all_reduce_stats(m["stats_t"])  # the only collective of the path: 9 int64 counters
     stats = stats_dict(m["stats_t"].cpu().tolist())
-    total = m["n_local"] * world * m["steps"]
+    total = m["n_local"] * world * m["steps"] * m["per_launch"]
     assert stats["steps"] == total, (stats["steps"], total)  # the kernels counted exactly the timed env-steps
     peak_gbs, peak_src = peaks()
     es = 8 if m["precision"] == "float64" else 4
     # single-step launch: 7 state words + time in, action in, 5 state words + time out, reward, flags
     bpe = (7 * es + 4) + (8 if m["continuous"] else 4) + (5 * es + 4) + es + 1
-    achieved = bpe * m["n_local"] * m["steps"] / m["elapsed"] / 1e9  # this rank's kernel, GB/s
+    achieved = bpe * m["n_local"] * m["steps"] * m["per_launch"] / m["elapsed"] / 1e9  # this rank's kernel, GB/s
     moved = None
     if m["mode"] == "many":
         # what one env-step really moves: action in, reward + flags out, and per launch the state
         # planes in + out (2 x 8 words) and the stash tag sector (32 B)
         per_launch = 2 * (7 * es + 4) + 32
-        moved = (8 if m["continuous"] else 4) + es + 1 + per_launch / max(min(m["spl"], m["steps"]), 1)
+        moved = (8 if m["continuous"] else 4) + es + 1 + per_launch / m["spl"]
     return {
         "value": total / elapsed_max, "elapsed_max_s": elapsed_max, "ms_per_step": 1e3 * elapsed_max / m["steps"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
                      "traffic": traffic_of(m), "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": bpe * m["n_local"] * (m["steps"] / max(m["launches"], 1)),
+                     "algorithmic_bytes_per_launch": bpe * m["n_local"] * m["per_launch"],
                      "bytes_per_env_step": bpe,
                      "bytes_per_env_step_moved_by_this_kernel": moved,
                      "frac_of_bytes_moved": None if moved is None else achieved / peak_gbs * moved / bpe,
@@ -482,7 +486,7 @@ def traffic_of(m):
 def brief(s, m, world):
     return {"config": m["name"], "mode": m["mode"], "envs_per_gpu": m["n_local"], "envs_total": m["n_local"] * world,
             "steps_per_launch": m["spl"] if m["mode"] == "many" else 1, "precision": m["precision"],
-            "env_steps_per_s": s["value"], "us_per_step": 1e3 * s["ms_per_step"],
+            "env_steps_per_s": s["value"], "us_per_env_step_of_all_envs": 1e3 * s["ms_per_step"] / m["per_launch"],
             "hbm_frac": s["roofline"]["frac"], "bytes_per_env_step": s["roofline"]["bytes_per_env_step"], "l2": m["l2"]}
 
 
@@ -589,7 +593,9 @@ def run_b200(args):
         extras = {}
         try:
             def one(nm, **kw):
-                mm = measure(torch, nm, world, rank, args, dist_on=dist_on, steps=128, warmup=64, **kw)
+                many = (kw.get("mode") or CONFIGS[nm]["mode"]) == "many"
+                mm = measure(torch, nm, world, rank, args, dist_on=dist_on, steps=6 if many else 128,
+                             warmup=3 if many else 32, **kw)
                 ss = summarise(torch, mm, world, dist_on)
                 mm["env"].close()
                 return brief(ss, mm, world)
