@@ -211,14 +211,22 @@ struct StreamLaunchOp {
             const size_t smem = stage_bytes<R, V>() + cell_bytes(a.w.use_grid);
             // bulk (TMA) staging for launches large enough to stream from HBM, per-lane cp.async below
             const bool tma = AQUA_TMA == 2 || (AQUA_TMA == 1 && (int64_t)a.n_stream >= kTmaMinEnvs);
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)g.blocks);
+            cfg.blockDim = dim3((unsigned)g.threads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = s;
+            cudaLaunchAttribute attr[1];  // consecutive steps overlap launch latency and prologue
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            attr[0].val.programmaticStreamSerializationAllowed = AQUA_PDL;
+            cfg.attrs = attr;
+            cfg.numAttrs = 1;
             if (a.w.waves) {
-                if (tma) step_stream_kernel<R, V, ACT, true, true><<<g.blocks, g.threads, smem, s>>>(a);
-                else step_stream_kernel<R, V, ACT, true, false><<<g.blocks, g.threads, smem, s>>>(a);
-            } else {
-                if (tma) step_stream_kernel<R, V, ACT, false, true><<<g.blocks, g.threads, smem, s>>>(a);
-                else step_stream_kernel<R, V, ACT, false, false><<<g.blocks, g.threads, smem, s>>>(a);
+                if (tma) return cudaLaunchKernelEx(&cfg, step_stream_kernel<R, V, ACT, true, true>, a);
+                return cudaLaunchKernelEx(&cfg, step_stream_kernel<R, V, ACT, true, false>, a);
             }
-            return cudaGetLastError();
+            if (tma) return cudaLaunchKernelEx(&cfg, step_stream_kernel<R, V, ACT, false, true>, a);
+            return cudaLaunchKernelEx(&cfg, step_stream_kernel<R, V, ACT, false, false>, a);
         } else {
             return cudaErrorNotSupported;
         }

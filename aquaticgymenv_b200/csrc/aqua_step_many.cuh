@@ -341,9 +341,10 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
                 for (int j = 0; j < V; ++j)
                     if (j >= nvalid) reward[j] = R(0);
             }
-            st.add_flags(fw, nvalid);
 #pragma unroll
             for (int j = 0; j < V; ++j) st.add_env<R>(reward[j]);
+            const bool any_done = __any_sync(full, fw != 0u);  // warp-uniform
+            if (any_done) st.add_flags(fw, 0);                 // (the env-steps are counted once, after the loop)
 
             // ---- outputs of step k (full-width: a partial thread writes into the row's padding) ----
             if (rew_ptr_k != nullptr) {
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
             if (!autoreset) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), e[j].tw & kTimeMask);
-            } else if (__any_sync(full, fw != 0u)) {
+            } else if (any_done) {
                 uint32_t ep[V], word = 0u;  // what gets queued: bit 0 of byte j, with episode ep[j]
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
@@ -390,6 +391,8 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_ker
                 if (__any_sync(full, pend != 0u)) thr = 1;
             }
         }
+
+        st.steps += (uint32_t)nvalid * (uint32_t)p.steps;
 
         // ---- stash out (records whose refill is still queued go back with their old tag) ----
         if (autoreset) {

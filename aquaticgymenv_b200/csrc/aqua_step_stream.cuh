@@ -120,6 +120,11 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
         }
     }
     __syncthreads();
+    // Programmatic dependent launch (launch_step sets the attribute): the CTAs of this launch may
+    // become resident, and stage the obstacle table above, while the previous kernel of the stream is
+    // still running; they wait here, before their first access to the state, until it has completed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
     constexpr int kSlot = stage_slot<R, V>(), kPitch = stage_pitch<R, V>();
     constexpr int kStage = kStageSlots * kPitch;
