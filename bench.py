@@ -619,6 +619,7 @@ def run_b200(args):
         line["extras"] = extras
         if rank == 0 and world == 1:
             line["cpu_baseline"] = cpu_baseline(args, cfg, n_local)
+            line["cpu_baseline"]["c1_single_env"] = c1_single_env(args)  # BASELINE config 1, both sides
     elif rank == 0:
         line["cpu_baseline"] = None
 
@@ -627,6 +628,46 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(line))
+
+
+def c1_single_env(args, steps=10000):
+    """BASELINE config 1: AquaEnv-v0 (discrete, no obstacles), ONE env, random policy, `steps` steps,
+    reset on done -- the reference's own gym path (unmodified Python env, one process) and the
+    drop-in single-env class (same API; every step is one call into the library: action up, kernel,
+    observation + reward + flags down, one synchronisation)."""
+    out = {"steps": steps, "env": "AquaEnv-v0 (no obstacles, waves, random boat + goal), single env, action_space.sample()"}
+    try:
+        from aquaticgymenv_b200 import gym_aqua
+        env = gym_aqua.make("AquaEnv-v0", seed=args.seed)
+        env.action_space.seed(0)
+        env.reset()
+        for _ in range(200):
+            if env.step(env.action_space.sample())[2]:
+                env.reset()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            if env.step(env.action_space.sample())[2]:
+                env.reset()
+        out["dropin_steps_per_s"] = steps / (time.perf_counter() - t0)
+        env.close()
+    except Exception as e:
+        out["dropin_error"] = repr(e)
+    try:
+        from oracle import ref_vector_env as rv
+        gym = rv.import_reference()
+        np.random.seed(0)
+        env = gym.make("AquaEnv-v0")
+        env.action_space.seed(0)
+        env.observation_space.seed(0)
+        env.reset()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            if env.step(env.action_space.sample())[2]:
+                env.reset()
+        out["reference_steps_per_s"] = steps / (time.perf_counter() - t0)
+    except Exception as e:
+        out["reference_error"] = repr(e)
+    return out
 
 
 def cpu_baseline(args, cfg, n_local):
