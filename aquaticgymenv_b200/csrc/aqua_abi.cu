@@ -436,25 +436,28 @@ int ensure_stash(aqua_env* env, cudaStream_t s) {
 }
 
 // Geometry of a multi-step launch: every env belongs to one thread for the whole launch, so the
-// grid is not persistent.  Envs per thread and threads per CTA are picked so that the launch fills
-// the GPU in whole waves where it can: narrow threads and small CTAs for small slabs (one wave, all
-// SMs evenly loaded), wide threads for large ones (fewer instructions per env-step).
+// grid is not persistent.  More envs per thread cost fewer instructions per env-step (7.3 / 8.6 / 12
+// warp-instructions at V = 4 / 2 / 1) but leave fewer warps; measured over slab sizes on one box
+// (profiles/r02l_step_many_v_by_size.txt) the widest thread that still gives every SM three 64-thread
+// CTAs wins or comes within 8 %: V = 4 from ~114k envs, V = 2 from ~57k, V = 1 below.
 // AQUA_MANY_V / AQUA_MANY_THREADS (environment) override the choice: tuning only.
 int pick_many_geom(const aqua_env* env, int64_t n, aqua::LaunchGeom* g) {
     const int wide = aqua::envs_per_thread(env->cfg.precision);
-    int v = 1, threads = 64;
-    const int64_t lanes = (int64_t)env->sm_count * 1024;  // threads one wave of narrow CTAs can hold (about)
-    if (n > 4 * lanes) { v = wide; threads = 128; }
-    else if (n > lanes) { v = 2; threads = 128; }
-    if (env->cfg.geometry == AQUA_GEOM_WIDE) { v = wide; threads = 128; }
-    if (env->cfg.geometry == AQUA_GEOM_NARROW) { v = 1; threads = 64; }
+    int threads = 64, v = 1;
+    for (int cand = wide; cand >= 1; cand /= 2)
+        if (n >= (int64_t)3 * env->sm_count * threads * cand) {
+            v = cand;
+            break;
+        }
+    if (env->cfg.geometry == AQUA_GEOM_WIDE) v = wide;
+    if (env->cfg.geometry == AQUA_GEOM_NARROW) v = 1;
     if (const char* s = getenv("AQUA_MANY_V")) {
         const int x = atoi(s);
         if (x == 1 || x == 2 || (x == 4 && wide == 4)) v = x;
     }
     if (const char* s = getenv("AQUA_MANY_THREADS")) {
         const int x = atoi(s);
-        if (x == 32 || x == 64 || x == 128 || x == 256) threads = x;
+        if (x == 32 || x == 64 || x == 128) threads = x;  // the kernel is bounded to 128 threads
     }
     g->v = v;
     g->threads = threads;

@@ -28,11 +28,13 @@
 
 namespace aqua {
 
-// register budget: 128-thread CTAs, 4 / 4 / 3 of them per SM at 1 / 2 / 4 envs per thread (128 / 128 / 168
-// registers: the narrow instantiations serve slabs too small to fill more warps anyway, and a tighter
-// cap makes the compiler recompute the loop's constants in every step)
+// Register budget: 128-thread CTAs, 5 of them per SM (96 registers) at 1 or 2 float envs per thread,
+// 4 (128 registers) at 4 float envs and for double.  Measured on one box
+// (profiles/r02k_step_many_occupancy_ab.txt): V = 4 at 128 instead of 146 registers (4 instead of 3
+// CTAs per SM, no spills) +6 % at 2^20 envs, +9 % at 2^24, +14 % on the 64-obstacle map; V = 2 at 96
+// instead of 107 (8 bytes spilled) +5 %.  One step further (V = 4 at 96) spills 200 bytes.
 #ifndef AQUA_MANY_MINB
-#define AQUA_MANY_MINB(V) ((V) == 4 ? 3 : 4)
+#define AQUA_MANY_MINB(V, F64) (((V) == 4 || (F64)) ? 4 : 5)
 #endif
 constexpr int kManyThreads = 128;  // launch bound; the launcher picks 32 .. 128 threads per CTA
 constexpr uint32_t kStashEmpty = 0xffffffffu;
@@ -126,7 +128,7 @@ __device__ __forceinline__ void philox2x32_10_v(uint32_t (&c0)[N], uint32_t (&c1
 }
 
 template <typename R, int V, int ACT, bool TAPE>
-__global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V)) step_many_kernel(const __grid_constant__ StepArgs p) {
+__global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8)) step_many_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ DriveSlot<R> s_drive[3];
