@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("AQUAGYM_LIB") or os.path.join(_HERE, "libaquagym.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "aquagym.h")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 OK, ERR_INVALID, ERR_CUDA, ERR_NO_DEVICE, ERR_ALLOC = 0, -1, -2, -3, -4
 F32, F64 = 0, 1
 GEOM_AUTO, GEOM_WIDE, GEOM_NARROW = 0, 1, 2
@@ -73,9 +73,11 @@ SIGNATURES = {
     "aqua_stats_reduce": (_int, [_vp, _vp, _vp, _int]),
     "aqua_get_stats": (_int, [_vp, _vp, C.POINTER(C.c_int64), _int]),
     "aqua_obstacle_grid": (_int, [_vp, _int, _vp, _vp, C.POINTER(_int)]),
+    "aqua_obstacle_grid_ex": (_int, [_vp, _int, _vp, _vp, _vp, C.POINTER(_int)]),
 }
-GRID_DIM = 48                      # AQUA_GRID_DIM
+GRID_DIM = 96                      # AQUA_GRID_DIM
 CELL_BLOCKED = 0xFFFFFFFFFFFFFFFF  # AQUA_CELL_BLOCKED
+CELL16_NONE, CELL16_BLOCKED, CELL16_OVERFLOW = 64, 0x4000, 0x8000
 
 _lib = None
 
@@ -91,12 +93,15 @@ def load():
             "`make -C aquaticgymenv_b200/csrc` (nvcc, sm_100a). aquaticgymenv_b200 has no CPU "
             "fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
+    lenient = bool(os.environ.get("AQUAGYM_LIB_ANY_ABI"))  # tools/many_ab.py: time an older build
     for name, (res, args) in SIGNATURES.items():
+        if lenient and not hasattr(lib, name):
+            continue
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
     got = lib.aqua_abi_version()
-    if got != ABI_VERSION:
+    if got != ABI_VERSION and not lenient:
         raise ImportError("libaquagym ABI %d, binding expects %d: rebuild" % (got, ABI_VERSION))
     _lib = lib
     return lib
@@ -120,4 +125,19 @@ def obstacle_grid(obstacles):
     check(load().aqua_obstacle_grid(tab.ctypes.data if k else None, k, rows.ctypes.data, cells.ctypes.data,
                                     C.byref(use_grid)))
     return rows[:k], cells.reshape(GRID_DIM, GRID_DIM), bool(use_grid.value)
+
+
+def obstacle_grid16(obstacles):
+    """aqua_obstacle_grid_ex: as obstacle_grid plus the 16-bit cell words the kernels read
+    (uint16 [GRID_DIM, GRID_DIM]).  Returns (rows, cells, cells16, use_grid)."""
+    import numpy as np
+    tab = np.ascontiguousarray(np.asarray(obstacles, np.float64).reshape(-1, 5))
+    k = tab.shape[0]
+    rows = np.zeros((max(k, 1), 5), np.float64)
+    cells = np.zeros(GRID_DIM * GRID_DIM, np.uint64)
+    cells16 = np.zeros(GRID_DIM * GRID_DIM, np.uint16)
+    use_grid = C.c_int(0)
+    check(load().aqua_obstacle_grid_ex(tab.ctypes.data if k else None, k, rows.ctypes.data, cells.ctypes.data,
+                                       cells16.ctypes.data, C.byref(use_grid)))
+    return rows[:k], cells.reshape(GRID_DIM, GRID_DIM), cells16.reshape(GRID_DIM, GRID_DIM), bool(use_grid.value)
 

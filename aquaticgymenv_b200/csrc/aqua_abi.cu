@@ -305,6 +305,9 @@ int aqua_create(aqua_env** out, const aqua_config* cfg) {
     w.autoreset = cfg->autoreset != 0;
     w.use_grid = use_grid != 0;
     w.forced = env->d_forced;
+    aqua::fill_small_table(cfg->precision, cfg->n_obstacles, cfg->obstacles, use_grid, &w);
+    if (const char* s = getenv("AQUA_SMALL_TABLE"))  // tests / tuning: 0 = the shared-memory table for every layout
+        if (atoi(s) == 0) w.small_mode = 0;
 
     AQ_CREATE(aqua::configure_kernels(cfg->precision));
     for (int ti = 0; ti < 2; ++ti) {
@@ -471,7 +474,7 @@ int aqua_step_many(aqua_env* env, void* stream, int64_t steps, const void* actio
                    void* reward, uint8_t* flags, int64_t row_stride) {
     if (int rc = check_env(env)) return rc;
     if (int rc = check_action_dtype(env, action_dtype)) return rc;
-    if (steps < 0) return fail(AQUA_ERR_INVALID, "steps must be >= 0");
+    if (steps < 0 || steps > 0x7fffffff) return fail(AQUA_ERR_INVALID, "steps must be in [0, 2^31)");
     if (actions == nullptr) return fail(AQUA_ERR_INVALID, "actions is NULL");
     if (row_stride < env->cfg.n_envs || row_stride % 16 != 0)
         return fail(AQUA_ERR_INVALID, "row_stride = %lld must be a multiple of 16 and >= n_envs = %lld",
@@ -498,7 +501,7 @@ int aqua_step_many(aqua_env* env, void* stream, int64_t steps, const void* actio
 
 int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t first_step_index) {
     if (int rc = check_env(env)) return rc;
-    if (steps < 0) return fail(AQUA_ERR_INVALID, "steps must be >= 0");
+    if (steps < 0 || steps > 0x7fffffff) return fail(AQUA_ERR_INVALID, "steps must be in [0, 2^31)");
     if (steps == 0) return AQUA_OK;
     env->host_obs_last = nullptr;
     DeviceGuard guard(env->device);
@@ -663,6 +666,11 @@ int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear) {
 
 int aqua_obstacle_grid(const double* obstacles, int n_obstacles, double* rows_out, uint64_t* cells_out,
                        int* use_grid_out) {
+    return aqua_obstacle_grid_ex(obstacles, n_obstacles, rows_out, cells_out, nullptr, use_grid_out);
+}
+
+int aqua_obstacle_grid_ex(const double* obstacles, int n_obstacles, double* rows_out, uint64_t* cells_out,
+                          uint16_t* cells16_out, int* use_grid_out) {
     if (n_obstacles < 0 || n_obstacles > AQUA_MAX_OBSTACLES)
         return fail(AQUA_ERR_INVALID, "n_obstacles must be in [0, %d], got %d", AQUA_MAX_OBSTACLES, n_obstacles);
     if ((n_obstacles > 0 && (obstacles == nullptr || rows_out == nullptr)) || cells_out == nullptr || use_grid_out == nullptr)
@@ -672,6 +680,7 @@ int aqua_obstacle_grid(const double* obstacles, int n_obstacles, double* rows_ou
     double h_tab64[AQUA_MAX_OBSTACLES * 5] = {0};
     aqua::build_obstacle_tables(AQUA_F64, n_obstacles, obstacles, h_tab, h_tab64, use_grid_out);
     aqua::copy_table_cells(AQUA_F64, h_tab, reinterpret_cast<unsigned long long*>(cells_out));
+    if (cells16_out != nullptr) aqua::copy_table_cells16(AQUA_F64, h_tab, cells16_out);
     free(h_tab);
     if (n_obstacles > 0) memcpy(rows_out, h_tab64, sizeof(double) * 5 * (size_t)n_obstacles);
     return AQUA_OK;

@@ -154,28 +154,40 @@ template <typename R> struct alignas(16) ObstacleBox {
     R cx, cy, a, b;
 };
 // Dense maps (more than kGridMinObstacles obstacles) are culled through a uniform grid over the
-// world.  cell[c] is the bit mask of the obstacles whose clearance region (obstacle inflated by
-// the radius 2.5, plus a safety margin) touches cell c, so only those few are tested exactly; a
-// cell that lies entirely inside one obstacle's clearance region (shrunk by the margin) holds
-// kCellBlocked instead: every point of it collides, no test needed.  Both classifications are made
-// on the host in float64 with a 0.05 px margin, hence conservative: the collision decision is
-// unchanged.  Lanes of a warp sit in different cells, so the loop runs as long as its busiest
-// lane: a 48 x 48 grid (2.08 px cells) leaves 2.7 iterations per warp on the 64-obstacle stress
-// map where 16 x 16 left 5.7.
-constexpr int kGridDim = 48;
+// world.  A cell lists the obstacles whose clearance region (obstacle inflated by the radius 2.5,
+// plus a safety margin) touches it, so only those are tested exactly; a cell that lies entirely
+// inside one obstacle's clearance region (shrunk by the margin) is marked blocked: every point of
+// it collides, no test needed.  Both classifications are made on the host in float64 with a
+// 0.05 px margin, hence conservative: the collision decision is unchanged.
+//
+// What the kernels read per position is one 16-bit word: the first two listed obstacles (7 bits
+// each, kCellNone = none), the blocked bit and an overflow bit.  Both listed obstacles are always
+// tested, in one unified form (a circle is a box of zero extents), kCellNone being a table entry
+// that never collides: straight-line code, no divergence between the lanes of a warp, whichever
+// cells they sit in.  With 96 x 96 cells (1.04 px) fewer than one position in a thousand of the
+// 64-obstacle stress map lies in a cell that lists more than two obstacles (overflow bit): those
+// lanes walk the cell's full 64-bit mask from global memory.
+constexpr int kGridDim = 96;
 constexpr int kGridCells = kGridDim * kGridDim;
 constexpr int kGridMinObstacles = 12;
 constexpr unsigned long long kCellBlocked = ~0ull;
+constexpr uint32_t kCellNone = AQUA_MAX_OBSTACLES;  // index of the entry that never collides
+constexpr uint32_t kCell16Blocked = 0x4000u, kCell16Overflow = 0x8000u;
 // host / global-memory layout
 template <typename R> struct ObstacleTable {
-    ObstacleBox<R> box[AQUA_MAX_OBSTACLES];
-    unsigned long long cell[kGridCells];
+    ObstacleBox<R> box[AQUA_MAX_OBSTACLES];        // brute-force layout (see ObstacleBox)
+    ObstacleBox<R> ubox[AQUA_MAX_OBSTACLES + 1];   // unified {cx, cy, half_x, half_y}; [kCellNone] never collides
+    R nr2[AQUA_MAX_OBSTACLES + 4];                 // -(reach^2) of the unified entries
+    unsigned short cell16[kGridCells];             // id0 | id1 << 7 | blocked | overflow
+    unsigned long long cell[kGridCells];           // full masks (kCellBlocked = blocked); global memory only
 };
-// what the kernels read, both parts in shared memory: the boxes always (static), the cells only
-// when the culling grid is in use (World::use_grid; at the end of the dynamic shared memory, see
-// cell_bytes()), NULL otherwise
+// What the kernels read.  Brute force (cell16 == NULL): `box` = the table's box[] in shared memory.
+// Culling grid: `box` = the unified entries, `nr2`, `cell16` in shared memory (cell16 at the end of
+// the dynamic shared memory, see cell_bytes()), `cell` in global memory.
 template <typename R> struct ObstacleView {
     const ObstacleBox<R>* box;
+    const R* nr2;
+    const unsigned short* cell16;
     const unsigned long long* cell;
 };
 constexpr double kRectR2 = 6.25;  // (boat or goal radius 2.5)^2, aqua.py:72,75
@@ -216,39 +228,61 @@ __device__ __forceinline__ void obstacle_clearance(const ObstacleView<R>& tab, i
 }
 constexpr float kClearFar = 1e30f;  // initial clearance: "no obstacle near"
 
+// squared clearance of one position against one unified entry
+template <typename R>
+__device__ __forceinline__ R unified_clearance(const ObstacleBox<R>& o, R nr2, R px, R py) {
+    const R ddx = fmax(fabs(px - o.cx) - o.a, R(0));
+    const R ddy = fmax(fabs(py - o.cy) - o.b, R(0));
+    return fma(ddx, ddx, fma(ddy, ddy, nr2));
+}
+
 // same result (sign of the minimum clearance) through the culling grid
 template <typename R, int V>
 __device__ __forceinline__ void obstacle_clearance_grid(const ObstacleView<R>& tab, int k_circ,
                                                         const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
+    (void)k_circ;
+    uint32_t over = 0u;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
         const int cx = min(max((int)((float)px[j] * (kGridDim / 100.0f)), 0), kGridDim - 1);
         const int cy = min(max((int)((float)py[j] * (kGridDim / 100.0f)), 0), kGridDim - 1);
-        unsigned long long mask = tab.cell[cy * kGridDim + cx];
-        if (mask == kCellBlocked) {  // inside an obstacle's clearance region for sure
-            clr[j] = R(-1);
-            mask = 0ull;
-        }
-        while (mask != 0ull) {
-            const int k = __ffsll((long long)mask) - 1;
-            mask &= mask - 1ull;
-            const ObstacleBox<R> o = tab.box[k];
-            const bool circle = k < k_circ;
-            const R hx = circle ? R(0) : o.a, hy = circle ? R(0) : o.b;
-            const R r2 = circle ? o.a : R(kRectR2);
-            const R ddx = fmax(fabs(px[j] - o.cx) - hx, R(0));
-            const R ddy = fmax(fabs(py[j] - o.cy) - hy, R(0));
-            clr[j] = fmin(clr[j], fma(ddx, ddx, fma(ddy, ddy, -r2)));
+        const uint32_t c = tab.cell16[cy * kGridDim + cx];
+        const uint32_t i0 = c & 127u, i1 = (c >> 7) & 127u;
+        const R d0 = unified_clearance<R>(tab.box[i0], tab.nr2[i0], px[j], py[j]);
+        const R d1 = unified_clearance<R>(tab.box[i1], tab.nr2[i1], px[j], py[j]);
+        const R d = fmin(clr[j], fmin(d0, d1));
+        clr[j] = (c & kCell16Blocked) ? R(-1) : d;  // blocked: inside an obstacle's clearance region for sure
+        over |= (c & kCell16Overflow) ? (1u << j) : 0u;
+    }
+    if (over != 0u) {  // rare: a cell that lists more than two obstacles
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            if (!((over >> j) & 1u)) continue;
+            const int cx = min(max((int)((float)px[j] * (kGridDim / 100.0f)), 0), kGridDim - 1);
+            const int cy = min(max((int)((float)py[j] * (kGridDim / 100.0f)), 0), kGridDim - 1);
+            unsigned long long mask = __ldg(tab.cell + cy * kGridDim + cx);
+            while (mask != 0ull) {
+                const int k = __ffsll((long long)mask) - 1;
+                mask &= mask - 1ull;
+                clr[j] = fmin(clr[j], unified_clearance<R>(tab.box[k], tab.nr2[k], px[j], py[j]));
+            }
         }
     }
 }
 
-// brute force for the small tables of the reference, grid for dense maps
-template <typename R, int V>
+// brute force for the small tables of the reference, grid for dense maps.  GRID: 1 / 0 = the kernel is
+// compiled for launches with / without the culling grid (step_many_kernel), -1 = decided per launch
+template <typename R, int V, int GRID = -1>
 __device__ __forceinline__ void obstacle_clearance_any(const ObstacleView<R>& tab, int k_circ, int k_obst,
                                                        const R (&px)[V], const R (&py)[V], R (&clr)[V]) {
-    if (tab.cell != nullptr) obstacle_clearance_grid<R, V>(tab, k_circ, px, py, clr);
-    else obstacle_clearance<R, V>(tab, k_circ, k_obst, px, py, clr);
+    if constexpr (GRID == 1) {
+        obstacle_clearance_grid<R, V>(tab, k_circ, px, py, clr);
+    } else if constexpr (GRID == 0) {
+        obstacle_clearance<R, V>(tab, k_circ, k_obst, px, py, clr);
+    } else {
+        if (tab.cell16 != nullptr) obstacle_clearance_grid<R, V>(tab, k_circ, px, py, clr);
+        else obstacle_clearance<R, V>(tab, k_circ, k_obst, px, py, clr);
+    }
 }
 
 // same test against the float64 table in global memory (reset path: rare, always float64 so
@@ -348,12 +382,12 @@ __device__ __forceinline__ bool outside_border_f(float x, float y) {
 
 // `band` = guard band of the float32 clearance (1e-4 x the largest squared reach of the table,
 // far above its rounding error): outside the band the float32 sign is the float64 sign.
-template <typename R>
+template <typename R, int GRID = -1>
 __device__ __forceinline__ bool reset_blocked(const ObstacleView<R>& tab, const double* __restrict__ tab64,
                                               int k_circ, int k_obst, float band, float x, float y) {
     const R px[1] = {(R)x}, py[1] = {(R)y};
     R clr[1] = {R(kClearFar)};
-    obstacle_clearance_any<R, 1>(tab, k_circ, k_obst, px, py, clr);
+    obstacle_clearance_any<R, 1, GRID>(tab, k_circ, k_obst, px, py, clr);
     if constexpr (sizeof(R) == 4) {
         if (fabsf(clr[0]) <= band) return hits_obstacle_g(tab64, k_obst, (double)x, (double)y);
     }
@@ -450,7 +484,7 @@ __device__ __forceinline__ CoopResetResult coop_reset(const PhiloxKeys& keys, co
 // envs can be collected 32 at a time: the streaming / general step kernels and the stash refill of
 // the multi-step kernel.  Accept/reject decisions are float64-exact (guard band, see above).
 // ------------------------------------------------------------------------------------------
-template <typename R>
+template <typename R, int GRID = -1>
 __device__ __forceinline__ CoopResetResult reset_env_lane(const PhiloxKeys& keys, const ObstacleView<R>& tab,
                                                           const double* __restrict__ tab64, int k_circ, int k_obst,
                                                           float band, WorldFlags wf, uint32_t env_id, uint32_t ep,
@@ -465,7 +499,7 @@ __device__ __forceinline__ CoopResetResult reset_env_lane(const PhiloxKeys& keys
             o.gx = draw_pos(r.z);
             o.gy = draw_pos(r.w);
             if (n >= kResetMaxTries) { atomicAdd(forced, 1u); break; }
-            if (!(outside_border_f(o.gx, o.gy) || reset_blocked<R>(tab, tab64, k_circ, k_obst, band, o.gx, o.gy))) break;
+            if (!(outside_border_f(o.gx, o.gy) || reset_blocked<R, GRID>(tab, tab64, k_circ, k_obst, band, o.gx, o.gy))) break;
         }
     }
     if (wf.random_boat) {  // aqua.py:110-115
@@ -476,7 +510,7 @@ __device__ __forceinline__ CoopResetResult reset_env_lane(const PhiloxKeys& keys
             o.th = draw_angle(r.z);
             if (n >= kResetMaxTries) { atomicAdd(forced, 1u); break; }
             if (!(reset_reached<R>(o.gx, o.gy, o.x, o.y) || outside_border_f(o.x, o.y) ||
-                  reset_blocked<R>(tab, tab64, k_circ, k_obst, band, o.x, o.y)))
+                  reset_blocked<R, GRID>(tab, tab64, k_circ, k_obst, band, o.x, o.y)))
                 break;
         }
     }
@@ -578,13 +612,11 @@ __device__ __forceinline__ void move_env(EnvState<R>& e, const Drive<R>& dr, R n
     e.th = wrap_angle(e.th + phi);  // aqua.py:183
 
     // ---- waves, aqua.py:188-191 (after the move) ----
-    if (waves) {
+    {  // has_waves = 0 clips to [0, 0] (aqua.py:23-25,189-191): selects, no branch
         const R wmax = R(0.05);
-        e.wx = fmin(fmax(e.wx + nx, -wmax), wmax);
-        e.wy = fmin(fmax(e.wy + ny, -wmax), wmax);
-    } else {  // has_waves = 0 clips to [0, 0] (aqua.py:23-25,189-191)
-        e.wx = R(0);
-        e.wy = R(0);
+        const R wxn = fmin(fmax(e.wx + nx, -wmax), wmax), wyn = fmin(fmax(e.wy + ny, -wmax), wmax);
+        e.wx = waves ? wxn : R(0);
+        e.wy = waves ? wyn : R(0);
     }
 
     // ---- time, aqua.py:141 ----

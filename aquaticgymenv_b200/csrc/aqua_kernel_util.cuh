@@ -297,25 +297,32 @@ __device__ __forceinline__ void flush_stats(ThreadStats& t, unsigned long long* 
 
 // dynamic shared memory a launch needs for the culling grid (dense maps only), placed behind the
 // staging buffers
-constexpr size_t kCellBytes = sizeof(unsigned long long) * kGridCells;
+constexpr size_t kCellBytes = sizeof(unsigned short) * kGridCells;
 __host__ __device__ inline size_t cell_bytes(int use_grid) { return use_grid ? kCellBytes : 0; }
+constexpr int kBoxSlots = AQUA_MAX_OBSTACLES + 1;  // s_box / s_nr2 entries: the table + the entry that never collides
 
-// Copies the obstacle table of the launch (global ObstacleTable<R>) into shared memory: the boxes
-// into `s_box`, the cells of a dense map into `s_cell`; returns the view the kernels read.  The
-// caller synchronises the CTA.
+// Copies the obstacle table of the launch (global ObstacleTable<R>) into shared memory and returns
+// the view the kernels read: the brute-force entries into `s_box`, or (dense map) the unified
+// entries into `s_box`, their reaches into `s_nr2` and the 16-bit cells into `s_cell`.  The caller
+// synchronises the CTA.
 template <typename R>
-__device__ __forceinline__ ObstacleView<R> stage_table(ObstacleBox<R>* s_box, unsigned char* s_cell, const void* g_tab,
-                                                       int k_obst, bool use_grid) {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(g_tab);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(s_box);
+__device__ __forceinline__ ObstacleView<R> stage_table(ObstacleBox<R>* s_box, R* s_nr2, unsigned char* s_cell,
+                                                       const void* g_tab_, int k_obst, bool use_grid) {
+    const ObstacleTable<R>* g_tab = reinterpret_cast<const ObstacleTable<R>*>(g_tab_);
     constexpr int kWordsPerBox = sizeof(ObstacleBox<R>) / 4;
-    for (int i = threadIdx.x; i < k_obst * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
-    if (use_grid) {  // dense map: the culling grid as well
-        constexpr int kCellOff = sizeof(ObstacleBox<R>) * AQUA_MAX_OBSTACLES / 4;
-        uint32_t* cdst = reinterpret_cast<uint32_t*>(s_cell);
-        for (int i = threadIdx.x; i < kGridCells * 2; i += blockDim.x) cdst[i] = __ldg(src + kCellOff + i);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(s_box);
+    if (!use_grid) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(g_tab->box);
+        for (int i = threadIdx.x; i < k_obst * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
+        return ObstacleView<R>{s_box, s_nr2, nullptr, g_tab->cell};
     }
-    return ObstacleView<R>{s_box, use_grid ? reinterpret_cast<const unsigned long long*>(s_cell) : nullptr};
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(g_tab->ubox);
+    for (int i = threadIdx.x; i < kBoxSlots * kWordsPerBox; i += blockDim.x) dst[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < kBoxSlots; i += blockDim.x) s_nr2[i] = __ldg(g_tab->nr2 + i);
+    const uint32_t* csrc = reinterpret_cast<const uint32_t*>(g_tab->cell16);
+    uint32_t* cdst = reinterpret_cast<uint32_t*>(s_cell);
+    for (int i = threadIdx.x; i < kGridCells / 2; i += blockDim.x) cdst[i] = __ldg(csrc + i);
+    return ObstacleView<R>{s_box, s_nr2, reinterpret_cast<const unsigned short*>(s_cell), g_tab->cell};
 }
 
 // ------------------------------------------------------------------------------------------

@@ -47,6 +47,14 @@ struct PhiloxKeys {
 };
 void make_philox_keys(uint64_t seed, PhiloxKeys* out);
 
+// A small obstacle table (at most 4 circles and 4 rectangles: every layout the reference ships) as
+// kernel parameters: its entries are constant-bank operands of the clearance arithmetic, which then
+// is straight-line code without loads (step_envs, aqua_packed.cuh).  Unused entries never collide.
+struct SmallTable {
+    float c[4][4];  // circles {cx, cy, -(radius + 2.5)^2, 0}
+    float r[4][4];  // rectangles {cx, cy, half_x, half_y}
+};
+
 // Everything a kernel needs to know about the world; travels by value in the parameter block.
 struct World {
     PhiloxKeys keys;
@@ -58,7 +66,9 @@ struct World {
     float reset_band;       // guard band of the float32 reset test, see reset_blocked()
     uint8_t waves, random_boat, random_goal, autoreset;
     uint8_t use_grid;       // dense map: obstacles are culled through the cell grid of the table
+    uint8_t small_mode;     // float32 tables of <= 4 circles and <= 4 rectangles: 1 (<= 2 rectangles) or 2; else 0
     unsigned int* forced;   // device counter of forced reset accepts (AQUA_STAT_FORCED_RESETS)
+    SmallTable small;       // valid when small_mode != 0
 };
 
 struct StepArgs {
@@ -106,7 +116,7 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 // K env-steps per launch (aqua_many.cu).  tape != 0: actions[K][row_stride] in, reward / flags
 // [K][row_stride] out (either may be NULL); tape == 0: the synthetic random policy (ACTION stream)
 cudaError_t launch_step_many(int precision, int action_dtype, int tape, const StepArgs& a, LaunchGeom g, cudaStream_t s);
-cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int use_grid, int* blocks_per_sm);
+cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int tab, int* blocks_per_sm);
 cudaError_t launch_stash_init(uint4* stash, int64_t ld, cudaStream_t s);
 cudaError_t launch_reset(int precision, const StepArgs& a, const uint8_t* mask, cudaStream_t s);
 cudaError_t launch_init_state(int precision, void* planes, int64_t ld, cudaStream_t s);
@@ -138,7 +148,10 @@ size_t obstacle_table_bytes(int precision);
 // enough for the culling grid and its cell masks are unambiguous (see kCellBlocked)
 int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_host, double* tab64_host,
                           int* use_grid);
+// World::small / small_mode from the caller's rows {cx, cy, type, a, b} (same float32 values as the table)
+void fill_small_table(int precision, int k, const double* rows5, int use_grid, World* w);
 // the cell masks of a host table built by build_obstacle_tables (aqua_obstacle_grid)
 void copy_table_cells(int precision, const void* tab_host, unsigned long long* out);
+void copy_table_cells16(int precision, const void* tab_host, unsigned short* out);
 
 }  // namespace aqua

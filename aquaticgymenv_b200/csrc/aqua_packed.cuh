@@ -103,14 +103,12 @@ __device__ __forceinline__ void move_pair(EnvState<float>& A, EnvState<float>& B
     const F2 tn = th + f2(da.phi, db.phi);  // aqua.py:183
     A.th = wrap_angle(lo(tn));
     B.th = wrap_angle(hi(tn));
-    if (waves) {  // aqua.py:188-191
+    {  // aqua.py:188-191; without waves the clip range is [0, 0] (aqua.py:23-25): selects, no branch
         const F2 wxn = wx + f2(nxa, nxb), wyn = wy + f2(nya, nyb);
-        A.wx = fminf(fmaxf(lo(wxn), -0.05f), 0.05f);
-        B.wx = fminf(fmaxf(hi(wxn), -0.05f), 0.05f);
-        A.wy = fminf(fmaxf(lo(wyn), -0.05f), 0.05f);
-        B.wy = fminf(fmaxf(hi(wyn), -0.05f), 0.05f);
-    } else {
-        A.wx = B.wx = A.wy = B.wy = 0.f;
+        A.wx = waves ? fminf(fmaxf(lo(wxn), -0.05f), 0.05f) : 0.f;
+        B.wx = waves ? fminf(fmaxf(hi(wxn), -0.05f), 0.05f) : 0.f;
+        A.wy = waves ? fminf(fmaxf(lo(wyn), -0.05f), 0.05f) : 0.f;
+        B.wy = waves ? fminf(fmaxf(hi(wyn), -0.05f), 0.05f) : 0.f;
     }
     A.tw += ((A.tw & kTimeMask) != kTimeMask) ? 1u : 0u;  // aqua.py:141
     B.tw += ((B.tw & kTimeMask) != kTimeMask) ? 1u : 0u;
@@ -151,6 +149,79 @@ __device__ __forceinline__ void obstacle_clearance_pairs(const ObstacleView<floa
                 const F2 ex = x2[q] - f2(o.cx), ey = y2[q] - f2(o.cy);
                 const F2 ux = f2(fabsf(lo(ex)), fabsf(hi(ex))) - f2(o.a);
                 const F2 uy = f2(fabsf(lo(ey)), fabsf(hi(ey))) - f2(o.b);
+                const F2 ddx = f2(fmaxf(lo(ux), 0.f), fmaxf(hi(ux), 0.f));
+                const F2 ddy = f2(fmaxf(lo(uy), 0.f), fmaxf(hi(uy), 0.f));
+                const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(-(float)kRectR2)));
+                clr[2 * q] = fminf(clr[2 * q], lo(d));
+                clr[2 * q + 1] = fminf(clr[2 * q + 1], hi(d));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Small tables (World::small, at most 4 circles + 4 rectangles): the entries are kernel parameters,
+// i.e. constant-bank operands, and the tests are straight-line code: no loads, no loop, every test
+// independent of the others.  Same operations per obstacle as obstacle_clearance(); the unused
+// entries never collide and the minimum does not depend on the order, so the decision is the same.
+// mode 1: the table has at most 2 rectangles, mode 2: up to 4.
+// ------------------------------------------------------------------------------------------
+template <int V>
+__device__ __forceinline__ void obstacle_clearance_small(const SmallTable& t, int mode, const float (&px)[V],
+                                                         const float (&py)[V], float (&clr)[V]) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int j = 0; j < V; ++j) {
+            const float ddx = px[j] - t.c[u][0], ddy = py[j] - t.c[u][1];
+            clr[j] = fminf(clr[j], fmaf(ddx, ddx, fmaf(ddy, ddy, t.c[u][2])));
+        }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1 && mode != 2) break;  // kernel-uniform
+#pragma unroll
+        for (int u = 2 * half; u < 2 * half + 2; ++u) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                const float ddx = fmaxf(fabsf(px[j] - t.r[u][0]) - t.r[u][2], 0.f);
+                const float ddy = fmaxf(fabsf(py[j] - t.r[u][1]) - t.r[u][3], 0.f);
+                clr[j] = fminf(clr[j], fmaf(ddx, ddx, fmaf(ddy, ddy, -(float)kRectR2)));
+            }
+        }
+    }
+}
+
+// the same with the V positions taken in pairs (packed arithmetic)
+template <int V>
+__device__ __forceinline__ void obstacle_clearance_small_pairs(const SmallTable& t, int mode, const float (&px)[V],
+                                                               const float (&py)[V], float (&clr)[V]) {
+    F2 x2[V / 2], y2[V / 2];
+#pragma unroll
+    for (int q = 0; q < V / 2; ++q) {
+        x2[q] = f2(px[2 * q], px[2 * q + 1]);
+        y2[q] = f2(py[2 * q], py[2 * q + 1]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+#pragma unroll
+        for (int q = 0; q < V / 2; ++q) {
+            const F2 ddx = x2[q] - f2(t.c[u][0]), ddy = y2[q] - f2(t.c[u][1]);
+            const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(t.c[u][2])));
+            clr[2 * q] = fminf(clr[2 * q], lo(d));
+            clr[2 * q + 1] = fminf(clr[2 * q + 1], hi(d));
+        }
+    }
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        if (half == 1 && mode != 2) break;  // kernel-uniform
+#pragma unroll
+        for (int u = 2 * half; u < 2 * half + 2; ++u) {
+#pragma unroll
+            for (int q = 0; q < V / 2; ++q) {
+                const F2 ex = x2[q] - f2(t.r[u][0]), ey = y2[q] - f2(t.r[u][1]);
+                const F2 ux = f2(fabsf(lo(ex)), fabsf(hi(ex))) - f2(t.r[u][2]);
+                const F2 uy = f2(fabsf(lo(ey)), fabsf(hi(ey))) - f2(t.r[u][3]);
                 const F2 ddx = f2(fmaxf(lo(ux), 0.f), fmaxf(hi(ux), 0.f));
                 const F2 ddy = f2(fmaxf(lo(uy), 0.f), fmaxf(hi(uy), 0.f));
                 const F2 d = fma2(ddx, ddx, fma2(ddy, ddy, f2(-(float)kRectR2)));
@@ -234,10 +305,15 @@ __device__ __forceinline__ void draw_wave_noise_v(const PhiloxKeys& keys, uint32
 
 // One env.step() (aqua.py:135-211) for the V envs of a thread: drives and wave increments in,
 // new state in place, rewards out; returns the flags word (byte j = env j).
-template <typename R, int V>
+// `small` / `small_mode`: World::small and World::small_mode of the launch (float only; 0 = use `tab`).
+// TAB: the obstacle test the kernel is compiled for -- 0 brute force over `tab`, 1 the small table,
+// 2 the culling grid (step_many_kernel: one instantiation per kind, so that its step loop holds one
+// test only) -- or -1: chosen per launch.
+template <typename R, int V, int TAB = -1>
 __device__ __forceinline__ uint32_t step_envs(EnvState<R> (&e)[V], const Drive<R> (&dr)[V], const float (&nx)[V],
                                               const float (&ny)[V], bool waves, const ObstacleView<R>& tab,
-                                              int k_circ, int k_obst, R (&reward)[V]) {
+                                              int k_circ, int k_obst, R (&reward)[V], const SmallTable& small,
+                                              int small_mode) {
     MoveTmp<R> m[V];
     R pxn[V], pyn[V], clr[V];
     uint32_t fw = 0u;
@@ -252,8 +328,17 @@ __device__ __forceinline__ uint32_t step_envs(EnvState<R> (&e)[V], const Drive<R
             pyn[j] = e[j].y;
             clr[j] = kClearFar;
         }
-        if (tab.cell != nullptr) obstacle_clearance_grid<R, V>(tab, k_circ, pxn, pyn, clr);
-        else obstacle_clearance_pairs<V>(tab, k_circ, k_obst, pxn, pyn, clr);
+        if constexpr (TAB == 1) {
+            obstacle_clearance_small_pairs<V>(small, small_mode, pxn, pyn, clr);
+        } else if constexpr (TAB == 2) {
+            obstacle_clearance_grid<R, V>(tab, k_circ, pxn, pyn, clr);
+        } else if constexpr (TAB == 0) {
+            obstacle_clearance_pairs<V>(tab, k_circ, k_obst, pxn, pyn, clr);
+        } else {
+            if (small_mode != 0) obstacle_clearance_small_pairs<V>(small, small_mode, pxn, pyn, clr);
+            else if (tab.cell16 != nullptr) obstacle_clearance_grid<R, V>(tab, k_circ, pxn, pyn, clr);
+            else obstacle_clearance_pairs<V>(tab, k_circ, k_obst, pxn, pyn, clr);
+        }
 #pragma unroll
         for (int q = 0; q < V / 2; ++q)
             fw |= finish_pair(e[2 * q], e[2 * q + 1], m[2 * q], m[2 * q + 1], clr[2 * q], clr[2 * q + 1], reward[2 * q],
@@ -267,7 +352,18 @@ __device__ __forceinline__ uint32_t step_envs(EnvState<R> (&e)[V], const Drive<R
             pyn[j] = e[j].y;
             clr[j] = R(kClearFar);
         }
-        obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
+        if constexpr (sizeof(R) == 4 && TAB == 1) {
+            obstacle_clearance_small<V>(small, small_mode, pxn, pyn, clr);
+        } else if constexpr (TAB == 2) {
+            obstacle_clearance_any<R, V, 1>(tab, k_circ, k_obst, pxn, pyn, clr);
+        } else if constexpr (TAB == 0) {
+            obstacle_clearance_any<R, V, 0>(tab, k_circ, k_obst, pxn, pyn, clr);
+        } else if constexpr (sizeof(R) == 4) {
+            if (small_mode != 0) obstacle_clearance_small<V>(small, small_mode, pxn, pyn, clr);
+            else obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
+        } else {
+            obstacle_clearance_any<R, V>(tab, k_circ, k_obst, pxn, pyn, clr);
+        }
 #pragma unroll
         for (int j = 0; j < V; ++j) fw |= finish_env<R>(e[j], m[j], clr[j], reward[j]) << (8 * j);
     }

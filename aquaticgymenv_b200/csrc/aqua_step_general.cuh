@@ -13,10 +13,11 @@ namespace aqua {
 // ------------------------------------------------------------------------------------------
 template <typename R, int V, int ACT, bool INJECT>
 __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
+    __shared__ ObstacleBox<R> s_box[kBoxSlots];
+    __shared__ R s_nr2[kBoxSlots + 3];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
-    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_nr2, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     __syncthreads();
 
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(kMaxThreads, V == 1 ? 4 : kMinBlocks) step_ker
                 }
             }
             Pack<R, V> vrew, ox, oy, oth, owx, owy;
-            const uint32_t fw_all = step_envs<R, V>(e, dr, nx, ny, waves, tab, k_circ, k_obst, vrew.v);
+            const uint32_t fw_all = step_envs<R, V>(e, dr, nx, ny, waves, tab, k_circ, k_obst, vrew.v, p.w.small, p.w.small_mode);
             Pack<uint8_t, V> vfl;
 #pragma unroll
             for (int j = 0; j < V; ++j) {

@@ -85,7 +85,7 @@ template <typename R> __device__ __forceinline__ void stash_unpack(const uint4& 
 // Refills the records of queued envs, one lane per env, in passes of up to 32 from the tail while
 // at least `min_batch` are queued (kLanePass: full passes; 1: flush).  Warp-collective.
 // `s_rec`: the warp's records in shared memory, two uint4 per env, env warp_rel first.
-template <typename R, int V>
+template <typename R, int V, int GRID>
 __device__ __forceinline__ int refill_drain(const StepArgs& p, const ObstacleView<R>& tab, const RefillQueue<V>& rq,
                                             int n, int min_batch, uint4* s_rec, uint32_t warp_rel) {
     const int lane = (int)(threadIdx.x & 31u);
@@ -97,8 +97,8 @@ __device__ __forceinline__ int refill_drain(const StepArgs& p, const ObstacleVie
         if (lane < take) {
             const uint32_t rel = rq.rel[first + lane];
             const uint32_t ep = rq.ep[first + lane];
-            const CoopResetResult rr = reset_env_lane<R>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
-                                                         p.w.reset_band, wf, p.env_id0 + rel, ep, p.w.forced);
+            const CoopResetResult rr = reset_env_lane<R, GRID>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
+                                                               p.w.reset_band, wf, p.env_id0 + rel, ep, p.w.forced);
             uint4 a, b;
             stash_pack(rr, ep, a, b);
             s_rec[2 * (rel - warp_rel)] = a;
@@ -127,15 +127,17 @@ __device__ __forceinline__ void philox2x32_10_v(uint32_t (&c0)[N], uint32_t (&c1
     }
 }
 
-template <typename R, int V, int ACT, bool TAPE>
+// TAB: the obstacle test of the launch's table -- 0 brute force, 1 small table (World::small), 2 culling grid
+template <typename R, int V, int ACT, bool TAPE, int TAB>
 __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8)) step_many_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
+    __shared__ ObstacleBox<R> s_box[kBoxSlots];
+    __shared__ R s_nr2[kBoxSlots + 3];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ DriveSlot<R> s_drive[3];
     // dynamic shared memory: the culling grid of a dense map, one refill queue per warp, the stash
     // records of the CTA's envs (2 x 16 bytes each)
-    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage, p.w.tab, p.w.k_obst, p.w.use_grid != 0);
-    RefillQueue<V>* const s_rq = reinterpret_cast<RefillQueue<V>*>(s_stage + cell_bytes(p.w.use_grid));
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_nr2, s_stage, p.w.tab, p.w.k_obst, TAB == 2);
+    RefillQueue<V>* const s_rq = reinterpret_cast<RefillQueue<V>*>(s_stage + cell_bytes(TAB == 2));
     uint4* const s_rec_cta = reinterpret_cast<uint4*>(s_rq + (blockDim.x >> 5));
     if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
@@ -157,7 +159,8 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     const uint32_t rel = warp_rel + lane * V;                                                      // this thread's
     const int nvalid = rel >= n ? 0 : (int)min((uint32_t)V, n - rel);
     const bool waves = p.w.waves != 0, autoreset = p.w.autoreset != 0;
-    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ;
+    const int k_obst = p.w.k_obst, k_circ = p.w.k_circ, small_mode = p.w.small_mode;
+    const int steps = (int)p.steps;  // the launcher bounds it to 2^31 - 1
     uint32_t valid_mask = 0u;  // 0xff in byte j for the envs of this thread that exist
 #pragma unroll
     for (int j = 0; j < V; ++j) valid_mask |= (j < nvalid ? 0xffu : 0u) << (8 * j);
@@ -220,8 +223,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
         constexpr int kActBytes = act_bytes<ACT, V>();
         const bool has = nvalid > 0;
         const char* act_ptr_k = TAPE ? p.act0 + (size_t)rel * (kActBytes / V) : nullptr;
-        char* rew_ptr_k = (p.reward != nullptr && has) ? p.rew0 + (size_t)rel * sizeof(R) : nullptr;
-        uint8_t* flg_ptr_k = (p.flags != nullptr && has) ? p.flg0 + rel : nullptr;
+        // (the row pointers advance every step whether or not the caller wants the output)
+        const bool has_rew = p.reward != nullptr && has, has_flg = p.flags != nullptr && has;
+        char* rew_ptr_k = p.rew0 + (size_t)rel * sizeof(R);
+        uint8_t* flg_ptr_k = p.flg0 + rel;
+        const size_t rew_row = (size_t)p.row_stride * sizeof(R), flg_row = (size_t)p.row_stride;
         // the actions of a step are loaded two steps ahead (a row of the tape comes from DRAM)
         const size_t act_row = (size_t)p.row_stride * (kActBytes / V);
         ActVals<ACT, V> act_next, act_next2;
@@ -229,16 +235,16 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
         for (int j = 0; j < ActVals<ACT, V>::N; ++j) act_next.w[j] = act_next2.w[j] = 0u;
         if (TAPE && has) {
             act_next = fetch_actions<ACT, V>(act_ptr_k, V);
-            if (p.steps > 1) act_next2 = fetch_actions<ACT, V>(act_ptr_k + act_row, V);
+            if (steps > 1) act_next2 = fetch_actions<ACT, V>(act_ptr_k + act_row, V);
             act_ptr_k += 2 * act_row;  // the row of step k + 2
         }
 
-        for (int64_t k = 0;; ++k) {
+        for (int k = 0;; ++k) {
             // ---- the ONE place where records are drawn: in full passes, all lanes busy; a flush only
             // when an env waits for its record.  What is still queued after the last step stays
             // undrawn (its record keeps a stale tag): the next launch queues it again ----
             if (autoreset && n_q >= thr) {
-                n_q = refill_drain<R, V>(p, tab, rq, n_q, thr, s_rec, warp_rel);
+                n_q = refill_drain<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, thr, s_rec, warp_rel);
                 thr = kLanePass;
             }
             if (__any_sync(full, pend != 0u)) {  // rare: the records of waiting envs are there now
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                 n_q = refill_push<V>(rq, n_q, pend, rel, next);
                 pend = 0u;
             }
-            if (k == p.steps) break;
+            if (k == steps) break;
 
             // ---- actions: this step's were loaded during the previous one ----
             Drive<R> dr[V];
@@ -266,7 +272,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
             if constexpr (TAPE) {
                 const ActVals<ACT, V> act = act_next;
                 act_next = act_next2;
-                if (k + 2 < p.steps && has) {
+                if (k + 2 < steps && has) {
                     act_next2 = fetch_actions<ACT, V>(act_ptr_k, V);
                     act_ptr_k += act_row;
                 }
@@ -297,7 +303,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                         for (int j = 0; j < V; ++j) st.bad += (j < nvalid && act.w[j] > 2u) ? 1u : 0u;
                     }
                 }
-                if (waves) {
+                {  // also without waves (the increments are unused then): no branch in the step's code
                     uint32_t tw[V];
 #pragma unroll
                     for (int j = 0; j < V; ++j) tw[j] = e[j].tw;
@@ -315,7 +321,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                     w1[j] = e[j].tw;
                 }
                 philox2x32_10_v<V>(a0, a1, p.w.keys.action, (uint32_t)(step >> 32));
-                if (waves) philox2x32_10_v<V>(w0, w1, p.w.keys.noise, 0u);
+                philox2x32_10_v<V>(w0, w1, p.w.keys.noise, 0u);
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     if constexpr (ACT == AQUA_ACT_F32X2) {
@@ -327,16 +333,14 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                         dr[j].h = d.h;
                         dr[j].chord = d.chord;
                     }
-                    if (waves) {
-                        nx[j] = draw_noise(w0[j]);
-                        ny[j] = draw_noise(w1[j]);
-                    }
+                    nx[j] = draw_noise(w0[j]);
+                    ny[j] = draw_noise(w1[j]);
                 }
             }
 
             // ---- the step ----
             R reward[V];
-            uint32_t fw = step_envs<R, V>(e, dr, nx, ny, waves, tab, k_circ, k_obst, reward);
+            uint32_t fw = step_envs<R, V, TAB>(e, dr, nx, ny, waves, tab, k_circ, k_obst, reward, p.w.small, small_mode);
             fw &= valid_mask;
             if (nvalid != V) {
 #pragma unroll
@@ -349,19 +353,19 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
             if (any_done) st.add_flags(fw, 0);                 // (the env-steps are counted once, after the loop)
 
             // ---- outputs of step k (full-width: a partial thread writes into the row's padding) ----
-            if (rew_ptr_k != nullptr) {
+            if (has_rew) {
                 Pack<R, V> vrew;
 #pragma unroll
                 for (int j = 0; j < V; ++j) vrew.v[j] = reward[j];
                 st_pack<R, V>(reinterpret_cast<R*>(rew_ptr_k), vrew);
-                rew_ptr_k += (size_t)p.row_stride * sizeof(R);
             }
-            if (flg_ptr_k != nullptr) {
+            if (has_flg) {
                 if constexpr (V == 4) *reinterpret_cast<uint32_t*>(flg_ptr_k) = fw;
                 else if constexpr (V == 2) *reinterpret_cast<uint16_t*>(flg_ptr_k) = (uint16_t)fw;
                 else *flg_ptr_k = (uint8_t)fw;
-                flg_ptr_k += p.row_stride;
             }
+            rew_ptr_k += rew_row;
+            flg_ptr_k += flg_row;
 
             // ---- finished envs: the next episode comes from the stash ----
             if (!autoreset) {
@@ -394,7 +398,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
             }
         }
 
-        st.steps += (uint32_t)nvalid * (uint32_t)p.steps;
+        st.steps += (uint32_t)nvalid * (uint32_t)steps;
 
         // ---- stash out (records whose refill is still queued go back with their old tag) ----
         if (autoreset) {
@@ -429,14 +433,6 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     }
     __syncthreads();
     flush_stats(st, s_stats, p.stats);
-}
-
-// fresh stash: no record drawn yet
-__global__ void stash_init_kernel(uint4* stash, int64_t ld) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ld) return;
-    stash[2 * i] = make_uint4(0u, 0u, 0u, 0u);
-    stash[2 * i + 1] = make_uint4(0u, 0u, 0u, kStashEmpty);
 }
 
 }  // namespace aqua

@@ -53,7 +53,7 @@ template <typename R, int ACT, bool WAVES>
 __global__ void __launch_bounds__(kNarrowThreads, 8) step_narrow_kernel(const __grid_constant__ StepArgs p) {
     __shared__ WarpResetQueue<1> s_wq[kNarrowThreads / 32];
     const ObstacleTable<R>* const g_tab = reinterpret_cast<const ObstacleTable<R>*>(p.w.tab);
-    const ObstacleView<R> tab{g_tab->box, p.w.use_grid ? g_tab->cell : nullptr};
+    const ObstacleView<R> tab{p.w.use_grid ? g_tab->ubox : g_tab->box, g_tab->nr2, p.w.use_grid ? g_tab->cell16 : nullptr, g_tab->cell};
 
 #if AQUA_PDL
     // Programmatic dependent launch (launch_step sets the attribute): the CTAs of this launch may
@@ -91,7 +91,12 @@ __global__ void __launch_bounds__(kNarrowThreads, 8) step_narrow_kernel(const __
         move_env<R>(e[0], dr[0], (R)nx, (R)ny, WAVES, m);
         const R pxn[1] = {e[0].x}, pyn[1] = {e[0].y};
         R clr[1] = {R(kClearFar)};
-        obstacle_clearance_any<R, 1>(tab, p.w.k_circ, p.w.k_obst, pxn, pyn, clr);
+        if constexpr (sizeof(R) == 4) {
+            if (p.w.small_mode != 0) obstacle_clearance_small<1>(p.w.small, p.w.small_mode, pxn, pyn, clr);
+            else obstacle_clearance_any<R, 1>(tab, p.w.k_circ, p.w.k_obst, pxn, pyn, clr);
+        } else {
+            obstacle_clearance_any<R, 1>(tab, p.w.k_circ, p.w.k_obst, pxn, pyn, clr);
+        }
         R reward;
         fw = finish_env<R>(e[0], m, clr[0], reward);
         st.add_flags(fw, 1);

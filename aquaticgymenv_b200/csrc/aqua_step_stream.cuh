@@ -100,12 +100,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 template <typename R, int V, int ACT, bool WAVES, bool TMA>
 __global__ void __launch_bounds__(kMaxThreads, kMinBlocks)
 step_stream_kernel(const __grid_constant__ StepArgs p) {
-    __shared__ ObstacleBox<R> s_box[AQUA_MAX_OBSTACLES];
+    __shared__ ObstacleBox<R> s_box[kBoxSlots];
+    __shared__ R s_nr2[kBoxSlots + 3];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ WarpResetQueue<V> s_wq[kMaxThreads / 32];
     __shared__ DriveSlot<R> s_drive[3];
     __shared__ __align__(8) unsigned long long s_bar[TMA ? kMaxThreads / 32 : 1][2];  // [warp][buffer]
-    const ObstacleView<R> tab = stage_table<R>(s_box, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
+    const ObstacleView<R> tab = stage_table<R>(s_box, s_nr2, s_stage + stage_bytes<R, V>(), p.w.tab, p.w.k_obst, p.w.use_grid != 0);
     if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
@@ -301,7 +302,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
             }
-            fw = step_envs<R, V>(e, dr, nx, ny, WAVES, tab, k_circ, k_obst, vrew.v);
+            fw = step_envs<R, V>(e, dr, nx, ny, WAVES, tab, k_circ, k_obst, vrew.v, p.w.small, p.w.small_mode);
             st.add_flags(fw, V);
 #pragma unroll
             for (int j = 0; j < V; ++j) st.add_env<R>(vrew.v[j]);

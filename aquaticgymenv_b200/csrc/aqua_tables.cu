@@ -115,7 +115,37 @@ template <typename R> static bool fill_table(int k, const double* rows5, Obstacl
             const unsigned long long m = cell_mask(k, rows5, cx, cy, &blocked);
             if (!blocked && m == kCellBlocked) grid_ok = false;  // a genuine full mask: ambiguous
             t->cell[cy * kGridDim + cx] = m;
+            // the 16-bit word the kernels read: the first two listed obstacles, blocked, overflow
+            uint32_t c = kCellNone | (kCellNone << 7);
+            if (blocked) {
+                c |= kCell16Blocked;
+            } else {
+                int found = 0;
+                for (int i = 0; i < k; ++i)
+                    if ((m >> i) & 1ull) {
+                        if (found == 0) c = (c & ~127u) | (uint32_t)i;
+                        else if (found == 1) c = (c & ~(127u << 7)) | ((uint32_t)i << 7);
+                        ++found;
+                    }
+                if (found > 2) c |= kCell16Overflow;
+            }
+            t->cell16[cy * kGridDim + cx] = (unsigned short)c;
         }
+    // unified entries: a circle is a box of zero extents and reach radius + 2.5
+    for (int i = 0; i <= AQUA_MAX_OBSTACLES; ++i) {
+        t->ubox[i].cx = t->ubox[i].cy = t->ubox[i].a = t->ubox[i].b = R(0);
+        t->nr2[i] = R(1e30);  // never collides (kCellNone, unused rows)
+    }
+    for (int i = 0; i < k; ++i) {
+        const double* o = rows5 + 5 * i;
+        const bool circle = o[2] == 0.0;
+        t->ubox[i].cx = (R)o[0];
+        t->ubox[i].cy = (R)o[1];
+        t->ubox[i].a = circle ? R(0) : (R)(o[3] / 2);
+        t->ubox[i].b = circle ? R(0) : (R)(o[4] / 2);
+        const double reach = circle ? o[3] + 2.5 : 2.5;
+        t->nr2[i] = circle ? -(R)(reach * reach) : R(-kRectR2);
+    }
     for (int i = 0; i < k; ++i) {
         const double* o = rows5 + 5 * i;
         const bool circle = o[2] == 0.0;
@@ -153,6 +183,43 @@ int build_obstacle_tables(int precision, int k, const double* rows5, void* tab_h
         d[4] = reach * reach;
     }
     return k_circ;
+}
+
+void fill_small_table(int precision, int k, const double* rows5, int use_grid, World* w) {
+    // entries that never collide: a circle of squared reach -1e30, a rectangle far outside the world
+    for (int i = 0; i < 4; ++i) {
+        const float cdummy[4] = {0.f, 0.f, 1e30f, 0.f}, rdummy[4] = {1e4f, 1e4f, 0.f, 0.f};
+        memcpy(w->small.c[i], cdummy, sizeof cdummy);
+        memcpy(w->small.r[i], rdummy, sizeof rdummy);
+    }
+    w->small_mode = 0;
+    if (precision != AQUA_F32 || k <= 0 || use_grid) return;
+    ObstacleTable<float>* t = new ObstacleTable<float>;
+    double sorted[AQUA_MAX_OBSTACLES * 5];
+    const int k_circ = sorted_rows(k, rows5, sorted);
+    fill_table<float>(k, sorted, t);  // the very values the generic kernels read
+    if (k_circ <= 4 && k - k_circ <= 4) {
+        for (int i = 0; i < k_circ; ++i) {
+            w->small.c[i][0] = t->box[i].cx;
+            w->small.c[i][1] = t->box[i].cy;
+            w->small.c[i][2] = -t->box[i].a;
+        }
+        for (int i = k_circ; i < k; ++i) {
+            float* r = w->small.r[i - k_circ];
+            r[0] = t->box[i].cx;
+            r[1] = t->box[i].cy;
+            r[2] = t->box[i].a;
+            r[3] = t->box[i].b;
+        }
+        w->small_mode = (k - k_circ) > 2 ? 2 : 1;
+    }
+    delete t;
+}
+
+void copy_table_cells16(int precision, const void* tab_host, unsigned short* out) {
+    const unsigned short* cell = precision == AQUA_F64 ? reinterpret_cast<const ObstacleTable<double>*>(tab_host)->cell16
+                                                        : reinterpret_cast<const ObstacleTable<float>*>(tab_host)->cell16;
+    memcpy(out, cell, sizeof(unsigned short) * kGridCells);
 }
 
 void copy_table_cells(int precision, const void* tab_host, unsigned long long* out) {

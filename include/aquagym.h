@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define AQUAGYM_ABI_VERSION 2
+#define AQUAGYM_ABI_VERSION 3
 
 typedef struct aqua_env aqua_env;
 
@@ -249,10 +249,21 @@ int aqua_get_stats(aqua_env* env, void* stream, int64_t* out_host, int clear);
  *                cx = (int)(float(px) * AQUA_GRID_DIM / 100) clamped: bit i set = row i may be
  *                reached from that cell; AQUA_CELL_BLOCKED = every point of the cell collides
  *   use_grid_out : 1 if the kernels cull this table through the grid, 0 if they test all rows */
-#define AQUA_GRID_DIM 48
+#define AQUA_GRID_DIM 96
 #define AQUA_CELL_BLOCKED 0xFFFFFFFFFFFFFFFFull
 int aqua_obstacle_grid(const double* obstacles, int n_obstacles, double* rows_out, uint64_t* cells_out,
                        int* use_grid_out);
+/* The same plus the 16-bit word the kernels actually read per position (ABI version 3):
+ *   cells16_out : HOST uint16[AQUA_GRID_DIM * AQUA_GRID_DIM] or NULL: bits 0-6 and 7-13 = the first
+ *                 two rows listed in the cell's mask (AQUA_CELL16_NONE = none; both are always
+ *                 tested), AQUA_CELL16_BLOCKED = every point of the cell collides,
+ *                 AQUA_CELL16_OVERFLOW = the mask lists more than two rows (the kernel then walks
+ *                 the full mask for that position) */
+#define AQUA_CELL16_NONE 64
+#define AQUA_CELL16_BLOCKED 0x4000
+#define AQUA_CELL16_OVERFLOW 0x8000
+int aqua_obstacle_grid_ex(const double* obstacles, int n_obstacles, double* rows_out, uint64_t* cells_out,
+                          uint16_t* cells16_out, int* use_grid_out);
 
 #ifdef __cplusplus
 }

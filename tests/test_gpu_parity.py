@@ -528,6 +528,36 @@ def test_step_many_equals_stepwise(name, n, K, precision, many_v, monkeypatch):
     b.close()
 
 
+@pytest.mark.parametrize("name", ["v1_discrete", "v2_continuous", "v1_discrete_nowaves"])
+@pytest.mark.parametrize("many_v", ["1", "2", "4"])
+def test_small_table_in_constant_bank_equals_shared_memory_table(name, many_v, monkeypatch):
+    """Layouts of at most 4 circles + 4 rectangles are tested from kernel parameters (World::small,
+    straight-line code); AQUA_SMALL_TABLE=0 makes the same library read the shared-memory table in
+    loops like any larger layout.  Same rewards, flags, state and statistics, bit for bit, through
+    aqua_step_many and through the single-step kernels (wide and narrow geometry)."""
+    torch = _torch()
+    monkeypatch.setenv("AQUA_MANY_V", many_v)
+    cfg = _cfg(name, seed=77, base=31)
+    n, K = 40000, 120
+    outs = []
+    for small in ("1", "0"):
+        monkeypatch.setenv("AQUA_SMALL_TABLE", small)
+        env = _make_gpu(cfg, n, "float32", autoreset=True, geometry="wide" if many_v == "4" else "narrow")
+        env.reset()
+        tape = _tape(env, K)
+        r, f = env.step_many(tape)
+        for t in range(20):
+            env.step_flags(env.random_actions(K + t))
+        outs.append((r.cpu().numpy(), f.cpu().numpy(), env.get_state().cpu().numpy(), env.reward.cpu().numpy().copy(),
+                     env.stats()))
+        env.close()
+    a, b = outs
+    assert int((a[1] & 2).sum()) > 0  # obstacles or borders were hit
+    for x, y in zip(a[:4], b[:4]):
+        assert np.array_equal(x, y)
+    assert a[4] == b[4]
+
+
 @pytest.mark.parametrize("precision", ["float64", "float32"])
 def test_step_many_interleaved_with_single_steps(precision):
     """Single-step launches advance episodes without touching the stash: the next step_many finds

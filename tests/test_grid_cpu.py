@@ -116,3 +116,30 @@ def test_rows_are_circles_first_with_squared_reach():
     rows, _, _ = N.obstacle_grid(table)
     assert np.allclose(rows[0], [15.0, 75.0, 0.0, 0.0, 7.5 ** 2])        # circle: radius + 2.5
     assert np.allclose(rows[1], [65.0, 85.0, 2.5, 2.5, 2.5 ** 2])        # rectangle: half extents, 2.5
+
+
+@pytest.mark.parametrize("k", [13, 40, 64])
+def test_cell16_words_follow_the_masks(k):
+    """The 16-bit word the kernels read per position (aqua_obstacle_grid_ex) is the cell's mask in
+    compact form: its first two obstacles (both always tested; 64 = the entry that never collides),
+    the blocked mark, and the overflow bit exactly where the mask lists more than two."""
+    rs = np.random.RandomState(900 + k)
+    table = _random_table(rs, k) if k < 64 else np.load(os.path.join(GOLDEN, "dense64_table.npy"))
+    rows, cells, cells16, use_grid = N.obstacle_grid16(table)
+    assert use_grid
+    overflow_seen = 0
+    for cy in range(G):
+        for cx in range(G):
+            m, c = int(cells[cy, cx]), int(cells16[cy, cx])
+            i0, i1 = c & 127, (c >> 7) & 127
+            if m == N.CELL_BLOCKED:
+                assert c & N.CELL16_BLOCKED and not c & N.CELL16_OVERFLOW and i0 == i1 == N.CELL16_NONE
+                continue
+            assert not c & N.CELL16_BLOCKED
+            bits = [i for i in range(len(rows)) if (m >> i) & 1]
+            want = (bits + [N.CELL16_NONE, N.CELL16_NONE])[:2]
+            assert [i0, i1] == want
+            assert bool(c & N.CELL16_OVERFLOW) == (len(bits) > 2)
+            overflow_seen += len(bits) > 2
+    if k == 64:  # the stress map: overflow cells exist (the fallback is exercised) but are rare
+        assert 0 < overflow_seen < 0.03 * G * G
