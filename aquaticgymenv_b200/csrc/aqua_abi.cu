@@ -76,7 +76,8 @@ struct aqua_env {
     int64_t* d_stats_out = nullptr;
     uint32_t* d_tile_ctr = nullptr;  // kTileCounters counter sets, handed out round robin per launch
     unsigned int* d_forced = nullptr;  // AQUA_STAT_FORCED_RESETS
-    uint4* d_stash = nullptr;          // step_many: pre-drawn next episodes, 32 bytes per env (lazy)
+    uint4* d_stash = nullptr;          // step_many: ring of pre-drawn episodes, 4 x 32 bytes per env + tags (lazy)
+    uint32_t* d_stash_tag = nullptr;
     void* d_term = nullptr;            // keep_terminal: 5 planes [ld]
     bool owns_term = false;
     unsigned launch_seq = 0;
@@ -111,6 +112,7 @@ aqua::StepArgs base_args(aqua_env* env) {
     a.stats = env->d_slots;
     a.term = env->d_term;
     a.stash = env->d_stash;
+    a.stash_tag = env->d_stash_tag;
     return a;
 }
 
@@ -428,13 +430,15 @@ int aqua_random_actions(aqua_env* env, void* stream, uint64_t step_index, void* 
 
 namespace {
 
-// the stash of step_many_kernel, allocated on first use (32 bytes per env; not capturable)
+// the episode ring of step_many_kernel, allocated on first use (144 bytes per env; not capturable)
 int ensure_stash(aqua_env* env, cudaStream_t s) {
     if (env->d_stash != nullptr) return AQUA_OK;
+    const size_t depth = (size_t)aqua::stash_ring_depth();
     void* ptr = nullptr;
-    AQ_CUDA(cudaMalloc(&ptr, (size_t)env->ld * 32));
+    AQ_CUDA(cudaMalloc(&ptr, (size_t)env->ld * depth * 36));  // records, then the tag plane
     env->d_stash = static_cast<uint4*>(ptr);
-    AQ_CUDA(aqua::launch_stash_init(env->d_stash, env->ld, s));
+    env->d_stash_tag = reinterpret_cast<uint32_t*>(static_cast<char*>(ptr) + (size_t)env->ld * depth * 32);
+    AQ_CUDA(aqua::launch_stash_init(env->d_stash_tag, (int64_t)((size_t)env->ld * depth), s));
     return AQUA_OK;
 }
 

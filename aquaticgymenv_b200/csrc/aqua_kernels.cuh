@@ -102,7 +102,8 @@ struct StepArgs {
     // multi-step kernel (step_many_kernel): rows of the action tape / reward / flags outputs are
     // row_stride envs apart; stash = one 32-byte record per env with the pre-drawn next episode
     int64_t row_stride;
-    uint4* stash;
+    uint4* stash;          // the ring: [env][kRingDepth] records of 32 bytes
+    uint32_t* stash_tag;   // [env][kRingDepth]: the episode each slot holds
 };
 
 struct LaunchGeom {
@@ -117,7 +118,8 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 // [K][row_stride] out (either may be NULL); tape == 0: the synthetic random policy (ACTION stream)
 cudaError_t launch_step_many(int precision, int action_dtype, int tape, const StepArgs& a, LaunchGeom g, cudaStream_t s);
 cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int tab, int* blocks_per_sm);
-cudaError_t launch_stash_init(uint4* stash, int64_t ld, cudaStream_t s);
+cudaError_t launch_stash_init(uint32_t* stash_tag, int64_t n_tags, cudaStream_t s);
+int stash_ring_depth();
 cudaError_t launch_reset(int precision, const StepArgs& a, const uint8_t* mask, cudaStream_t s);
 cudaError_t launch_init_state(int precision, void* planes, int64_t ld, cudaStream_t s);
 cudaError_t launch_random_actions(const World& w, int64_t n, uint64_t step_index, void* actions,

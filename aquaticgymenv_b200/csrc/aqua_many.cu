@@ -53,18 +53,18 @@ cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int
     return many_dispatch(precision, v, tab, action_dtype, tape, c);
 }
 
-// fresh stash: no record drawn yet
-__global__ void stash_init_kernel(uint4* stash, int64_t ld) {
+// fresh ring: no slot holds an episode
+__global__ void stash_init_kernel(uint32_t* stash_tag, int64_t n_tags) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= ld) return;
-    stash[2 * i] = make_uint4(0u, 0u, 0u, 0u);
-    stash[2 * i + 1] = make_uint4(0u, 0u, 0u, kStashEmpty);
+    if (i < n_tags) stash_tag[i] = kStashEmpty;
 }
 
-cudaError_t launch_stash_init(uint4* stash, int64_t ld, cudaStream_t s) {
+cudaError_t launch_stash_init(uint32_t* stash_tag, int64_t n_tags, cudaStream_t s) {
     const int threads = 256;
-    stash_init_kernel<<<(int)((ld + threads - 1) / threads), threads, 0, s>>>(stash, ld);
+    stash_init_kernel<<<(int)((n_tags + threads - 1) / threads), threads, 0, s>>>(stash_tag, n_tags);
     return cudaGetLastError();
 }
+
+int stash_ring_depth() { return kRingDepth; }
 
 }  // namespace aqua

@@ -17,9 +17,10 @@ struct ManyCall {
     int* out;
 };
 
-// dynamic shared memory of a launch: culling grid, refill queues, stash records
+// dynamic shared memory of a launch: culling grid, refill queues, stash records, the lanes' records in the making
 template <int V> static size_t many_smem(int threads, int use_grid) {
-    return cell_bytes(use_grid) + (size_t)(threads / 32) * sizeof(RefillQueue<V>) + (size_t)threads * V * 32;
+    return cell_bytes(use_grid) + (size_t)(threads / 32) * sizeof(RefillQueue<V>) + (size_t)threads * V * 32 +
+           (size_t)threads * sizeof(LaneWork);
 }
 
 template <typename R, int V, int ACT, bool TAPE, int TAB> static cudaError_t many_call(const ManyCall& c) {

@@ -11,17 +11,24 @@
 //
 // Auto-reset without a stall: the state of an episode's first step depends only on (env id,
 // episode index), never on how the previous episode ended, so it is drawn AHEAD OF TIME.  Every env
-// has a 32-byte "stash" record = the reset state of the episode after the current one, tagged with
-// that episode's index: in global memory between launches, in shared memory while a launch runs
-// (read once before and written back once after the K steps, coalesced).  When an env finishes, its
-// owner swaps the record in (two 16-byte shared-memory loads) and goes on with the next step; the
-// env is queued for a refill of its record, and
-// the warp refills 32 queued envs at a time with one LANE per env (reset_env_lane: the reference's
-// rejection loops, aqua.py:100-126, all lanes busy).  A record whose tag is not the episode wanted
-// (first launch, or the single-step kernels advanced the episode meanwhile, or the env finished
-// again before its refill ran) is queued for a refill like any other and drawn at once when its env
-// finishes first, so the stash is a cache: results do not depend on it
-// (test_step_many_equals_stepwise, test_step_many_interleaved_with_single_steps).
+// owns a RING of kRingDepth 32-byte records in global memory: slot e mod kRingDepth holds the reset
+// state of episode e, tagged e (the tags also sit in a plane of their own, 16 bytes per env).
+//   * The record of each env's NEXT episode is in shared memory.  When an env finishes, its owner
+//     swaps that record in (two 16-byte shared-memory loads), starts an asynchronous copy
+//     (cp.async) of the following slot from the ring into the same place, and queues the slot it
+//     used up for the episode kRingDepth ahead.
+//   * Queued records are drawn in ROUNDS of one try per lane (ring_round): a lane carries one record
+//     through the reference's rejection loops (aqua.py:100-126), one try per round, and takes the next
+//     queued record as soon as its own is accepted.  A round runs when 32 records are queued or in the
+//     making, so every round has all lanes busy and the rejection loops of different envs never wait
+//     for the unluckiest one; between rounds the lanes' records sit in shared memory.
+//   * A launch first reads the tags of its envs and queues every slot that does not hold one of the
+//     env's next kRingDepth episodes (still queued when the previous launch ended; never drawn; or a
+//     single-step launch / aqua_set_state moved the episode on).
+// An env that finishes kRingDepth times before its used-up slots were drawn again finds a record with
+// the wrong tag: everything queued is then drawn before the next step.  The ring is thus a cache:
+// results do not depend on it (test_step_many_equals_stepwise,
+// test_step_many_interleaved_with_single_steps).
 #pragma once
 
 #include "aqua_kernel_util.cuh"
@@ -82,32 +89,96 @@ template <typename R> __device__ __forceinline__ void stash_unpack(const uint4& 
     e.tw = r1.w << AQUA_TIME_BITS;
 }
 
-// Refills the records of queued envs, one lane per env, in passes of up to 32 from the tail while
-// at least `min_batch` are queued (kLanePass: full passes; 1: flush).  Warp-collective.
-// `s_rec`: the warp's records in shared memory, two uint4 per env, env warp_rel first.
+constexpr int kRingDepth = 4;  // records per env; divides the episode range (2^21), so slot = episode & 3
+constexpr uint32_t kNoWork = 0xffffffffu;
+
+// the record a lane is drawing: env (relative to env_begin; kNoWork = idle), episode, try index
+// (bit 31: the goal is accepted, the boat is being drawn) and the accepted goal
+struct LaneWork {
+    uint32_t rel, ep, n;
+    float gx, gy;
+};
+
+// One round of the launch's record drawing (warp-collective): idle lanes take queued records from
+// the tail of the queue, then every busy lane evaluates ONE try of its record's sampling sequence
+// (try n = Philox(env, episode, n, RESET): the goal candidate while the goal is open, then the boat
+// candidate -- exactly the sequence of reset_env_lane / aqua.py:100-126, accept decisions
+// float64-exact).  A lane whose boat is accepted writes the record to the ring and is idle again.
+#ifndef AQUA_RING_INLINE
+#define AQUA_RING_INLINE 1
+#endif
+#if AQUA_RING_INLINE
+#define AQUA_RING_FN __device__ __forceinline__
+#else
+#define AQUA_RING_FN __device__ __noinline__
+#endif
 template <typename R, int V, int GRID>
-__device__ __forceinline__ int refill_drain(const StepArgs& p, const ObstacleView<R>& tab, const RefillQueue<V>& rq,
-                                            int n, int min_batch, uint4* s_rec, uint32_t warp_rel) {
-    const int lane = (int)(threadIdx.x & 31u);
-    const WorldFlags wf{p.w.waves != 0, p.w.random_boat != 0, p.w.random_goal != 0};
-    __syncwarp();  // queue entries are visible to the whole warp
-    while (n >= min_batch && n > 0) {
-        const int take = min(n, 32);
-        const int first = n - take;
-        if (lane < take) {
-            const uint32_t rel = rq.rel[first + lane];
-            const uint32_t ep = rq.ep[first + lane];
-            const CoopResetResult rr = reset_env_lane<R, GRID>(p.w.keys, tab, p.w.tab64, p.w.k_circ, p.w.k_obst,
-                                                               p.w.reset_band, wf, p.env_id0 + rel, ep, p.w.forced);
-            uint4 a, b;
-            stash_pack(rr, ep, a, b);
-            s_rec[2 * (rel - warp_rel)] = a;
-            s_rec[2 * (rel - warp_rel) + 1] = b;
+AQUA_RING_FN void ring_round(const StepArgs& p, const ObstacleView<R>& tab, const RefillQueue<V>& rq,
+                                           int& n_q, int& n_act, LaneWork* sw) {
+    const unsigned full = 0xffffffffu;
+    LaneWork w = *sw;  // the lane's record lives in shared memory between rounds (rounds are rare)
+    const unsigned lt = (1u << (threadIdx.x & 31u)) - 1u;
+    const bool random_goal = p.w.random_goal != 0, random_boat = p.w.random_boat != 0;
+    const unsigned mi = __ballot_sync(full, w.rel == kNoWork);
+    if (n_q > 0 && mi != 0u) {  // warp-uniform
+        const int rank = __popc(mi & lt);
+        if (w.rel == kNoWork && rank < n_q) {
+            w.rel = rq.rel[n_q - 1 - rank];
+            w.ep = rq.ep[n_q - 1 - rank];
+            w.n = random_goal ? 0u : 0x80000000u;
+            w.gx = 25.f;  // aqua.py:107
+            w.gy = 80.f;
         }
-        n = first;
+        n_q -= min(n_q, __popc(mi));
     }
-    __syncwarp();  // orders the record stores before the owners' loads (same warp)
-    return n;
+    if (w.rel != kNoWork) {
+        const uint32_t env_id = p.env_id0 + w.rel;
+        const bool boat = (w.n >> 31) != 0u;
+        const uint32_t nt = w.n & 0x7fffffffu;
+        bool fin = false;
+        float x = 85.f, y = 45.f, th = 0.f;  // aqua.py:117
+        if (boat && !random_boat) {
+            fin = true;
+        } else {
+            const uint4 r = philox_env(p.w.keys, env_id, w.ep, nt, kStreamReset);
+            const float cx = draw_pos(boat ? r.x : r.z), cy = draw_pos(boat ? r.y : r.w);
+            const bool force = nt + 1u >= kResetMaxTries;  // bounded loop: this try is accepted as is
+            bool ok = true;
+            if (force) {
+                atomicAdd(p.w.forced, 1u);
+            } else {
+                ok = !(outside_border_f(cx, cy) || (boat && reset_reached<R>(w.gx, w.gy, cx, cy)) ||
+                       reset_blocked<R, GRID>(tab, p.w.tab64, p.w.k_circ, p.w.k_obst, p.w.reset_band, cx, cy));
+            }
+            w.n += 1u;
+            if (ok && !boat) {  // aqua.py:102-105
+                w.gx = cx;
+                w.gy = cy;
+                w.n |= 0x80000000u;
+                fin = !random_boat;
+            } else if (ok) {  // aqua.py:110-115
+                fin = true;
+                x = cx;
+                y = cy;
+                th = draw_angle(r.z);
+            }
+        }
+        if (fin) {
+            CoopResetResult rr;
+            rr.x = x; rr.y = y; rr.th = th; rr.gx = w.gx; rr.gy = w.gy;
+            rr.wx = rr.wy = 0.f;
+            if (p.w.waves) draw_wave_init(p.w.keys, env_id, w.ep, rr.wx, rr.wy);  // aqua.py:124
+            uint4 a, b;
+            stash_pack(rr, w.ep, a, b);
+            const size_t slot = (size_t)(p.env_begin + w.rel) * kRingDepth + (w.ep & (kRingDepth - 1));
+            __stcg(p.stash + 2 * slot, a);
+            __stcg(p.stash + 2 * slot + 1, b);
+            __stcg(p.stash_tag + slot, w.ep);
+            w.rel = kNoWork;
+        }
+    }
+    *sw = w;
+    n_act = __popc(__ballot_sync(full, w.rel != kNoWork));
 }
 
 // ten Philox2x32 rounds of N independent counters side by side
@@ -127,6 +198,14 @@ __device__ __forceinline__ void philox2x32_10_v(uint32_t (&c0)[N], uint32_t (&c1
     }
 }
 
+// starts the copy of the ring slot of episode `ep` of env `rel` into the env's shared-memory record
+__device__ __forceinline__ void ring_prefetch(const StepArgs& p, uint32_t rel, uint32_t ep, uint4* dst) {
+    const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel) * kRingDepth + (ep & (kRingDepth - 1)));
+    cp_async<16>(dst, src);
+    cp_async<16>(dst + 1, src + 1);
+    cp_async_commit();
+}
+
 // TAB: the obstacle test of the launch's table -- 0 brute force, 1 small table (World::small), 2 culling grid
 template <typename R, int V, int ACT, bool TAPE, int TAB>
 __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8)) step_many_kernel(const __grid_constant__ StepArgs p) {
@@ -139,6 +218,7 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     const ObstacleView<R> tab = stage_table<R>(s_box, s_nr2, s_stage, p.w.tab, p.w.k_obst, TAB == 2);
     RefillQueue<V>* const s_rq = reinterpret_cast<RefillQueue<V>*>(s_stage + cell_bytes(TAB == 2));
     uint4* const s_rec_cta = reinterpret_cast<uint4*>(s_rq + (blockDim.x >> 5));
+    LaneWork* const sw = reinterpret_cast<LaneWork*>(s_rec_cta + 2 * (size_t)blockDim.x * V) + threadIdx.x;
     if (threadIdx.x < kSlotStats) s_stats[threadIdx.x] = 0ull;
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
@@ -152,6 +232,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
+    // Where the used-up records of the ring are drawn again.  Dense maps (culling grid; episodes of
+    // ~27 steps on the 64-obstacle map): inside the step loop, whenever they fill a round.  Sparse maps:
+    // before the first step of the next launch, all at once -- measured on one box
+    // (profiles/r03_ring_ab.txt) the step loop without that code runs 3 to 12 % faster there.
+    constexpr bool kInLoop = TAB == 2;
     const unsigned full = 0xffffffffu;
     const uint32_t n = p.n_stream;
     const uint32_t lane = threadIdx.x & 31u;
@@ -168,10 +253,9 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     ThreadStats st;
     if (warp_rel < n) {  // warp-uniform
         RefillQueue<V>& rq = s_rq[threadIdx.x >> 5];
-        int n_q = 0;           // queued refills, warp-uniform
-        int thr = kLanePass;   // queue length that triggers a refill pass; 1 = flush before the next step
+        int n_q = 0;           // queued records, warp-uniform
+        int n_act = 0;         // lanes that are drawing a record, warp-uniform
         uint32_t pend = 0u;    // bit 0 of byte j: env j finished and waits for the refill of its record
-        uint4* const g_rec = p.stash + 2 * (p.env_begin + (int64_t)rel);             // this thread's, global
         uint4* const s_rec = s_rec_cta + 2 * (size_t)(threadIdx.x & ~31u) * V;         // the warp's, shared
         uint4* const my_rec = s_rec + 2 * (size_t)lane * V;                            // this thread's, shared
         const uint32_t env_id = p.env_id0 + rel;
@@ -198,23 +282,43 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
             }
         }
 
-        // ---- stash in: global -> shared.  A record that is not the one of the env's next episode (never
-        // drawn; or the previous launch ended before its refill ran; or a single-step launch moved the
-        // episode on) is queued like any other refill: it is drawn by the next full pass, or at once
-        // when its env finishes first ----
+        // ---- the ring: queue the stale slots of this warp's envs and draw them, all lanes busy; then
+        // the record of each env's next episode into shared memory ----
         if (autoreset) {
-            uint32_t want[V], word = 0u;
+            sw->rel = kNoWork;
+            uint32_t next_ep[V];
+            uint4 tg[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) {
-                want[j] = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
-                if (j < nvalid) {  // global -> shared, 32 V contiguous bytes per thread
-                    const uint4 r0 = __ldcg(g_rec + 2 * j), r1 = __ldcg(g_rec + 2 * j + 1);
-                    my_rec[2 * j] = r0;
-                    my_rec[2 * j + 1] = r1;
-                    word |= (r1.w != want[j] ? 1u : 0u) << (8 * j);
-                }
+                next_ep[j] = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+                tg[j] = make_uint4(0u, 0u, 0u, 0u);
+                if (j < nvalid) tg[j] = __ldcg(reinterpret_cast<const uint4*>(p.stash_tag) + (p.env_begin + (int64_t)rel + j));
             }
-            if (__any_sync(full, word != 0u)) n_q = refill_push<V>(rq, n_q, word, rel, want);
+#pragma unroll
+            for (int d = kRingDepth - 1; d >= 0; --d) {  // the nearest episodes last: they are taken first
+                uint32_t want[V], word = 0u;
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    want[j] = (next_ep[j] + (uint32_t)d) & kEpisodeMask;
+                    const uint32_t sl = want[j] & (kRingDepth - 1);
+                    const uint32_t have = sl == 0u ? tg[j].x : (sl == 1u ? tg[j].y : (sl == 2u ? tg[j].z : tg[j].w));
+                    word |= ((j < nvalid && have != want[j]) ? 1u : 0u) << (8 * j);
+                }
+                if (__any_sync(full, word != 0u)) n_q = refill_push<V>(rq, n_q, word, rel, want);
+                __syncwarp();  // queue entries are visible to the whole warp
+                while (n_q + n_act >= 32) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+            }
+            // sparse maps: a launch draws all its records here and starts with a full ring
+            if constexpr (!kInLoop)
+                while (n_q + n_act > 0) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+            __syncwarp();  // orders the record stores of all lanes before the owners' loads
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+                if (j < nvalid) {
+                    const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (next_ep[j] & (kRingDepth - 1)));
+                    my_rec[2 * j] = __ldcg(src);
+                    my_rec[2 * j + 1] = __ldcg(src + 1);
+                }
         }
 
         // ---- per-step I/O: row k of the tape is row_stride envs after row k - 1.  A thread without
@@ -240,27 +344,35 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
         }
 
         for (int k = 0;; ++k) {
-            // ---- the ONE place where records are drawn: in full passes, all lanes busy; a flush only
-            // when an env waits for its record.  What is still queued after the last step stays
-            // undrawn (its record keeps a stale tag): the next launch queues it again ----
-            if (autoreset && n_q >= thr) {
-                n_q = refill_drain<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, thr, s_rec, warp_rel);
-                thr = kLanePass;
-            }
-            if (__any_sync(full, pend != 0u)) {  // rare: the records of waiting envs are there now
-                uint32_t next[V];
+            if (autoreset) {
+                if (__any_sync(full, pend != 0u)) {
+                    // rare: an env finished whose record was not in the ring (it finished kRingDepth times
+                    // before the records it used up were drawn again): everything queued is drawn now,
+                    // the owner takes its record from the ring
+                    __syncwarp();
+                    while (n_q + n_act > 0) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                    __syncwarp();
+                    uint32_t after[V], word = 0u;
 #pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
-                    next[j] = (want + 1u) & kEpisodeMask;
-                    if ((pend >> (8 * j)) & 1u) {
-                        const uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
-                        if (r1.w != want) __trap();  // the flush above drew exactly this record
-                        stash_unpack<R>(r0, r1, e[j]);
+                    for (int j = 0; j < V; ++j) {
+                        const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
+                        after[j] = (want + kRingDepth) & kEpisodeMask;
+                        if ((pend >> (8 * j)) & 1u) {
+                            const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (want & (kRingDepth - 1)));
+                            const uint4 r0 = __ldcg(src), r1 = __ldcg(src + 1);
+                            if (r1.w != want) __trap();  // the rounds above drew exactly this record
+                            stash_unpack<R>(r0, r1, e[j]);
+                            ring_prefetch(p, rel + j, (want + 1u) & kEpisodeMask, &my_rec[2 * j]);
+                            word |= 1u << (8 * j);
+                        }
                     }
+                    if constexpr (kInLoop) n_q = refill_push<V>(rq, n_q, word, rel, after);  // the slot it used up
+                    pend = 0u;
+                    __syncwarp();
                 }
-                n_q = refill_push<V>(rq, n_q, pend, rel, next);
-                pend = 0u;
+                // dense maps: the records used up so far are drawn again as soon as they fill a round
+                if constexpr (kInLoop)
+                    while (n_q + n_act >= 32) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
             }
             if (k == steps) break;
 
@@ -373,42 +485,38 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                 for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), e[j].tw & kTimeMask);
             } else if (any_done) {
                 uint32_t ep[V], word = 0u;  // what gets queued: bit 0 of byte j, with episode ep[j]
+                cp_async_wait<0>();         // the records copied in after earlier swaps have landed
 #pragma unroll
                 for (int j = 0; j < V; ++j) {
                     const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;  // the episode that opens now
-                    ep[j] = (want + 1u) & kEpisodeMask;                                        // the record after it
+                    ep[j] = want;
                     if ((fw >> (8 * j)) & 1u) {
                         st.length += e[j].tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
                         if (p.term != nullptr) store_terminal<R>(p, p.env_begin + rel + j, e[j]);  // aqua.py:213
                         const uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
-                        word |= 1u << (8 * j);
-                        if (r1.w == want) {  // swap it in; its successor is drawn by a later pass
+                        if (r1.w == want) {  // swap it in; the slot after it is on its way
                             stash_unpack<R>(r0, r1, e[j]);
-                        } else {
-                            // the env finished again before the refill of its record ran (or the record was
-                            // never drawn): queue exactly this record (a second entry for it is harmless),
-                            // flush before the next step, pick it up there
-                            ep[j] = want;
+                            ring_prefetch(p, rel + j, (want + 1u) & kEpisodeMask, &my_rec[2 * j]);
+                            if constexpr (kInLoop) {  // queue the slot it used up
+                                word |= 1u << (8 * j);
+                                ep[j] = (want + kRingDepth) & kEpisodeMask;
+                            }
+                        } else {  // not in the ring: queue exactly this record, it is drawn before the next step
+                            word |= 1u << (8 * j);
                             pend |= 1u << (8 * j);
                         }
                     }
                 }
-                n_q = refill_push<V>(rq, n_q, word, rel, ep);
-                if (__any_sync(full, pend != 0u)) thr = 1;
+                if (kInLoop || __any_sync(full, word != 0u)) {
+                    n_q = refill_push<V>(rq, n_q, word, rel, ep);
+                    __syncwarp();  // queue entries are visible to the whole warp
+                }
             }
         }
 
         st.steps += (uint32_t)nvalid * (uint32_t)steps;
 
-        // ---- stash out (records whose refill is still queued go back with their old tag) ----
-        if (autoreset) {
-#pragma unroll
-            for (int j = 0; j < V; ++j)
-                if (j < nvalid) {
-                    __stcg(g_rec + 2 * j, my_rec[2 * j]);
-                    __stcg(g_rec + 2 * j + 1, my_rec[2 * j + 1]);
-                }
-        }
+        cp_async_wait<0>();
 
         // ---- state out (full-width: the plane padding behind the last env is scratch) ----
         if (nvalid > 0) {

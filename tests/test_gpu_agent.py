@@ -134,11 +134,11 @@ def test_reference_callers_run_on_the_dropin_env():
     from impl.utils import aqua_term_string
     from testing.test_optimal import OptimalAquaPolicy
     from testing.test_random import RandomAquaPolicy
-    env = gym.make("AquaEnv-v0", obstacles=False)
+    env = gym.make("AquaEnv-v0", obstacles=False, seed=20261018)   # seeded: the win count below is a fixed number
     assert type(env).__module__.startswith("aquaticgymenv_b200")
     assert env.reward_goal() == 10 and env.reward_collision() == -10 and env.reward_max_steps() == -10  # aqua.py:86-88
     wins = 0
-    for _ in range(12):
+    for _ in range(16):
         tot_rew, info, tot_steps = OptimalAquaPolicy().test(env, render=True)   # render(): no-op shim
         msg = aqua_term_string(info, tot_rew, tot_steps)
         assert sum(info.values()) == 1 and 1 <= tot_steps <= 1001
@@ -146,7 +146,7 @@ def test_reference_callers_run_on_the_dropin_env():
         assert ("REACHED GOAL" in msg) == bool(info['Termination.success'])
         if info['Termination.success']:
             assert tot_rew > 10 - 1e-9          # +10 at the goal plus a positive shaping sum
-    assert wins >= 9                            # the bearing controller on an obstacle-free map
+    assert wins >= 11                           # the bearing controller on an obstacle-free map (16 episodes)
     tot_rew, info, tot_steps = RandomAquaPolicy(strategy=0, env_action_space=env.action_space).test(env, render=False)
     assert sum(info.values()) == 1
     obs = env.reset()
