@@ -438,7 +438,7 @@ int ensure_stash(aqua_env* env, cudaStream_t s) {
     AQ_CUDA(cudaMalloc(&ptr, (size_t)env->ld * depth * 36));  // records, then the tag plane
     env->d_stash = static_cast<uint4*>(ptr);
     env->d_stash_tag = reinterpret_cast<uint32_t*>(static_cast<char*>(ptr) + (size_t)env->ld * depth * 32);
-    AQ_CUDA(aqua::launch_stash_init(env->d_stash_tag, (int64_t)((size_t)env->ld * depth), s));
+    AQ_CUDA(aqua::launch_stash_init(ptr, (size_t)env->ld * depth * 36, s));
     return AQUA_OK;
 }
 

@@ -118,7 +118,7 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 // [K][row_stride] out (either may be NULL); tape == 0: the synthetic random policy (ACTION stream)
 cudaError_t launch_step_many(int precision, int action_dtype, int tape, const StepArgs& a, LaunchGeom g, cudaStream_t s);
 cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int tab, int* blocks_per_sm);
-cudaError_t launch_stash_init(uint32_t* stash_tag, int64_t n_tags, cudaStream_t s);
+cudaError_t launch_stash_init(void* ring, size_t bytes, cudaStream_t s);
 int stash_ring_depth();
 cudaError_t launch_reset(int precision, const StepArgs& a, const uint8_t* mask, cudaStream_t s);
 cudaError_t launch_init_state(int precision, void* planes, int64_t ld, cudaStream_t s);

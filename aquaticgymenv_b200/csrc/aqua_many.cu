@@ -53,16 +53,12 @@ cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int
     return many_dispatch(precision, v, tab, action_dtype, tape, c);
 }
 
-// fresh ring: no slot holds an episode
-__global__ void stash_init_kernel(uint32_t* stash_tag, int64_t n_tags) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_tags) stash_tag[i] = kStashEmpty;
-}
-
-cudaError_t launch_stash_init(uint32_t* stash_tag, int64_t n_tags, cudaStream_t s) {
-    const int threads = 256;
-    stash_init_kernel<<<(int)((n_tags + threads - 1) / threads), threads, 0, s>>>(stash_tag, n_tags);
-    return cudaGetLastError();
+// Fresh ring: no slot holds an episode.  The records' own tag words count as well (a record is taken
+// on the strength of the tag it carries): the whole allocation is filled with 0xff = kStashEmpty, so
+// that no record a previous owner of the memory left behind can pass for one of this env's.
+cudaError_t launch_stash_init(void* ring, size_t bytes, cudaStream_t s) {
+    static_assert(kStashEmpty == 0xffffffffu, "memset pattern");
+    return cudaMemsetAsync(ring, 0xff, bytes, s);
 }
 
 int stash_ring_depth() { return kRingDepth; }

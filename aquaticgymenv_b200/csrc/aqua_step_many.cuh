@@ -344,11 +344,16 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
         }
 
         for (int k = 0;; ++k) {
+            // Records are written to the ring only here (and before the first step), with no copy out of
+            // the ring in flight in the warp: every lane waits for its own copies, then the warp
+            // synchronises.  A copy therefore never sees half of a record (the tag sits in its second
+            // 16 bytes), and one started later sees the finished record.
             if (autoreset) {
                 if (__any_sync(full, pend != 0u)) {
                     // rare: an env finished whose record was not in the ring (it finished kRingDepth times
                     // before the records it used up were drawn again): everything queued is drawn now,
                     // the owner takes its record from the ring
+                    cp_async_wait<0>();
                     __syncwarp();
                     while (n_q + n_act > 0) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
                     __syncwarp();
@@ -371,8 +376,15 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                     __syncwarp();
                 }
                 // dense maps: the records used up so far are drawn again as soon as they fill a round
-                if constexpr (kInLoop)
-                    while (n_q + n_act >= 32) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                if constexpr (kInLoop) {
+                    if (n_q + n_act >= 32) {
+                        cp_async_wait<0>();
+                        __syncwarp();
+                        do ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                        while (n_q + n_act >= 32);
+                        __syncwarp();  // orders the record stores before the copies the owners start later
+                    }
+                }
             }
             if (k == steps) break;
 
@@ -493,7 +505,12 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                     if ((fw >> (8 * j)) & 1u) {
                         st.length += e[j].tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
                         if (p.term != nullptr) store_terminal<R>(p, p.env_begin + rel + j, e[j]);  // aqua.py:213
-                        const uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
+                        uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
+                        if (kInLoop && r1.w != want) {  // copied before the slot was drawn again?  look at the ring itself
+                            const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (want & (kRingDepth - 1)));
+                            r0 = __ldcg(src);
+                            r1 = __ldcg(src + 1);
+                        }
                         if (r1.w == want) {  // swap it in; the slot after it is on its way
                             stash_unpack<R>(r0, r1, e[j]);
                             ring_prefetch(p, rel + j, (want + 1u) & kEpisodeMask, &my_rec[2 * j]);
