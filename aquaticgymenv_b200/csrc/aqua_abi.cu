@@ -443,19 +443,21 @@ int ensure_stash(aqua_env* env, cudaStream_t s) {
 }
 
 // Geometry of a multi-step launch: every env belongs to one thread for the whole launch, so the
-// grid is not persistent.  More envs per thread cost fewer instructions per env-step (7.3 / 8.6 / 12
-// warp-instructions at V = 4 / 2 / 1) but leave fewer warps; measured over slab sizes on one box
-// (profiles/r02l_step_many_v_by_size.txt) the widest thread that still gives every SM three 64-thread
-// CTAs wins or comes within 8 %: V = 4 from ~114k envs, V = 2 from ~57k, V = 1 below.
+// grid is not persistent.  More envs per thread give a thread more independent work and cost fewer
+// instructions per env-step, but leave fewer warps.  Measured over slab sizes on one box, launches
+// back to back (profiles/r03f_step_many_v_by_size_*.txt, three maps): one env per thread up to ~330
+// envs per SM and again around 660 (one full wave of its CTAs), two envs per thread otherwise --
+// at 65,536 envs (440 per SM) and from ~780 per SM on; four per thread (128 registers) no longer wins
+// anywhere.  128-thread CTAs on dense maps from ~1300 envs per SM (the culling grid is staged once
+// per CTA), 64-thread CTAs otherwise.
 // AQUA_MANY_V / AQUA_MANY_THREADS (environment) override the choice: tuning only.
 int pick_many_geom(const aqua_env* env, int64_t n, aqua::LaunchGeom* g) {
     const int wide = aqua::envs_per_thread(env->cfg.precision);
-    int threads = 64, v = 1;
-    for (int cand = wide; cand >= 1; cand /= 2)
-        if (n >= (int64_t)3 * env->sm_count * threads * cand) {
-            v = cand;
-            break;
-        }
+    const int64_t per_sm = n / std::max(env->sm_count, 1);
+    const bool grid = env->world.use_grid != 0;
+    int threads = 64, v = 2;
+    if (per_sm <= 332 || (!grid && per_sm > 553 && per_sm <= 775)) v = 1;
+    if (grid && per_sm >= 1328) threads = 128;
     if (env->cfg.geometry == AQUA_GEOM_WIDE) v = wide;
     if (env->cfg.geometry == AQUA_GEOM_NARROW) v = 1;
     if (const char* s = getenv("AQUA_MANY_V")) {
