@@ -7,11 +7,11 @@ namespace aqua {
 
 static int many_tab_kind(const World& w) { return w.small_mode != 0 ? 1 : (w.use_grid ? 2 : 0); }
 
-static cudaError_t many_dispatch(int precision, int v, int tab, int act, int tape, const ManyCall& c) {
-    if (precision == AQUA_F64) return many_tu_f64(v, tab == 1 ? 0 : tab, act, tape, c);
-    if (v == 1) return many_tu_f32v1(tab, act, tape, c);
-    if (v == 2) return many_tu_f32v2(tab, act, tape, c);
-    if (v == 4) return many_tu_f32v4(tab, act, tape, c);
+static cudaError_t many_dispatch(int precision, int v, int tab, int inloop, int act, int tape, const ManyCall& c) {
+    if (precision == AQUA_F64) return many_tu_f64(v, tab == 1 ? 0 : tab, inloop, act, tape, c);
+    if (v == 1) return many_tu_f32v1(tab, inloop, act, tape, c);
+    if (v == 2) return many_tu_f32v2(tab, inloop, act, tape, c);
+    if (v == 4) return many_tu_f32v4(tab, inloop, act, tape, c);
     return cudaErrorInvalidValue;
 }
 
@@ -40,7 +40,8 @@ cudaError_t launch_step_many(int precision, int action_dtype, int tape, const St
     c.a = &b;
     c.g = g;
     c.s = s;
-    return many_dispatch(precision, g.v, many_tab_kind(a.w), action_dtype, tape, c);
+    const int tab = many_tab_kind(a.w);
+    return many_dispatch(precision, g.v, tab, tab == 2 || a.steps > kRingStartOnlySteps, action_dtype, tape, c);
 }
 
 // `tab`: 0 brute force, 1 small table, 2 culling grid (as the launcher derives it from the World)
@@ -50,7 +51,7 @@ cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int
     c.threads = threads;
     c.use_grid = tab == 2;
     c.out = blocks_per_sm;
-    return many_dispatch(precision, v, tab, action_dtype, tape, c);
+    return many_dispatch(precision, v, tab, tab == 2, action_dtype, tape, c);
 }
 
 // Fresh ring: no slot holds an episode.  The records' own tag words count as well (a record is taken

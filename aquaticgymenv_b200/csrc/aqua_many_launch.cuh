@@ -23,9 +23,9 @@ template <int V> static size_t many_smem(int threads, int use_grid) {
            (size_t)threads * sizeof(LaneWork);
 }
 
-template <typename R, int V, int ACT, bool TAPE, int TAB> static cudaError_t many_call(const ManyCall& c) {
+template <typename R, int V, int ACT, bool TAPE, int TAB, bool INLOOP> static cudaError_t many_call(const ManyCall& c) {
     if (c.kind == 1)
-        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(c.out, step_many_kernel<R, V, ACT, TAPE, TAB>, c.threads,
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(c.out, step_many_kernel<R, V, ACT, TAPE, TAB, INLOOP>, c.threads,
                                                              many_smem<V>(c.threads, c.use_grid));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)c.g.blocks);
@@ -37,35 +37,35 @@ template <typename R, int V, int ACT, bool TAPE, int TAB> static cudaError_t man
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, step_many_kernel<R, V, ACT, TAPE, TAB>, *c.a);
+    return cudaLaunchKernelEx(&cfg, step_many_kernel<R, V, ACT, TAPE, TAB, INLOOP>, *c.a);
 }
 
-template <typename R, int V, int TAB> static cudaError_t many_act(int act, int tape, const ManyCall& c) {
+template <typename R, int V, int TAB, bool INLOOP> static cudaError_t many_act(int act, int tape, const ManyCall& c) {
     if (!tape)  // random policy: the action dtype only tells discrete from continuous
-        return act == AQUA_ACT_F32X2 ? many_call<R, V, AQUA_ACT_F32X2, false, TAB>(c)
-                                     : many_call<R, V, AQUA_ACT_I32, false, TAB>(c);
+        return act == AQUA_ACT_F32X2 ? many_call<R, V, AQUA_ACT_F32X2, false, TAB, INLOOP>(c)
+                                     : many_call<R, V, AQUA_ACT_I32, false, TAB, INLOOP>(c);
     switch (act) {
-        case AQUA_ACT_I32: return many_call<R, V, AQUA_ACT_I32, true, TAB>(c);
-        case AQUA_ACT_I64: return many_call<R, V, AQUA_ACT_I64, true, TAB>(c);
-        case AQUA_ACT_U8: return many_call<R, V, AQUA_ACT_U8, true, TAB>(c);
-        case AQUA_ACT_F32X2: return many_call<R, V, AQUA_ACT_F32X2, true, TAB>(c);
+        case AQUA_ACT_I32: return many_call<R, V, AQUA_ACT_I32, true, TAB, INLOOP>(c);
+        case AQUA_ACT_I64: return many_call<R, V, AQUA_ACT_I64, true, TAB, INLOOP>(c);
+        case AQUA_ACT_U8: return many_call<R, V, AQUA_ACT_U8, true, TAB, INLOOP>(c);
+        case AQUA_ACT_F32X2: return many_call<R, V, AQUA_ACT_F32X2, true, TAB, INLOOP>(c);
         default: return cudaErrorInvalidValue;
     }
 }
 
-// tab: 0 brute force, 1 small table (float only), 2 culling grid
-template <typename R, int V> static cudaError_t many_tab(int tab, int act, int tape, const ManyCall& c) {
-    if (tab == 2) return many_act<R, V, 2>(act, tape, c);
+// tab: 0 brute force, 1 small table (float only), 2 culling grid; inloop: see step_many_kernel
+template <typename R, int V> static cudaError_t many_tab(int tab, int inloop, int act, int tape, const ManyCall& c) {
+    if (tab == 2) return many_act<R, V, 2, true>(act, tape, c);
     if constexpr (sizeof(R) == 4) {
-        if (tab == 1) return many_act<R, V, 1>(act, tape, c);
+        if (tab == 1) return inloop ? many_act<R, V, 1, true>(act, tape, c) : many_act<R, V, 1, false>(act, tape, c);
     }
-    return many_act<R, V, 0>(act, tape, c);
+    return inloop ? many_act<R, V, 0, true>(act, tape, c) : many_act<R, V, 0, false>(act, tape, c);
 }
 
 // one per translation unit
-cudaError_t many_tu_f32v1(int tab, int act, int tape, const ManyCall& c);
-cudaError_t many_tu_f32v2(int tab, int act, int tape, const ManyCall& c);
-cudaError_t many_tu_f32v4(int tab, int act, int tape, const ManyCall& c);
-cudaError_t many_tu_f64(int v, int tab, int act, int tape, const ManyCall& c);
+cudaError_t many_tu_f32v1(int tab, int inloop, int act, int tape, const ManyCall& c);
+cudaError_t many_tu_f32v2(int tab, int inloop, int act, int tape, const ManyCall& c);
+cudaError_t many_tu_f32v4(int tab, int inloop, int act, int tape, const ManyCall& c);
+cudaError_t many_tu_f64(int v, int tab, int inloop, int act, int tape, const ManyCall& c);
 
 }  // namespace aqua

@@ -89,6 +89,7 @@ template <typename R> __device__ __forceinline__ void stash_unpack(const uint4& 
     e.tw = r1.w << AQUA_TIME_BITS;
 }
 
+constexpr int kRingStartOnlySteps = 160;  // longer launches draw records inside the step loop on every map
 constexpr int kRingDepth = 4;  // records per env; divides the episode range (2^21), so slot = episode & 3
 constexpr uint32_t kNoWork = 0xffffffffu;
 
@@ -104,6 +105,12 @@ struct LaneWork {
 // (try n = Philox(env, episode, n, RESET): the goal candidate while the goal is open, then the boat
 // candidate -- exactly the sequence of reset_env_lane / aqua.py:100-126, accept decisions
 // float64-exact).  A lane whose boat is accepted writes the record to the ring and is idle again.
+// AQUA_RING_FULL_DRAIN=1: a launch on a sparse map draws every stale record before its first step;
+// 0: only in full rounds of 32 -- what is left (fewer than 32 records, the ones farthest ahead: they
+// are queued first and taken last) waits for the next launch
+#ifndef AQUA_RING_FULL_DRAIN
+#define AQUA_RING_FULL_DRAIN 1
+#endif
 #ifndef AQUA_RING_INLINE
 #define AQUA_RING_INLINE 1
 #endif
@@ -207,7 +214,8 @@ __device__ __forceinline__ void ring_prefetch(const StepArgs& p, uint32_t rel, u
 }
 
 // TAB: the obstacle test of the launch's table -- 0 brute force, 1 small table (World::small), 2 culling grid
-template <typename R, int V, int ACT, bool TAPE, int TAB>
+// INLOOP: used-up ring records are drawn again inside the step loop (dense maps, long launches)
+template <typename R, int V, int ACT, bool TAPE, int TAB, bool INLOOP>
 __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8)) step_many_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[kBoxSlots];
     __shared__ R s_nr2[kBoxSlots + 3];
@@ -232,11 +240,12 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    // Where the used-up records of the ring are drawn again.  Dense maps (culling grid; episodes of
-    // ~27 steps on the 64-obstacle map): inside the step loop, whenever they fill a round.  Sparse maps:
-    // before the first step of the next launch, all at once -- measured on one box
-    // (profiles/r03_ring_ab.txt) the step loop without that code runs 3 to 12 % faster there.
-    constexpr bool kInLoop = TAB == 2;
+    // Where the used-up records of the ring are drawn again.  INLOOP (dense maps: episodes of ~27 steps
+    // on the 64-obstacle map; launches of more than kRingStartOnlySteps steps on any map): inside the step
+    // loop, whenever they fill a round.  Otherwise: before the first step of the next launch, all at
+    // once -- measured on one box (profiles/r03_ring_ab.txt) the step loop without that code runs 3 to
+    // 12 % faster on the sparse maps, as long as a launch is short enough for four records per env.
+    constexpr bool kInLoop = INLOOP;
     const unsigned full = 0xffffffffu;
     const uint32_t n = p.n_stream;
     const uint32_t lane = threadIdx.x & 31u;
@@ -308,9 +317,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                 __syncwarp();  // queue entries are visible to the whole warp
                 while (n_q + n_act >= 32) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
             }
+#if AQUA_RING_FULL_DRAIN
             // sparse maps: a launch draws all its records here and starts with a full ring
             if constexpr (!kInLoop)
                 while (n_q + n_act > 0) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+#endif
             __syncwarp();  // orders the record stores of all lanes before the owners' loads
 #pragma unroll
             for (int j = 0; j < V; ++j)

@@ -491,7 +491,8 @@ def _tape(env, K, first=0):
 @pytest.mark.parametrize("many_v", ["1", "2", "wide"])
 @pytest.mark.parametrize("precision", ["float64", "float32"])
 @pytest.mark.parametrize("name,n,K", [("v1_discrete", 10003, 150), ("dense64_continuous", 4100, 120),
-                                      ("v1_discrete", 77, 40), ("v2_continuous", 1, 300)])
+                                      ("v1_discrete", 77, 40), ("v2_continuous", 1, 300),
+                                      ("v1_discrete", 3001, 640)])   # 640: a launch long enough for the in-loop ring
 def test_step_many_equals_stepwise(name, n, K, precision, many_v, monkeypatch):
     """aqua_step_many (K steps in one launch, state in registers, next episodes from the stash) ==
     K aqua_step launches on the same tape: rewards, flags, final state and statistics, bit for bit,

@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Same-box A/B of libaquagym.so builds (aquaticgymenv_b200/variants/*.so) on the aqua_step_many
+"""Same-box A/B of libaquagym.so builds (launches timed four at a time, back to back) (aquaticgymenv_b200/variants/*.so) on the aqua_step_many
 workloads of BASELINE.json: one subprocess per (build, workload), the builds interleaved, twice.
 usage (GPU box): python tools/many_ab.py [K]      worker: python tools/many_ab.py --one <workload index> K"""
 import glob
@@ -10,19 +10,16 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # (label, env id, envs, obstacles, V, threads); V = 0: the library's own geometry
-WORK = [("c2 65536 v1", "AquaEnv-v1", 65536, None, 1, 64), ("c2 65536 v2", "AquaEnv-v1", 65536, None, 2, 64),
-        ("c3 131072 cont v2", "AquaContinuousEnv-v1", 131072, None, 2, 64),
-        ("c3 131072 cont v4", "AquaContinuousEnv-v1", 131072, None, 4, 64),
-        ("head 2^20 v4", "AquaEnv-v1", 1 << 20, None, 4, 64),
-        ("c4 dense 2^19 v4", "AquaEnv-v0", 1 << 19, "dense64", 4, 128),
-        ("c4 dense 2^19 v2", "AquaEnv-v0", 1 << 19, "dense64", 2, 128),
-        ("c4 dense 2^22 v4", "AquaEnv-v0", 1 << 22, "dense64", 4, 128)]
+WORK = [("c2 65536", "AquaEnv-v1", 65536, None, 0, 0), ("c3 131072 cont", "AquaContinuousEnv-v1", 131072, None, 0, 0),
+        ("head 2^20", "AquaEnv-v1", 1 << 20, None, 0, 0), ("c4 dense 2^19", "AquaEnv-v0", 1 << 19, "dense64", 0, 0),
+        ("c4 dense 2^22", "AquaEnv-v0", 1 << 22, "dense64", 0, 0), ("98304", "AquaEnv-v1", 98304, None, 0, 0),
+        ("c2 65536 v1", "AquaEnv-v1", 65536, None, 1, 64)]
 
 if len(sys.argv) > 1 and sys.argv[1] == "--one":
     sys.path.insert(0, ROOT)
     from tools.many_probe import rate
     w = WORK[int(sys.argv[2])]
-    print(json.dumps(rate(w[1], w[2], int(sys.argv[3]), w[4], w[5], obstacles=w[3], reps=7)))
+    print(json.dumps(rate(w[1], w[2], int(sys.argv[3]), w[4], w[5], obstacles=w[3], reps=5, b2b=4)))
     sys.exit(0)
 
 K = sys.argv[1] if len(sys.argv) > 1 else "64"

@@ -22,7 +22,8 @@ except Exception:
     pass
 
 
-def rate(env_id, n, K, v, threads, obstacles=None, reps=5, mode="tape", precision="float32"):
+def rate(env_id, n, K, v, threads, obstacles=None, reps=5, mode="tape", precision="float32", b2b=1):
+    """b2b: launches back to back per timing (as bench.py times them); v = 0: the library's own geometry"""
     os.environ["AQUA_MANY_V"] = str(v)
     os.environ["AQUA_MANY_THREADS"] = str(threads)
     kw = {}
@@ -48,10 +49,11 @@ def rate(env_id, n, K, v, threads, obstacles=None, reps=5, mode="tape", precisio
     for _ in range(reps):
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
-        run()
+        for _ in range(b2b):
+            run()
         e.record()
         torch.cuda.synchronize()
-        best = min(best, s.elapsed_time(e) * 1e-3)
+        best = min(best, s.elapsed_time(e) * 1e-3 / b2b)
     st = env.stats()
     env.close()
     r = n * K / best
