@@ -31,6 +31,8 @@
 // test_step_many_interleaved_with_single_steps).
 #pragma once
 
+#include <type_traits>
+
 #include "aqua_kernel_util.cuh"
 
 namespace aqua {
@@ -87,6 +89,34 @@ template <typename R> __device__ __forceinline__ void stash_unpack(const uint4& 
     e.wx = (R)__uint_as_float(r1.y);
     e.wy = (R)__uint_as_float(r1.z);
     e.tw = r1.w << AQUA_TIME_BITS;
+}
+
+// A record read from shared memory as eight separate 32-bit words.  A 16-byte load would tie x, y,
+// heading and goal of ONE env to four consecutive registers, while the packed arithmetic of the
+// step wants the same quantity of TWO envs side by side: the compiler then transposes the state
+// with register moves in every step.  This path runs once per episode.
+__device__ __forceinline__ void record_words(const uint4* rec, uint4& r0, uint4& r1) {
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(rec);
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r0.x) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+4];" : "=r"(r0.y) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+8];" : "=r"(r0.z) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+12];" : "=r"(r0.w) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+16];" : "=r"(r1.x) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+20];" : "=r"(r1.y) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+24];" : "=r"(r1.z) : "r"(a));
+    asm volatile("ld.shared.u32 %0, [%1+28];" : "=r"(r1.w) : "r"(a));
+}
+// the same from the ring in global memory (L2)
+__device__ __forceinline__ void record_words_global(const uint4* rec, uint4& r0, uint4& r1) {
+    const uint32_t* g = reinterpret_cast<const uint32_t*>(rec);
+    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(r0.x) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+4];" : "=r"(r0.y) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+8];" : "=r"(r0.z) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+12];" : "=r"(r0.w) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+16];" : "=r"(r1.x) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+20];" : "=r"(r1.y) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+24];" : "=r"(r1.z) : "l"(g));
+    asm volatile("ld.global.cg.u32 %0, [%1+28];" : "=r"(r1.w) : "l"(g));
 }
 
 constexpr int kRingStartOnlySteps = 160;  // longer launches draw records inside the step loop on every map
@@ -205,6 +235,17 @@ __device__ __forceinline__ void philox2x32_10_v(uint32_t (&c0)[N], uint32_t (&c1
     }
 }
 
+// the drives of two envs with discrete actions a, b in {0, 1, 2} from the pair table (three 8-byte loads)
+template <typename R>
+__device__ __forceinline__ void pair_drives(const R (*tab)[6], uint32_t a, uint32_t b, Drive<R>& da, Drive<R>& db) {
+    const R* t = tab[3u * a + b];
+    using P2 = typename std::conditional<sizeof(R) == 4, float2, double2>::type;
+    const P2 phi = *reinterpret_cast<const P2*>(t), h = *reinterpret_cast<const P2*>(t + 2), chord = *reinterpret_cast<const P2*>(t + 4);
+    da.phi = phi.x; db.phi = phi.y;
+    da.h = h.x; db.h = h.y;
+    da.chord = chord.x; db.chord = chord.y;
+}
+
 // starts the copy of the ring slot of episode `ep` of env `rel` into the env's shared-memory record
 __device__ __forceinline__ void ring_prefetch(const StepArgs& p, uint32_t rel, uint32_t ep, uint4* dst) {
     const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel) * kRingDepth + (ep & (kRingDepth - 1)));
@@ -221,6 +262,9 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     __shared__ R s_nr2[kBoxSlots + 3];
     __shared__ unsigned long long s_stats[kSlotStats];
     __shared__ DriveSlot<R> s_drive[3];
+    // the drives of an env PAIR (actions a, b): entry 3 a + b = {phi_a, phi_b}, {h_a, h_b}, {chord_a, chord_b},
+    // each read with one 8-byte load straight into the register pair the packed arithmetic takes
+    __shared__ __align__(16) R s_drive2[9][6];
     // dynamic shared memory: the culling grid of a dense map, one refill queue per warp, the stash
     // records of the CTA's envs (2 x 16 bytes each)
     const ObstacleView<R> tab = stage_table<R>(s_box, s_nr2, s_stage, p.w.tab, p.w.k_obst, TAB == 2);
@@ -231,6 +275,13 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
         s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
+    }
+    if (ACT != AQUA_ACT_F32X2 && V > 1 && threadIdx.x < 9) {
+        const Drive<R> da = drive_from_index<R>(threadIdx.x / 3), db = drive_from_index<R>(threadIdx.x % 3);
+        R* t = s_drive2[threadIdx.x];
+        t[0] = da.phi; t[1] = db.phi;
+        t[2] = da.h; t[3] = db.h;
+        t[4] = da.chord; t[5] = db.chord;
     }
     __syncthreads();
     // Programmatic dependent launch (the launcher sets the attribute): this CTA may have been made
@@ -375,7 +426,8 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                         after[j] = (want + kRingDepth) & kEpisodeMask;
                         if ((pend >> (8 * j)) & 1u) {
                             const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (want & (kRingDepth - 1)));
-                            const uint4 r0 = __ldcg(src), r1 = __ldcg(src + 1);
+                            uint4 r0, r1;
+                            record_words_global(src, r0, r1);
                             if (r1.w != want) __trap();  // the rounds above drew exactly this record
                             stash_unpack<R>(r0, r1, e[j]);
                             ring_prefetch(p, rel + j, (want + 1u) & kEpisodeMask, &my_rec[2 * j]);
@@ -426,12 +478,15 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                 } else {
                     uint32_t worst = 0u;
 #pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        worst = max(worst, act.w[j]);
-                        const DriveSlot<R> d = s_drive[min(act.w[j], 2u)];  // outside {0,1,2}: full throttle
-                        dr[j].phi = d.phi;
-                        dr[j].h = d.h;
-                        dr[j].chord = d.chord;
+                    for (int j = 0; j < V; ++j) worst = max(worst, act.w[j]);
+                    if constexpr (V == 1) {
+                        const DriveSlot<R> d = s_drive[min(act.w[0], 2u)];  // outside {0,1,2}: full throttle
+                        dr[0].phi = d.phi;
+                        dr[0].h = d.h;
+                        dr[0].chord = d.chord;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < V / 2; ++q) pair_drives<R>(s_drive2, min(act.w[2 * q], 2u), min(act.w[2 * q + 1], 2u), dr[2 * q], dr[2 * q + 1]);
                     }
                     if (worst > 2u) {  // rare
 #pragma unroll
@@ -462,11 +517,13 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                     if constexpr (ACT == AQUA_ACT_F32X2) {
                         uint32_t bad = 0u;
                         dr[j] = drive_continuous<R>(draw_thrust(a0[j]), draw_thrust(a1[j]), bad);
-                    } else {
+                    } else if constexpr (V == 1) {
                         const DriveSlot<R> d = s_drive[__umulhi(a0[j], 3u)];
                         dr[j].phi = d.phi;
                         dr[j].h = d.h;
                         dr[j].chord = d.chord;
+                    } else if ((j & 1) == 0) {
+                        pair_drives<R>(s_drive2, __umulhi(a0[j], 3u), __umulhi(a0[j + (V > 1 ? 1 : 0)], 3u), dr[j], dr[j + (V > 1 ? 1 : 0)]);
                     }
                     nx[j] = draw_noise(w0[j]);
                     ny[j] = draw_noise(w1[j]);
@@ -516,11 +573,11 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
                     if ((fw >> (8 * j)) & 1u) {
                         st.length += e[j].tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
                         if (p.term != nullptr) store_terminal<R>(p, p.env_begin + rel + j, e[j]);  // aqua.py:213
-                        uint4 r0 = my_rec[2 * j], r1 = my_rec[2 * j + 1];
+                        uint4 r0, r1;
+                        record_words(&my_rec[2 * j], r0, r1);
                         if (kInLoop && r1.w != want) {  // copied before the slot was drawn again?  look at the ring itself
                             const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (want & (kRingDepth - 1)));
-                            r0 = __ldcg(src);
-                            r1 = __ldcg(src + 1);
+                            record_words_global(src, r0, r1);
                         }
                         if (r1.w == want) {  // swap it in; the slot after it is on its way
                             stash_unpack<R>(r0, r1, e[j]);
