@@ -4,6 +4,11 @@
 
 #include "aqua_kernel_util.cuh"
 
+// tuning only (tools/tune.py variants): -DAQUA_STREAM_TAB=1 compiles the streaming kernel for small-table launches alone
+#ifndef AQUA_STREAM_TAB
+#define AQUA_STREAM_TAB -1
+#endif
+
 namespace aqua {
 
 // ------------------------------------------------------------------------------------------
@@ -302,7 +307,7 @@ step_stream_kernel(const __grid_constant__ StepArgs p) {
 #pragma unroll
                 for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
             }
-            fw = step_envs<R, V>(e, dr, nx, ny, WAVES, tab, k_circ, k_obst, vrew.v, p.w.small, p.w.small_mode);
+            fw = step_envs<R, V, (sizeof(R) == 4 ? AQUA_STREAM_TAB : -1)>(e, dr, nx, ny, WAVES, tab, k_circ, k_obst, vrew.v, p.w.small, p.w.small_mode);
             st.add_flags(fw, V);
 #pragma unroll
             for (int j = 0; j < V; ++j) st.add_env<R>(vrew.v[j]);

@@ -446,10 +446,15 @@ def summarise(torch, m, world, dist_on):
     achieved = bpe * m["n_local"] * m["steps"] * m["per_launch"] / m["elapsed"] / 1e9  # this rank's kernel, GB/s
     moved = None
     if m["mode"] == "many":
-        # what one env-step really moves: action in, reward + flags out, and per launch the state
-        # planes in + out (2 x 8 words) and the stash tag sector (32 B)
-        per_launch = 2 * (7 * es + 4) + 32
-        moved = (8 if m["continuous"] else 4) + es + 1 + per_launch / m["spl"]
+        # what one env-step really moves: action in, reward + flags out; per launch the state planes
+        # in + out (2 x 8 words), the four ring tags (16 B) and the record of the env's next episode
+        # (32 B); per finished episode (episodes / env-steps of the timed region) a record copied in
+        # (32 B) and one drawn again (32 B + its tag).  The measured DRAM bytes of the same launch are
+        # `traffic` (ncu), when this exact configuration was captured.
+        per_launch = 2 * (7 * es + 4) + 16 + 32
+        per_episode = 32 + 36
+        moved = ((8 if m["continuous"] else 4) + es + 1 + per_launch / m["spl"] +
+                 per_episode * stats["episodes"] / max(stats["steps"], 1))
     return {
         "value": total / elapsed_max, "elapsed_max_s": elapsed_max, "ms_per_step": 1e3 * elapsed_max / m["steps"],
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
