@@ -2,6 +2,7 @@
 // validation, launch geometry and the host-buffer step pipeline.  No exceptions cross the ABI;
 // every CUDA failure becomes a status + thread-local message.  There is no CPU fallback.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -46,6 +47,7 @@ struct DeviceGuard {
 
 constexpr int kHostStreams = 4;       // host-step pipeline depth
 constexpr int kTileCounters = 64;     // launches that may be in flight at once on one handle
+constexpr int64_t kMappedMaxEnvs = 8192;  // host steps of at most this many envs go through mapped host memory
 constexpr int64_t kHostChunkMin = 1024 * 1024;  // every copy costs several us to issue and start: few, large
                                                 // ones (tools/e2e_probe.py: 1 chunk at 2^20 envs, 16 at 2^24)
 
@@ -93,6 +95,11 @@ struct aqua_env {
     size_t d_actions_bytes = 0;
     void* d_reward = nullptr;
     uint8_t* d_flags = nullptr;
+    // small slabs (aqua_step_host with at most kMappedMaxEnvs envs): one block of mapped pinned host
+    // memory that the kernels read the actions from and write reward, flags and observation to
+    void* h_map = nullptr;
+    void* d_map = nullptr;  // the same memory as the device addresses it
+    uint32_t map_seq = 0;   // sequence number of the last mapped step (the completion word the host polls)
     // goal planes of the caller's host observation buffer: sent whole once, then only the entries of
     // envs whose episode changed (see aqua_step_host)
     const void* host_obs_last = nullptr;  // the obs buffer whose goal planes are current, or NULL
@@ -148,6 +155,62 @@ int check_action_dtype(const aqua_env* env, int dtype) {
         return fail(AQUA_ERR_INVALID, "AquaContinuousEnv takes AQUA_ACT_F32X2 actions (aqua.py:143-151), got dtype %d", dtype);
     if (!env->cfg.continuous && dtype == AQUA_ACT_F32X2)
         return fail(AQUA_ERR_INVALID, "AquaEnv takes a discrete action index (aqua.py:154), got AQUA_ACT_F32X2");
+    return AQUA_OK;
+}
+
+// Host step of a small slab (the single-env drop-in above all: aqua.py:135-213 once per call).  Copies
+// through the copy engines cost several microseconds each to issue and to complete, four of them
+// per step; here the step kernel reads the actions from, and writes reward and flags to, a block of
+// MAPPED pinned host memory, a second small kernel writes the five observation planes there, and
+// the call waits once: two launches and one synchronisation per step.
+int step_host_mapped(aqua_env* env, cudaStream_t s, const void* actions, int action_dtype, void* obs, void* reward,
+                     uint8_t* flags) {
+    const int64_t n = env->cfg.n_envs;
+    const size_t es = elem_size(env->cfg.precision);
+    const size_t ab = action_bytes(action_dtype);
+    const size_t cap = (size_t)kMappedMaxEnvs;
+    // layout: actions [cap x 8] | observation [5][n] (cap x 5 x 8) | reward [cap x 8] | flags [cap]
+    //         | completion word
+    const size_t off_obs = cap * 8, off_rew = off_obs + cap * 40, off_flg = off_rew + cap * 8, off_done = off_flg + cap,
+                 total = off_done + 64;
+    if (env->h_map == nullptr) {
+        AQ_CUDA(cudaHostAlloc(&env->h_map, total, cudaHostAllocMapped));
+        AQ_CUDA(cudaHostGetDevicePointer(&env->d_map, env->h_map, 0));
+        memset(env->h_map, 0, total);
+    }
+    char* h = static_cast<char*>(env->h_map);
+    char* d = static_cast<char*>(env->d_map);
+    memcpy(h, actions, (size_t)n * ab);
+    aqua::StepArgs a = base_args(env);
+    a.actions = d;
+    a.reward = d + off_rew;
+    a.flags = reinterpret_cast<uint8_t*>(d + off_flg);
+    aqua::LaunchGeom g;
+    pick_geom(env, n, false, action_dtype, &g);
+    AQ_CUDA(aqua::launch_step(env->cfg.precision, action_dtype, a, g, s));
+    // The observation kernel runs after the step kernel (stream order) and sets the completion word
+    // last; the host polls that word -- a synchronisation through the driver costs several microseconds
+    // more -- and falls back to the stream if it does not arrive (a failed launch shows up there).
+    const uint32_t seq = ++env->map_seq;
+    AQ_CUDA(aqua::launch_copy_obs_planes(env->cfg.precision, env->state, env->ld, n, d + off_obs,
+                                         reinterpret_cast<uint32_t*>(d + off_done), seq, s));
+    volatile uint32_t* done = reinterpret_cast<volatile uint32_t*>(h + off_done);
+    bool arrived = false;
+    for (int spin = 0; spin < 4000000; ++spin) {
+        if (*done == seq) {
+            arrived = true;
+            break;
+        }
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#endif
+    }
+    if (!arrived) AQ_CUDA(cudaStreamSynchronize(s));
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (obs != nullptr) memcpy(obs, h + off_obs, (size_t)5 * (size_t)n * es);
+    if (reward != nullptr) memcpy(reward, h + off_rew, (size_t)n * es);
+    if (flags != nullptr) memcpy(flags, h + off_flg, (size_t)n);
+    env->host_obs_last = nullptr;
     return AQUA_OK;
 }
 
@@ -347,6 +410,7 @@ int aqua_destroy(aqua_env* env) {
             }
         if (env->ev_in) keep(cudaEventDestroy(env->ev_in));
     }
+    if (env->h_map) keep(cudaFreeHost(env->h_map));
     if (env->d_actions) keep(cudaFree(env->d_actions));
     if (env->d_reward) keep(cudaFree(env->d_reward));
     if (env->d_flags) keep(cudaFree(env->d_flags));
@@ -534,6 +598,8 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
     if (int rc = check_action_dtype(env, action_dtype)) return rc;
     if (actions == nullptr) return fail(AQUA_ERR_INVALID, "actions is NULL");
     DeviceGuard guard(env->device);
+    if (env->cfg.n_envs <= kMappedMaxEnvs && getenv("AQUA_HOST_NO_MAPPED") == nullptr)
+        return step_host_mapped(env, static_cast<cudaStream_t>(stream), actions, action_dtype, obs, reward, flags);
     if (int rc = ensure_host_pipeline(env, action_dtype)) return rc;
 
     const int64_t n = env->cfg.n_envs;

@@ -446,6 +446,35 @@ cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_
     return cudaGetLastError();
 }
 
+// planes 0..4 (the observation, aqua.py:213) of envs [0, n) into `out` = [5][n] of the state's element
+// type, by ONE thread block; then `*done = seq` (system scope).  `out` and `done` are mapped host
+// memory (small-slab host step): the host thread polls `done` instead of synchronising the stream.
+template <typename R>
+__global__ void copy_obs_planes_kernel(const void* planes, int64_t ld, int64_t n, R* out, volatile uint32_t* done,
+                                       uint32_t seq) {
+    void* pl = const_cast<void*>(planes);
+    for (int64_t i = threadIdx.x; i < n; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) out[(int64_t)k * n + i] = plane<R>(pl, ld, k)[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *done = seq;
+        __threadfence_system();
+    }
+}
+
+cudaError_t launch_copy_obs_planes(int precision, const void* planes, int64_t ld, int64_t n, void* out, uint32_t* done,
+                                   uint32_t seq, cudaStream_t s) {
+    const int threads = n >= 1024 ? 1024 : (n > 32 ? 256 : 32);
+    if (precision == AQUA_F64)
+        copy_obs_planes_kernel<double><<<1, threads, 0, s>>>(planes, ld, n, static_cast<double*>(out), done, seq);
+    else
+        copy_obs_planes_kernel<float><<<1, threads, 0, s>>>(planes, ld, n, static_cast<float*>(out), done, seq);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, const uint8_t* flags, int64_t lo,
                                 int64_t len, void* h_gx, void* h_gy, cudaStream_t s) {
     const int threads = 256;

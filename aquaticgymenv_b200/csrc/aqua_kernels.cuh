@@ -130,6 +130,9 @@ cudaError_t launch_set_state(int precision, void* planes, int64_t ld, int64_t n,
                              cudaStream_t s);
 cudaError_t launch_observe(int precision, const void* planes, int64_t ld, int64_t n, float* out, int normalized,
                            cudaStream_t s);
+// planes 0..4 of envs [0, n) into out[5][n], then *done = seq (both mapped host memory)
+cudaError_t launch_copy_obs_planes(int precision, const void* planes, int64_t ld, int64_t n, void* out, uint32_t* done,
+                                   uint32_t seq, cudaStream_t s);
 // writes the goals of the finished envs of [lo, lo + len) into the caller's (device-mapped) host planes
 cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, const uint8_t* flags, int64_t lo,
                                 int64_t len, void* h_gx, void* h_gy, cudaStream_t s);

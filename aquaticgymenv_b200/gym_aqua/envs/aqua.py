@@ -10,6 +10,7 @@ import numpy as np
 
 from .. import _base
 from ... import spaces
+from ... import _native as N
 from ...vec_env import AquaVecEnv
 
 
@@ -65,6 +66,9 @@ class AquaEnv(_base.Env):
         self._rew_h = np.zeros(1, np.float64)
         self._flg_h = np.zeros(1, np.uint8)
         self._prev_obs = self._last_obs = None
+        import ctypes
+        self._ptrs = tuple(ctypes.c_void_p(a.ctypes.data) for a in (self._act_h, self._obs_h, self._rew_h, self._flg_h))
+        self._adt = N.ACT_F32X2 if self.continuous else N.ACT_I32
 
     def seed(self, seed=None):
         """Key of the env's draw streams (reset samples, wave noise): ``None`` = a fresh one from
@@ -102,7 +106,7 @@ class AquaEnv(_base.Env):
             idx = int(action)
             self.actions[idx]  # IndexError on a bad index, like aqua.py:154
             self._act_h[0] = idx % len(self.actions)
-        self._vec.step_host(self._act_h, self._obs_h, self._rew_h, self._flg_h)
+        self._vec.step_host_raw(self._ptrs[0], self._adt, self._ptrs[1], self._ptrs[2], self._ptrs[3])
         flags = int(self._flg_h[0])
         self.time += 1
         self._prev_obs, self._last_obs = self._last_obs, self._obs_h[:, 0].copy()

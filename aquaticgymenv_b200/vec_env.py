@@ -312,6 +312,14 @@ class AquaVecEnv(object):
         self._step_index += 1
         return obs_out, reward_out, flags_out
 
+    def step_host_raw(self, actions_ptr, action_dtype, obs_ptr, reward_ptr, flags_ptr):
+        """``aqua_step_host`` on raw host addresses (``ctypes.c_void_p``) the caller keeps alive and has
+        validated once: what the single-env drop-in calls every step (no per-call conversions)."""
+        N.check(self.lib.aqua_step_host_ex(self._h, self._stream(), actions_ptr, action_dtype, obs_ptr, reward_ptr,
+                                           flags_ptr, 0))
+        self._host_obs_prev = None
+        self._step_index += 1
+
     def host_d2h_bytes_per_env(self):
         """Bytes per env-step that :meth:`step_host` copies device -> host when all three outputs are
         requested (obs planes that changed, reward, flags)."""

@@ -708,6 +708,32 @@ def test_step_host_equals_device_step(precision):
     b.close()
 
 
+@pytest.mark.parametrize("precision", ["float64", "float32"])
+@pytest.mark.parametrize("name,n", [("v1_discrete", 1), ("v2_continuous", 777), ("dense64_discrete", 8192)])
+def test_small_slab_host_step_through_mapped_memory(name, n, precision):
+    """Host steps of at most 8192 envs (the single-env drop-in) read actions from and write reward,
+    flags and observation to mapped pinned memory: two launches, one synchronisation.  Same results
+    as the device step, with every action dtype."""
+    cfg = _cfg(name, seed=19, base=7)
+    a = _make_gpu(cfg, n, precision, autoreset=True)
+    b = _make_gpu(cfg, n, precision, autoreset=True)
+    a.reset()
+    b.reset()
+    np_real = np.float64 if precision == "float64" else np.float32
+    for t in range(60):
+        act = a.random_actions(t)
+        a.step_flags(act)
+        act_h = act.cpu().numpy()
+        if not a.continuous:
+            act_h = act_h.astype([np.int32, np.int64, np.uint8][t % 3])
+        obs_h, rew_h, fl_h = b.step_host(act_h)
+        assert obs_h.dtype == np_real and np.array_equal(obs_h, a.obs_planes.cpu().numpy()), t
+        assert np.array_equal(rew_h, a.reward.cpu().numpy()) and np.array_equal(fl_h, a.flags.cpu().numpy()), t
+    assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy()) and a.stats() == b.stats()
+    a.close()
+    b.close()
+
+
 def test_step_host_with_pinned_buffers_updates_goals_in_place():
     """Pinned host buffers (what bench.py's e2e leg uses): the goals of finished envs are written
     straight into the caller's planes by a small kernel.  Also the extreme case: a map without free
