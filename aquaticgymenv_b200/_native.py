@@ -24,6 +24,7 @@ EPISODE_MASK = 0x1FFFFF
 N_PLANES = 8
 TILE = 1024
 N_STATS = 9
+MLP_WEIGHTS = 4739  # AQUA_MLP_WEIGHTS
 STAT_NAMES = ("episodes", "collided", "timeout", "success", "length_sum", "reward_sum_fx", "steps",
               "bad_actions", "forced_resets")
 REWARD_FIXED_POINT = 1048576.0
@@ -65,6 +66,7 @@ SIGNATURES = {
     "aqua_random_actions": (_int, [_vp, _vp, _u64, _vp, _int]),
     "aqua_step_many": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _i64]),
     "aqua_rollout_random": (_int, [_vp, _vp, _i64, _u64]),
+    "aqua_rollout_policy": (_int, [_vp, _vp, _i64, _vp, C.c_float, _u64, _vp, _vp, _vp, _i64]),
     "aqua_step_host": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "aqua_step_host_ex": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp, _int]),
     "aqua_observe": (_int, [_vp, _vp, _vp, _int]),

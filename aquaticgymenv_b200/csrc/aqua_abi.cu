@@ -587,6 +587,39 @@ int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t fir
     return AQUA_OK;
 }
 
+int aqua_rollout_policy(aqua_env* env, void* stream, int64_t steps, const float* weights, float epsilon,
+                        uint64_t first_step_index, int32_t* actions_out, void* reward, uint8_t* flags,
+                        int64_t row_stride) {
+    if (int rc = check_env(env)) return rc;
+    if (env->cfg.continuous) return fail(AQUA_ERR_INVALID, "aqua_rollout_policy: the Q-network chooses among the discrete actions");
+    if (steps < 0 || steps > 0x7fffffff) return fail(AQUA_ERR_INVALID, "steps must be in [0, 2^31)");
+    if (weights == nullptr) return fail(AQUA_ERR_INVALID, "weights is NULL");
+    if (!(epsilon >= 0.f && epsilon <= 1.f)) return fail(AQUA_ERR_INVALID, "epsilon must be in [0, 1]");
+    const bool outputs = actions_out != nullptr || reward != nullptr || flags != nullptr;
+    if (outputs && (row_stride < env->cfg.n_envs || row_stride % 16 != 0))
+        return fail(AQUA_ERR_INVALID, "row_stride = %lld must be a multiple of 16 and >= n_envs = %lld",
+                    (long long)row_stride, (long long)env->cfg.n_envs);
+    if ((reinterpret_cast<uintptr_t>(actions_out) & 15u) || (reinterpret_cast<uintptr_t>(reward) & 15u) ||
+        (reinterpret_cast<uintptr_t>(flags) & 15u) || (reinterpret_cast<uintptr_t>(weights) & 15u))
+        return fail(AQUA_ERR_INVALID, "weights, actions_out, reward and flags must be 16-byte aligned");
+    if (steps == 0) return AQUA_OK;
+    env->host_obs_last = nullptr;
+    DeviceGuard guard(env->device);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (int rc = ensure_stash(env, s)) return rc;
+    aqua::StepArgs a = base_args(env);
+    a.reward = reward;
+    a.flags = flags;
+    a.row_stride = row_stride;
+    a.steps = steps;
+    a.step0 = first_step_index;
+    a.mlp_w = weights;
+    a.mlp_eps = epsilon;
+    a.act_out = actions_out;
+    AQ_CUDA(aqua::launch_step_policy(env->cfg.precision, a, 128, s));
+    return AQUA_OK;
+}
+
 int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
                    void* reward, uint8_t* flags) {
     return aqua_step_host_ex(env, stream, actions, action_dtype, obs, reward, flags, 0);

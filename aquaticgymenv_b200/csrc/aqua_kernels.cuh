@@ -104,6 +104,11 @@ struct StepArgs {
     int64_t row_stride;
     uint4* stash;          // the ring: [env][kRingDepth] records of 32 bytes
     uint32_t* stash_tag;   // [env][kRingDepth]: the episode each slot holds
+    // in-kernel policy (aqua_rollout_policy): the Q-network's AQUA_MLP_WEIGHTS floats, the exploration
+    // rate, and (or NULL) the chosen actions [steps][row_stride]
+    const float* mlp_w;
+    float mlp_eps;
+    int32_t* act_out;
 };
 
 struct LaunchGeom {
@@ -117,6 +122,8 @@ cudaError_t launch_step(int precision, int action_dtype, const StepArgs& a, Laun
 // K env-steps per launch (aqua_many.cu).  tape != 0: actions[K][row_stride] in, reward / flags
 // [K][row_stride] out (either may be NULL); tape == 0: the synthetic random policy (ACTION stream)
 cudaError_t launch_step_many(int precision, int action_dtype, int tape, const StepArgs& a, LaunchGeom g, cudaStream_t s);
+// K env-steps per launch with the actions chosen in the kernel by the Q-network a.mlp_w (V = 1)
+cudaError_t launch_step_policy(int precision, const StepArgs& a, int threads, cudaStream_t s);
 cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int tab, int* blocks_per_sm);
 cudaError_t launch_stash_init(void* ring, size_t bytes, cudaStream_t s);
 int stash_ring_depth();

@@ -44,6 +44,31 @@ cudaError_t launch_step_many(int precision, int action_dtype, int tape, const St
     return many_dispatch(precision, g.v, tab, tab == 2 || a.steps > kRingStartOnlySteps, action_dtype, tape, c);
 }
 
+cudaError_t launch_step_policy(int precision, const StepArgs& a, int threads, cudaStream_t s) {
+    const int64_t n = a.env_end - a.env_begin;
+    if (n <= 0 || n > ((int64_t)1 << 31) || a.mlp_w == nullptr) return cudaErrorInvalidValue;
+    StepArgs b = a;
+    const size_t es = precision == AQUA_F64 ? 8 : 4;
+    for (int pl = 0; pl < AQUA_N_PLANES; ++pl)
+        b.pl0[pl] = static_cast<const char*>(a.planes) + ((size_t)pl * (size_t)a.ld) * es +
+                    (size_t)a.env_begin * (pl == AQUA_PLANE_TIME ? 4 : es);
+    b.act0 = nullptr;
+    b.rew0 = a.reward != nullptr ? static_cast<char*>(a.reward) + (size_t)a.env_begin * es : nullptr;
+    b.flg0 = a.flags != nullptr ? a.flags + a.env_begin : nullptr;
+    if (b.act_out != nullptr) b.act_out += a.env_begin;
+    b.n_stream = (uint32_t)n;
+    b.env_id0 = (uint32_t)(a.w.env_id_base + (uint64_t)a.env_begin);
+    ManyCall c = {};
+    c.kind = 0;
+    c.a = &b;
+    c.g.threads = threads;
+    c.g.v = 1;
+    c.g.blocks = (int)((n + threads - 1) / threads);
+    c.s = s;
+    const int tab = many_tab_kind(a.w);
+    return precision == AQUA_F64 ? many_tu_mlp_f64(tab, c) : many_tu_mlp_f32(tab, c);
+}
+
 // `tab`: 0 brute force, 1 small table, 2 culling grid (as the launcher derives it from the World)
 cudaError_t many_occupancy(int precision, int v, int action_dtype, int tape, int threads, int tab, int* blocks_per_sm) {
     ManyCall c = {};

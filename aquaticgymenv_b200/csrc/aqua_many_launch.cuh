@@ -62,7 +62,23 @@ template <typename R, int V> static cudaError_t many_tab(int tab, int inloop, in
     return inloop ? many_act<R, V, 0, true>(act, tape, c) : many_act<R, V, 0, false>(act, tape, c);
 }
 
+// the in-kernel policy: one env per thread, discrete actions, records drawn in the step loop
+template <typename R> static cudaError_t many_mlp(int tab, const ManyCall& c) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)c.g.blocks);
+    cfg.blockDim = dim3((unsigned)c.g.threads);
+    cfg.dynamicSmemBytes = many_smem<1>(c.g.threads, tab == 2);
+    cfg.stream = c.s;
+    if (tab == 2) return cudaLaunchKernelEx(&cfg, step_many_kernel<R, 1, AQUA_ACT_I32, false, 2, true, true>, *c.a);
+    if constexpr (sizeof(R) == 4) {
+        if (tab == 1) return cudaLaunchKernelEx(&cfg, step_many_kernel<R, 1, AQUA_ACT_I32, false, 1, true, true>, *c.a);
+    }
+    return cudaLaunchKernelEx(&cfg, step_many_kernel<R, 1, AQUA_ACT_I32, false, 0, true, true>, *c.a);
+}
+
 // one per translation unit
+cudaError_t many_tu_mlp_f32(int tab, const ManyCall& c);
+cudaError_t many_tu_mlp_f64(int tab, const ManyCall& c);
 cudaError_t many_tu_f32v1(int tab, int inloop, int act, int tape, const ManyCall& c);
 cudaError_t many_tu_f32v2(int tab, int inloop, int act, int tape, const ManyCall& c);
 cudaError_t many_tu_f32v4(int tab, int inloop, int act, int tape, const ManyCall& c);

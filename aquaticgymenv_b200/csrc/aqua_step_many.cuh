@@ -235,6 +235,78 @@ __device__ __forceinline__ void philox2x32_10_v(uint32_t (&c0)[N], uint32_t (&c1
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The reference's Q-network (dqn.py:301-314: Dense 64 relu, Dense 64 relu, Dense 3 linear) evaluated by
+// one lane for its own env.  `w` (shared memory) holds the Keras weights in their own layout:
+// W1[5][64], b1[64], W2[64][64], b2[64], W3[64][3], b3[3] (kernels are [in][out]).  float32, every
+// multiply-add an fma in ascending input order; the second hidden layer is produced 16 units at a
+// time and folded into the three outputs at once, so only the first hidden layer is kept.
+// Returns the first index of the largest output (numpy.argmax).
+// ------------------------------------------------------------------------------------------
+constexpr int kMlpIn = 5, kMlpHidden = 64, kMlpOut = 3;
+constexpr int kMlpW1 = 0, kMlpB1 = kMlpW1 + kMlpIn * kMlpHidden, kMlpW2 = kMlpB1 + kMlpHidden,
+              kMlpB2 = kMlpW2 + kMlpHidden * kMlpHidden, kMlpW3 = kMlpB2 + kMlpHidden,
+              kMlpB3 = kMlpW3 + kMlpHidden * kMlpOut, kMlpWeights = kMlpB3 + kMlpOut;  // 4739
+static_assert(kMlpWeights == AQUA_MLP_WEIGHTS, "header and kernel agree on the weight count");
+
+__device__ __forceinline__ uint32_t mlp_greedy_action(const float* __restrict__ w, float x, float y, float th, float gx,
+                                                      float gy) {
+    // AquaStateNormalizer (utils.py:23-27) as observe_kernel computes it
+    const float in[kMlpIn] = {x * (1.0f / 100.0f), y * (1.0f / 100.0f),
+                              fmaf(th, 1.0f / (2.0f * 3.14159265358979323846f), 0.5f), gx * (1.0f / 100.0f),
+                              gy * (1.0f / 100.0f)};
+    float h1[kMlpHidden];
+#pragma unroll
+    for (int o = 0; o < kMlpHidden; o += 4) {
+        float4 acc = *reinterpret_cast<const float4*>(w + kMlpB1 + o);
+#pragma unroll
+        for (int k = 0; k < kMlpIn; ++k) {
+            const float4 ww = *reinterpret_cast<const float4*>(w + kMlpW1 + k * kMlpHidden + o);
+            acc.x = fmaf(in[k], ww.x, acc.x);
+            acc.y = fmaf(in[k], ww.y, acc.y);
+            acc.z = fmaf(in[k], ww.z, acc.z);
+            acc.w = fmaf(in[k], ww.w, acc.w);
+        }
+        h1[o] = fmaxf(acc.x, 0.f);
+        h1[o + 1] = fmaxf(acc.y, 0.f);
+        h1[o + 2] = fmaxf(acc.z, 0.f);
+        h1[o + 3] = fmaxf(acc.w, 0.f);
+    }
+    float q[kMlpOut];
+#pragma unroll
+    for (int c = 0; c < kMlpOut; ++c) q[c] = w[kMlpB3 + c];
+#pragma unroll 1
+    for (int ob = 0; ob < kMlpHidden; ob += 16) {
+        float acc[16];
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(w + kMlpB2 + ob + i);
+            acc[i] = b.x; acc[i + 1] = b.y; acc[i + 2] = b.z; acc[i + 3] = b.w;
+        }
+#pragma unroll
+        for (int k = 0; k < kMlpHidden; ++k) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                const float4 ww = *reinterpret_cast<const float4*>(w + kMlpW2 + k * kMlpHidden + ob + i);
+                acc[i] = fmaf(h1[k], ww.x, acc[i]);
+                acc[i + 1] = fmaf(h1[k], ww.y, acc[i + 1]);
+                acc[i + 2] = fmaf(h1[k], ww.z, acc[i + 2]);
+                acc[i + 3] = fmaf(h1[k], ww.w, acc[i + 3]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float h2 = fmaxf(acc[i], 0.f);
+#pragma unroll
+            for (int c = 0; c < kMlpOut; ++c) q[c] = fmaf(h2, w[kMlpW3 + (ob + i) * kMlpOut + c], q[c]);
+        }
+    }
+    uint32_t a = 0u;
+    if (q[1] > q[0]) a = 1u;
+    if (q[2] > q[a]) a = 2u;
+    return a;
+}
+
 // the drives of two envs with discrete actions a, b in {0, 1, 2} from the pair table (three 8-byte loads)
 template <typename R>
 __device__ __forceinline__ void pair_drives(const R (*tab)[6], uint32_t a, uint32_t b, Drive<R>& da, Drive<R>& db) {
@@ -256,8 +328,10 @@ __device__ __forceinline__ void ring_prefetch(const StepArgs& p, uint32_t rel, u
 
 // TAB: the obstacle test of the launch's table -- 0 brute force, 1 small table (World::small), 2 culling grid
 // INLOOP: used-up ring records are drawn again inside the step loop (dense maps, long launches)
-template <typename R, int V, int ACT, bool TAPE, int TAB, bool INLOOP>
-__global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8)) step_many_kernel(const __grid_constant__ StepArgs p) {
+// MLP: the actions come from the reference's Q-network (dqn.py:301-314) evaluated by the env's own lane
+// (aqua_rollout_policy); V = 1, discrete actions, no tape
+template <typename R, int V, int ACT, bool TAPE, int TAB, bool INLOOP, bool MLP = false>
+__global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, sizeof(R) == 8)) step_many_kernel(const __grid_constant__ StepArgs p) {
     __shared__ ObstacleBox<R> s_box[kBoxSlots];
     __shared__ R s_nr2[kBoxSlots + 3];
     __shared__ unsigned long long s_stats[kSlotStats];
@@ -265,6 +339,8 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     // the drives of an env PAIR (actions a, b): entry 3 a + b = {phi_a, phi_b}, {h_a, h_b}, {chord_a, chord_b},
     // each read with one 8-byte load straight into the register pair the packed arithmetic takes
     __shared__ __align__(16) R s_drive2[9][6];
+    __shared__ __align__(16) float s_mlp[MLP ? kMlpWeights + 1 : 4];
+    static_assert(!MLP || (V == 1 && !TAPE && ACT == AQUA_ACT_I32), "the in-kernel policy: one env per thread, discrete");
     // dynamic shared memory: the culling grid of a dense map, one refill queue per warp, the stash
     // records of the CTA's envs (2 x 16 bytes each)
     const ObstacleView<R> tab = stage_table<R>(s_box, s_nr2, s_stage, p.w.tab, p.w.k_obst, TAB == 2);
@@ -275,6 +351,9 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
     if (ACT != AQUA_ACT_F32X2 && threadIdx.x < 3) {  // aqua.py:33-42
         const Drive<R> d = drive_from_index<R>(threadIdx.x);
         s_drive[threadIdx.x] = DriveSlot<R>{d.phi, d.h, d.chord, R(0)};
+    }
+    if constexpr (MLP) {
+        for (int i = threadIdx.x; i < kMlpWeights; i += blockDim.x) s_mlp[i] = __ldg(p.mlp_w + i);
     }
     if (ACT != AQUA_ACT_F32X2 && V > 1 && threadIdx.x < 9) {
         const Drive<R> da = drive_from_index<R>(threadIdx.x / 3), db = drive_from_index<R>(threadIdx.x % 3);
@@ -456,7 +535,24 @@ __global__ void __launch_bounds__(kManyThreads, AQUA_MANY_MINB(V, sizeof(R) == 8
             float nx[V], ny[V];
 #pragma unroll
             for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
-            if constexpr (TAPE) {
+            if constexpr (MLP) {
+                // the greedy action of the Q-network on the normalised observation (test_dqn.py:14-22,
+                // utils.py:23-27), epsilon-greedy with the ACTION stream (dqn.py:212-228)
+                uint32_t a = mlp_greedy_action(s_mlp, (float)e[0].x, (float)e[0].y, (float)e[0].th, (float)e[0].gx, (float)e[0].gy);
+                if (p.mlp_eps > 0.f) {
+                    const uint2 w = draw_action_words(p.w.keys, env_id, p.step0 + (uint64_t)k);
+                    if (__fmul_rn(u24(w.x), 0x1p-24f) < p.mlp_eps) a = __umulhi(w.y, 3u);
+                }
+                if (p.act_out != nullptr && has) p.act_out[(size_t)k * (size_t)p.row_stride + rel] = (int32_t)a;
+                const DriveSlot<R> d = s_drive[a];
+                dr[0].phi = d.phi;
+                dr[0].h = d.h;
+                dr[0].chord = d.chord;
+                uint32_t tw[V];
+#pragma unroll
+                for (int j = 0; j < V; ++j) tw[j] = e[j].tw;
+                draw_wave_noise_v<V>(p.w.keys, env_id, tw, nx, ny);
+            } else if constexpr (TAPE) {
                 const ActVals<ACT, V> act = act_next;
                 act_next = act_next2;
                 if (k + 2 < steps && has) {

@@ -389,6 +389,44 @@ class AquaVecEnv(object):
         N.check(self.lib.aqua_rollout_random(self._h, self._stream(), int(steps), int(first_step_index)))
         self._step_index = int(first_step_index) + int(steps)
 
+    @staticmethod
+    def pack_q_network(q_function):
+        """The weights of the reference's Q-network (dqn.py:301-314; a torch Sequential with three Linear
+        layers 5-64-64-3, e.g. ``savedmodel.load_q_network`` or ``dqn.create_model``) as the flat float32
+        vector ``aqua_rollout_policy`` takes: Keras layout W1[5][64], b1, W2[64][64], b2, W3[64][3], b3."""
+        linears = [m for m in q_function if isinstance(m, torch.nn.Linear)]
+        shapes = [tuple(m.weight.shape) for m in linears]
+        if shapes != [(64, 5), (64, 64), (3, 64)]:
+            raise ValueError("rollout_policy evaluates the reference's 5-64-64-3 network, got layers %r" % (shapes,))
+        parts = []
+        for m in linears:
+            parts += [m.weight.detach().t().contiguous().reshape(-1), m.bias.detach().reshape(-1)]  # torch keeps [out, in]
+        w = torch.cat(parts).to(torch.float32).contiguous()
+        assert w.numel() == N.MLP_WEIGHTS
+        return w
+
+    def rollout_policy(self, weights, steps, epsilon=0.0, first_step_index=None, want_actions=False, want_reward=False,
+                       want_flags=False):
+        """``steps`` env-steps in ONE launch with the actions chosen in the kernel by the Q-network
+        ``weights`` (:meth:`pack_q_network`), greedy or epsilon-greedy (``aqua_rollout_policy``).
+        Returns ``(actions, reward, flags)``: ``[steps, row_stride]`` tensors (columns >= num_envs are
+        padding) for the outputs asked for, ``None`` otherwise; the statistics count everything."""
+        self._check_open()
+        if first_step_index is None:
+            first_step_index = self._step_index
+        w = weights.to(self.device, torch.float32).contiguous()
+        if w.numel() != N.MLP_WEIGHTS:
+            raise ValueError("weights must hold %d floats (pack_q_network)" % N.MLP_WEIGHTS)
+        stride = (self.num_envs + 15) // 16 * 16
+        acts = torch.empty(steps, stride, dtype=torch.int32, device=self.device) if want_actions else None
+        rew = torch.empty(steps, stride, dtype=self.dtype, device=self.device) if want_reward else None
+        flg = torch.empty(steps, stride, dtype=torch.uint8, device=self.device) if want_flags else None
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(self.lib.aqua_rollout_policy(self._h, self._stream(), int(steps), ptr(w), float(epsilon),
+                                             int(first_step_index), ptr(acts), ptr(rew), ptr(flg), stride))
+        self._step_index = int(first_step_index) + int(steps)
+        return acts, rew, flg
+
     def observe(self, normalized=False, out=None):
         """Observation rows ``[N, 5]`` float32, contiguous (network input).  ``normalized`` applies
         ``AquaStateNormalizer.__call__`` (main/impl/utils.py:23-27) in the same kernel."""

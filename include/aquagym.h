@@ -190,8 +190,10 @@ int aqua_random_actions(aqua_env* env, void* stream, uint64_t step_index, void* 
  * Identical, bit for bit, to `steps` calls of aqua_step on the rows.  With autoreset the next
  * episode of a finished env starts in the same launch (its first observation is NOT materialised
  * per step: the state planes hold the observation after the last step; keep_terminal keeps the
- * terminal one).  The first call allocates 32 bytes per env for the pre-drawn next episodes (so it
- * cannot be captured in a CUDA graph; later calls can). */
+ * terminal one).  The first call allocates 144 bytes per env for the ring of pre-drawn next episodes
+ * (four records + their tags; so it cannot be captured in a CUDA graph; later calls can).  Launches
+ * of up to 160 steps draw the records an env used up before the first step of the next call; longer
+ * launches, and dense maps, draw them inside the step loop. */
 int aqua_step_many(aqua_env* env, void* stream, int64_t steps, const void* actions, int action_dtype,
                    void* reward, uint8_t* flags, int64_t row_stride);
 
@@ -199,12 +201,33 @@ int aqua_step_many(aqua_env* env, void* stream, int64_t steps, const void* actio
  * first_step_index + 1, ...): no tape, no per-step outputs, the statistics count everything. */
 int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t first_step_index);
 
+/* `steps` env.step() calls in ONE launch with the actions chosen IN the kernel by the reference's
+ * Q-network (main/impl/dqn.py:301-314: Dense 64 relu, Dense 64 relu, Dense 3 linear) on the normalised
+ * observation (main/impl/utils.py:23-27), greedy (test_dqn.py:14-22) or epsilon-greedy
+ * (dqn.py:212-228): what an evaluation loop, or the acting side of the DQN loop, calls instead of
+ * observe -> network -> argmax -> step per env-step.  Discrete-action handles only.
+ *   weights : DEVICE float[AQUA_MLP_WEIGHTS] in Keras layout: W1[5][64], b1[64], W2[64][64], b2[64],
+ *             W3[64][3], b3[3] (kernels are [in][out])
+ *   epsilon : with this probability a step takes a uniform random action instead (0 = greedy); the
+ *             draws are those of aqua_random_actions keyed by first_step_index + k
+ *   actions_out : device int32 [steps][row_stride] or NULL: the actions taken
+ *   reward / flags / row_stride : as in aqua_step_many (each may be NULL; row_stride may be 0 then)
+ * The network is evaluated in float32 with fused multiply-adds in ascending input order; the action is
+ * the first index of the largest output. */
+#define AQUA_MLP_WEIGHTS 4739
+int aqua_rollout_policy(aqua_env* env, void* stream, int64_t steps, const float* weights, float epsilon,
+                        uint64_t first_step_index, int32_t* actions_out, void* reward, uint8_t* flags,
+                        int64_t row_stride);
+
 /* Host-buffer step: the call a host-side gym user makes.  Copies `actions` (HOST, preferably
  * pinned) to the device, steps, and copies obs (float[5][N] planes x,y,theta,gx,gy; double if
  * F64), reward and flags back to HOST buffers, chunked and pipelined over internal streams;
  * returns after everything has landed.  obs/reward/flags may be NULL to skip that copy.
  * `stream` is the stream earlier asynchronous calls on this handle were issued on: the internal
- * streams wait for it first. */
+ * streams wait for it first.  Handles of at most 8192 envs (the single-env drop-in) take another
+ * route: the kernels read the actions from and write the outputs to mapped pinned memory of the
+ * library, on `stream` itself, and the call polls a completion word (two launches per step, no
+ * copy-engine transfer; AQUA_HOST_NO_MAPPED in the environment disables it). */
 int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
                    void* reward, uint8_t* flags);
 

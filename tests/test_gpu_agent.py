@@ -123,6 +123,87 @@ def test_shipped_policies_reproduce_the_published_success_rates(name, env_id, pu
     env.close()
 
 
+@pytest.mark.parametrize("precision", ["float32", "float64"])
+def test_in_kernel_q_network_policy(precision):
+    """aqua_rollout_policy: the reference's 5-64-64-3 Q-network (dqn.py:301-314) evaluated inside the
+    step kernel by the env's own lane.  (1) Its action is the argmax of the network on the normalised
+    observation (float64 numpy evaluation of the same weights; steps where the two best outputs are
+    closer than 1e-4 are not judged).  (2) The step it takes is aqua_step with that action, bit for
+    bit.  (3) K steps in one launch == K launches of one step.  (4) epsilon-greedy explores at the
+    requested rate, and the same first_step_index replays the same exploration."""
+    import os
+    import torch
+    from aquaticgymenv_b200 import gym_aqua, savedmodel
+    from tests.conftest import GOLDEN
+    n, K = 3000, 40
+    mk = lambda: gym_aqua.make("AquaEnv-v1", num_envs=n, seed=23, precision=precision)
+    a, b, c = mk(), mk(), mk()
+    q = savedmodel.load_q_network(os.path.join(GOLDEN, "policy_with_obs.npz"), device=a.device)
+    w = a.pack_q_network(q)
+    lin = [m for m in q if isinstance(m, torch.nn.Linear)]
+    W = [(m.weight.detach().double().cpu().numpy().T, m.bias.detach().double().cpu().numpy()) for m in lin]
+    for e in (a, b, c):
+        e.reset()
+    judged = 0
+    for k in range(K):
+        obs = a.observe(normalized=True).double().cpu().numpy()
+        h = np.maximum(obs @ W[0][0] + W[0][1], 0.0)
+        h = np.maximum(h @ W[1][0] + W[1][1], 0.0)
+        qv = h @ W[2][0] + W[2][1]
+        top = np.sort(qv, axis=1)
+        clear = (top[:, -1] - top[:, -2]) > 1e-4
+        acts, rew, flg = a.rollout_policy(w, 1, want_actions=True, want_reward=True, want_flags=True)
+        got = acts[0, :n].cpu().numpy()
+        assert np.array_equal(got[clear], qv.argmax(1)[clear]), k
+        assert got.min() >= 0 and got.max() <= 2
+        judged += int(clear.sum())
+        b.step_flags(acts[0, :n].contiguous())                      # the same step through aqua_step
+        assert torch.equal(b.reward, rew[0, :n]) and torch.equal(b.flags, flg[0, :n]), k
+    assert judged > 0.99 * n * K
+    assert np.array_equal(a.get_state().cpu().numpy(), b.get_state().cpu().numpy()) and a.stats() == b.stats()
+    acts_c, rew_c, flg_c = c.rollout_policy(w, K, want_actions=True, want_reward=True, want_flags=True)   # one launch
+    assert np.array_equal(a.get_state().cpu().numpy(), c.get_state().cpu().numpy()) and a.stats() == c.stats()
+    # exploration: epsilon = 0.3 replaces the greedy action by a uniform one in 30 % of the steps
+    d, e = mk(), mk()
+    d.reset()
+    e.reset()
+    greedy = d.rollout_policy(w, 1, first_step_index=500, want_actions=True)[0][0, :n]
+    mixed = e.rollout_policy(w, 1, epsilon=0.3, first_step_index=500, want_actions=True)[0][0, :n]
+    changed = float((greedy != mixed).float().mean())
+    assert abs(changed - 0.3 * 2 / 3) < 0.04, changed
+    f = mk()
+    f.reset()
+    again = f.rollout_policy(w, 1, epsilon=0.3, first_step_index=500, want_actions=True)[0][0, :n]
+    assert torch.equal(mixed, again)
+    f.close()
+    with pytest.raises(Exception):
+        gym_aqua.make("AquaContinuousEnv-v1", num_envs=64, seed=1).rollout_policy(w, 1)
+    for x in (a, b, c, d, e):
+        x.close()
+
+
+@pytest.mark.parametrize("name,env_id,published", [("no_obs", "AquaEnv-v0", 0.938), ("with_obs", "AquaEnv-v1", 0.667)])
+def test_shipped_policies_replayed_inside_the_kernel(name, env_id, published):
+    """The same end-to-end check as above with the network evaluated in the kernel: 8192 first
+    episodes (every env's first episode: it ends within 1001 steps) from ONE launch of 1001 steps."""
+    import os
+    import torch
+    from aquaticgymenv_b200 import gym_aqua, savedmodel
+    from tests.conftest import GOLDEN
+    env = gym_aqua.make(env_id, num_envs=8192, seed=11)
+    env.reset()
+    q = savedmodel.load_q_network(os.path.join(GOLDEN, "policy_%s.npz" % name), device=env.device)
+    _, _, flg = env.rollout_policy(env.pack_q_network(q), 1001, want_flags=True)
+    flg = flg[:, :8192]
+    done = (flg & 1) != 0
+    assert bool(done.any(dim=0).all())                      # every env finished its first episode
+    first = done.float().argmax(dim=0)                      # step of the first done
+    outcome = flg.gather(0, first[None, :])[0]
+    success = float(((outcome & 8) != 0).float().mean())
+    assert abs(success - published) < 0.04, success
+    env.close()
+
+
 def test_reference_callers_run_on_the_dropin_env():
     """The reference's own caller code, imported unmodified from its main/ package, against the
     drop-in: Policy.test (main/testing/__init__.py:17-36) with OptimalAquaPolicy
