@@ -706,7 +706,53 @@ def cpu_baseline(args, cfg, n_local):
             out.update({k: out["port"][k] for k in ("value", "kind", "sample")})
     except Exception as e:
         out["port"] = {"error": repr(e)}
+    try:
+        out["parity_check"] = parity_check(args)
+    except Exception as e:
+        out["parity_check"] = {"error": repr(e)}
     return out
+
+
+def parity_check(args, n=8192, launches=2, spl=64):
+    """The measured call (aqua_step_many, the headline config's env) against the oracle in the same run,
+    on the same random actions: the float64 instantiation flag for flag over n x launches x spl
+    env-steps, and the float32 throughput layout over its first launch -- how many envs keep the
+    oracle's flag history, and the drift of their state (scaled as tests/helpers.py: 100 px, 2 pi,
+    0.05, 10).  The oracle is used here as the checker only."""
+    import torch
+    from aquaticgymenv_b200 import gym_aqua
+    from oracle import aqua_oracle as ao
+    res = {"envs": n, "env_steps": n * launches * spl}
+    scale = np.array([100.0, 100.0, 2 * np.pi, 0.05, 0.05, 100.0, 100.0])[:, None]
+    for precision in ("float64", "float32"):
+        env = gym_aqua.make("AquaEnv-v1", num_envs=n, seed=args.seed + 99, precision=precision)
+        ref = ao.OracleVecEnv(n, continuous=False, obstacles=env.table, seed=args.seed + 99)
+        env.reset()
+        ref.reset()
+        same = np.ones(n, bool)
+        mism = 0
+        for l in range(launches if precision == "float64" else 1):
+            tape = torch.stack([env.random_actions(l * spl + k) for k in range(spl)])
+            n16 = (n + 15) // 16 * 16
+            t16 = torch.full((spl, n16), 2, dtype=torch.int32, device=tape.device)
+            t16[:, :n] = tape
+            _, flg = env.step_many(t16)
+            flg = flg[:, :n].cpu().numpy()
+            acts = tape.cpu().numpy()
+            for k in range(spl):
+                _, _, f_ref, _ = ref.step(acts[k], autoreset=True)
+                d = flg[k] != f_ref
+                mism += int(d.sum())
+                same &= ~d
+        diff = env.get_state().cpu().numpy()[:7] - ref.get_state()[:7]
+        diff[2] = (diff[2] + np.pi) % (2 * np.pi) - np.pi   # headings on either side of the +-pi seam are close
+        err = np.abs(diff) / scale
+        key = "f64" if precision == "float64" else "f32"
+        res[key + "_flag_mismatches"] = mism
+        res[key + "_envs_with_the_oracles_flag_history"] = int(same.sum())
+        res[key + "_max_scaled_state_error_of_those"] = float(err[:, same].max())
+        env.close()
+    return res
 
 
 def main():
