@@ -675,6 +675,27 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
     }
     const bool sparse_goals = obs_dev != nullptr;
     const int n_obs_planes = sparse_goals ? 3 : 5;
+    // All the caller's output buffers pinned and mapped: ONE kernel per chunk writes them straight
+    // from the SMs (launch_pack_host) instead of three copy-engine transfers and the goal kernel.
+    // (AQUA_HOST_NO_PACK in the environment keeps the copy-engine route: tuning / tests.)
+    auto mapped = [](const void* h) -> char* {
+        if (h == nullptr) return nullptr;
+        cudaPointerAttributes pa;
+        if (cudaPointerGetAttributes(&pa, h) == cudaSuccess && pa.type == cudaMemoryTypeHost && pa.devicePointer != nullptr)
+            return static_cast<char*>(pa.devicePointer);
+        cudaGetLastError();
+        return nullptr;
+    };
+    char* const m_obs = mapped(obs);
+    char* const m_rew = mapped(reward);
+    char* const m_flg = mapped(flags);
+    const bool pack = getenv("AQUA_HOST_NO_PACK") == nullptr && (obs == nullptr || m_obs != nullptr) &&
+                      (reward == nullptr || m_rew != nullptr) && flags != nullptr && m_flg != nullptr;
+    if (pack && getenv("AQUA_HOST_CHUNKS") == nullptr) {  // a few chunks on alternating streams: a chunk's writes overlap the next one's step
+        // (measured, profiles/r03v_e2e_*.jsonl: four chunks at 2^20 envs, chunks of 2^20 at 2^24)
+        chunk = std::min<int64_t>(std::max<int64_t>((n + 3) / 4, 256 * 1024), 1024 * 1024);
+        chunk = (chunk + AQUA_TILE - 1) / AQUA_TILE * AQUA_TILE;
+    }
     int c = 0;
     for (int64_t lo = 0; lo < n && err == cudaSuccess; lo += chunk, ++c) {
         const int64_t hi = std::min(n, lo + chunk);
@@ -692,6 +713,11 @@ int aqua_step_host_ex(aqua_env* env, void* stream, const void* actions, int acti
         aqua::LaunchGeom g;
         pick_geom(env, len, false, action_dtype, &g);
         AQ_TRY(aqua::launch_step(env->cfg.precision, action_dtype, a, g, s));
+        if (pack) {
+            AQ_TRY(aqua::launch_pack_host(env->cfg.precision, env->state, env->ld, env->d_reward, env->d_flags, lo, len, n,
+                                          m_obs, m_rew, reinterpret_cast<uint8_t*>(m_flg), sparse_goals ? 1 : 0, s));
+            continue;
+        }
         if (flags != nullptr)
             AQ_TRY(cudaMemcpyAsync(flags + lo, env->d_flags + lo, (size_t)len, cudaMemcpyDeviceToHost, s));
         if (reward != nullptr)

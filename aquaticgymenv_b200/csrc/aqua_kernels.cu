@@ -140,6 +140,62 @@ __global__ void goal_updates_kernel(const void* planes, int64_t ld, const uint8_
     h_gy[i] = plane<R>(pl, ld, AQUA_PLANE_GOAL_Y)[i];
 }
 
+// The outputs of a host step written by the SMs straight into the caller's MAPPED pinned buffers
+// (posted writes over PCIe, 16 bytes per thread and plane): planes x, y, angle (and the goal planes,
+// or -- sparse_goals -- only the goals of the envs that finished), reward, flags of the envs
+// [lo, lo + len).  One launch instead of three copy-engine transfers and the goal kernel.  A thread
+// moves 16 / sizeof(R) consecutive envs; `lo` is a multiple of AQUA_TILE, every base pointer 16-byte
+// aligned, and the tail of a slab is moved element by element.
+template <typename R>
+__global__ void pack_host_kernel(const void* planes, int64_t ld, const R* __restrict__ reward,
+                                 const uint8_t* __restrict__ flags, int64_t lo, int64_t len, int64_t n, R* h_obs, R* h_rew,
+                                 uint8_t* h_flg, int sparse_goals) {
+    constexpr int W = 16 / (int)sizeof(R);
+    void* pl = const_cast<void*>(planes);
+    const int64_t k = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * W;
+    if (k >= len) return;
+    const int64_t i = lo + k;
+    const bool full = k + W <= len;
+    uint8_t fl[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) fl[j] = (full || k + j < len) ? flags[i + j] : (uint8_t)0;
+    if (h_obs != nullptr) {
+        const int n_planes = sparse_goals ? 3 : 5;
+        for (int p = 0; p < n_planes; ++p) {
+            const R* src = plane<R>(pl, ld, p) + i;
+            R* dst = h_obs + (int64_t)p * n + i;
+            if (full && (((uintptr_t)dst) & 15u) == 0) {
+                *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+            } else {
+                for (int j = 0; j < W && k + j < len; ++j) dst[j] = src[j];
+            }
+        }
+        if (sparse_goals) {
+#pragma unroll
+            for (int j = 0; j < W; ++j)
+                if (fl[j] & AQUA_FLAG_DONE) {
+                    h_obs[(int64_t)3 * n + i + j] = plane<R>(pl, ld, AQUA_PLANE_GOAL_X)[i + j];
+                    h_obs[(int64_t)4 * n + i + j] = plane<R>(pl, ld, AQUA_PLANE_GOAL_Y)[i + j];
+                }
+        }
+    }
+    if (h_rew != nullptr) {
+        if (full && (((uintptr_t)(h_rew + i)) & 15u) == 0) {
+            *reinterpret_cast<uint4*>(h_rew + i) = *reinterpret_cast<const uint4*>(reward + i);
+        } else {
+            for (int j = 0; j < W && k + j < len; ++j) h_rew[i + j] = reward[i + j];
+        }
+    }
+    if (h_flg != nullptr) {
+        if (full && W == 4 && (((uintptr_t)(h_flg + i)) & 3u) == 0) {
+            *reinterpret_cast<uint32_t*>(h_flg + i) = (uint32_t)fl[0] | ((uint32_t)fl[1] << 8) | ((uint32_t)fl[W > 2 ? 2 : 0] << 16) |
+                                                       ((uint32_t)fl[W > 3 ? 3 : 0] << 24);
+        } else {
+            for (int j = 0; j < W && k + j < len; ++j) h_flg[i + j] = fl[j];
+        }
+    }
+}
+
 // K3: fold the per-CTA slots (kSlotStats counters each) and the forced-reset counter into
 // int64[AQUA_N_STATS]
 __global__ void stats_reduce_kernel(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear) {
@@ -484,6 +540,21 @@ cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, c
     else
         goal_updates_kernel<float><<<blocks_for(len, threads), threads, 0, s>>>(planes, ld, flags, lo, len,
                                                                                static_cast<float*>(h_gx), static_cast<float*>(h_gy));
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_host(int precision, const void* planes, int64_t ld, const void* reward, const uint8_t* flags,
+                             int64_t lo, int64_t len, int64_t n, void* h_obs, void* h_rew, uint8_t* h_flg, int sparse_goals,
+                             cudaStream_t s) {
+    const int threads = 256;
+    if (precision == AQUA_F64)
+        pack_host_kernel<double><<<blocks_for((len + 1) / 2, threads), threads, 0, s>>>(
+            planes, ld, static_cast<const double*>(reward), flags, lo, len, n, static_cast<double*>(h_obs),
+            static_cast<double*>(h_rew), h_flg, sparse_goals);
+    else
+        pack_host_kernel<float><<<blocks_for((len + 3) / 4, threads), threads, 0, s>>>(
+            planes, ld, static_cast<const float*>(reward), flags, lo, len, n, static_cast<float*>(h_obs),
+            static_cast<float*>(h_rew), h_flg, sparse_goals);
     return cudaGetLastError();
 }
 

@@ -143,6 +143,10 @@ cudaError_t launch_copy_obs_planes(int precision, const void* planes, int64_t ld
 // writes the goals of the finished envs of [lo, lo + len) into the caller's (device-mapped) host planes
 cudaError_t launch_goal_updates(int precision, const void* planes, int64_t ld, const uint8_t* flags, int64_t lo,
                                 int64_t len, void* h_gx, void* h_gy, cudaStream_t s);
+// x, y, angle (+ goals, or the finished envs' goals only), reward, flags of envs [lo, lo + len) into MAPPED host buffers
+cudaError_t launch_pack_host(int precision, const void* planes, int64_t ld, const void* reward, const uint8_t* flags,
+                             int64_t lo, int64_t len, int64_t n, void* h_obs, void* h_rew, uint8_t* h_flg, int sparse_goals,
+                             cudaStream_t s);
 cudaError_t launch_stats_reduce(unsigned long long* slots, unsigned int* forced, int64_t* out, int clear, cudaStream_t s);
 // per-device, once: opt the step kernels in to their dynamic shared memory (staging buffers)
 cudaError_t configure_kernels(int precision);

@@ -33,9 +33,12 @@ if len(sys.argv) > 2:  # child: one chunk count
     print(json.dumps({"envs": n, "chunks": os.environ.get("AQUA_HOST_CHUNKS", "default"), "us_per_step": dt * 1e6,
                       "env_steps_per_s": n / dt, "d2h_gbs": 17 * n / dt / 1e9}))
 else:
-    for k in ("default", "1", "2", "4", "8", "16"):
-        env = dict(os.environ)
-        if k != "default":
-            env["AQUA_HOST_CHUNKS"] = k
-        out = subprocess.run([sys.executable, __file__, str(n), "child"], env=env, capture_output=True, text=True)
-        print(out.stdout.strip() or out.stderr[-400:], flush=True)
+    for route in ("pack kernel (SM writes to the mapped buffers)", "copy engines"):
+        for k in ("default", "1", "2", "4", "8", "16"):
+            env = dict(os.environ)
+            if k != "default":
+                env["AQUA_HOST_CHUNKS"] = k
+            if route == "copy engines":
+                env["AQUA_HOST_NO_PACK"] = "1"
+            out = subprocess.run([sys.executable, __file__, str(n), "child"], env=env, capture_output=True, text=True)
+            print(route + ": " + (out.stdout.strip() or out.stderr[-400:]), flush=True)
