@@ -67,6 +67,7 @@ SIGNATURES = {
     "aqua_step_many": (_int, [_vp, _vp, _i64, _vp, _int, _vp, _vp, _i64]),
     "aqua_rollout_random": (_int, [_vp, _vp, _i64, _u64]),
     "aqua_rollout_policy": (_int, [_vp, _vp, _i64, _vp, C.c_float, _u64, _vp, _vp, _vp, _i64]),
+    "aqua_rollout_policy_dev": (_int, [_vp, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _i64]),
     "aqua_step_host": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "aqua_step_host_ex": (_int, [_vp, _vp, _vp, _int, _vp, _vp, _vp, _int]),
     "aqua_observe": (_int, [_vp, _vp, _vp, _int]),

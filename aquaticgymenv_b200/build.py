@@ -10,7 +10,7 @@ LIB = os.path.join(_HERE, "libaquagym.so")
 
 
 def build(force=False, verbose=False):
-    cmd = ["make", "-j4", "-C", CSRC] + (["-B"] if force else [])
+    cmd = ["make", "-j8", "-C", CSRC] + (["-B"] if force else [])
     out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or out.returncode != 0:
         print(out.stdout)

@@ -235,6 +235,12 @@ int ensure_host_pipeline(aqua_env* env, int action_dtype) {
 
 }  // namespace
 
+namespace {
+int rollout_policy_impl(aqua_env* env, void* stream, int64_t steps, const float* weights, float epsilon,
+                        uint64_t first_step_index, const float* epsilon_dev, const uint64_t* first_step_index_dev,
+                        int32_t* actions_out, void* reward, uint8_t* flags, int64_t row_stride);
+}
+
 extern "C" {
 
 int aqua_abi_version(void) { return AQUAGYM_ABI_VERSION; }
@@ -590,6 +596,25 @@ int aqua_rollout_random(aqua_env* env, void* stream, int64_t steps, uint64_t fir
 int aqua_rollout_policy(aqua_env* env, void* stream, int64_t steps, const float* weights, float epsilon,
                         uint64_t first_step_index, int32_t* actions_out, void* reward, uint8_t* flags,
                         int64_t row_stride) {
+    return rollout_policy_impl(env, stream, steps, weights, epsilon, first_step_index, nullptr, nullptr, actions_out, reward,
+                               flags, row_stride);
+}
+
+int aqua_rollout_policy_dev(aqua_env* env, void* stream, int64_t steps, const float* weights, const float* epsilon_dev,
+                            const uint64_t* first_step_index_dev, int32_t* actions_out, void* reward, uint8_t* flags,
+                            int64_t row_stride) {
+    if (epsilon_dev == nullptr || first_step_index_dev == nullptr)
+        return fail(AQUA_ERR_INVALID, "epsilon_dev and first_step_index_dev must not be NULL");
+    return rollout_policy_impl(env, stream, steps, weights, 0.f, 0, epsilon_dev, first_step_index_dev, actions_out, reward,
+                               flags, row_stride);
+}
+
+}  // extern "C"
+
+namespace {
+int rollout_policy_impl(aqua_env* env, void* stream, int64_t steps, const float* weights, float epsilon,
+                        uint64_t first_step_index, const float* epsilon_dev, const uint64_t* first_step_index_dev,
+                        int32_t* actions_out, void* reward, uint8_t* flags, int64_t row_stride) {
     if (int rc = check_env(env)) return rc;
     if (env->cfg.continuous) return fail(AQUA_ERR_INVALID, "aqua_rollout_policy: the Q-network chooses among the discrete actions");
     if (steps < 0 || steps > 0x7fffffff) return fail(AQUA_ERR_INVALID, "steps must be in [0, 2^31)");
@@ -616,9 +641,14 @@ int aqua_rollout_policy(aqua_env* env, void* stream, int64_t steps, const float*
     a.mlp_w = weights;
     a.mlp_eps = epsilon;
     a.act_out = actions_out;
+    a.mlp_eps_dev = epsilon_dev;
+    a.step0_dev = reinterpret_cast<const unsigned long long*>(first_step_index_dev);
     AQ_CUDA(aqua::launch_step_policy(env->cfg.precision, a, 128, s));
     return AQUA_OK;
 }
+}  // namespace
+
+extern "C" {
 
 int aqua_step_host(aqua_env* env, void* stream, const void* actions, int action_dtype, void* obs,
                    void* reward, uint8_t* flags) {

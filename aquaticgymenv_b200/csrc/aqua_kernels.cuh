@@ -109,6 +109,10 @@ struct StepArgs {
     const float* mlp_w;
     float mlp_eps;
     int32_t* act_out;
+    // the same two values read on the device (aqua_rollout_policy_dev: a captured CUDA graph replays
+    // the launch with a new exploration rate and step index each time), or NULL
+    const float* mlp_eps_dev;
+    const unsigned long long* step0_dev;
 };
 
 struct LaunchGeom {

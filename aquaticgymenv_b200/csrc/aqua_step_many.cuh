@@ -484,6 +484,12 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
             act_ptr_k += 2 * act_row;  // the row of step k + 2
         }
 
+        float mlp_eps = 0.f;
+        uint64_t mlp_step0 = 0;
+        if constexpr (MLP) {
+            mlp_eps = p.mlp_eps_dev != nullptr ? __ldg(p.mlp_eps_dev) : p.mlp_eps;
+            mlp_step0 = p.step0_dev != nullptr ? (uint64_t)__ldg(p.step0_dev) : p.step0;
+        }
         for (int k = 0;; ++k) {
             // Records are written to the ring only here (and before the first step), with no copy out of
             // the ring in flight in the warp: every lane waits for its own copies, then the warp
@@ -539,9 +545,9 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
                 // the greedy action of the Q-network on the normalised observation (test_dqn.py:14-22,
                 // utils.py:23-27), epsilon-greedy with the ACTION stream (dqn.py:212-228)
                 uint32_t a = mlp_greedy_action(s_mlp, (float)e[0].x, (float)e[0].y, (float)e[0].th, (float)e[0].gx, (float)e[0].gy);
-                if (p.mlp_eps > 0.f) {
-                    const uint2 w = draw_action_words(p.w.keys, env_id, p.step0 + (uint64_t)k);
-                    if (__fmul_rn(u24(w.x), 0x1p-24f) < p.mlp_eps) a = __umulhi(w.y, 3u);
+                if (mlp_eps > 0.f) {
+                    const uint2 w = draw_action_words(p.w.keys, env_id, mlp_step0 + (uint64_t)k);
+                    if (__fmul_rn(u24(w.x), 0x1p-24f) < mlp_eps) a = __umulhi(w.y, 3u);
                 }
                 if (p.act_out != nullptr && has) p.act_out[(size_t)k * (size_t)p.row_stride + rel] = (int32_t)a;
                 const DriveSlot<R> d = s_drive[a];

@@ -47,6 +47,42 @@ def create_model(n_obs=5, n_actions=3):
                                torch.nn.ReLU(), torch.nn.Linear(64, n_actions))
 
 
+class FlatQNetwork(torch.nn.Module):
+    """The same network (dqn.py:301-314) with all 4,739 weights in ONE flat parameter laid out as Keras
+    stores them (W1[5][64], b1, W2[64][64], b2, W3[64][3], b3; kernels [in][out]): exactly the vector
+    ``aqua_rollout_policy`` reads, so the online network of the trainer is evaluated inside the step
+    kernel without any repacking.  Initialised like ``create_model`` (torch's Linear defaults)."""
+
+    SHAPES = ((5, 64), (64, 64), (64, 3))
+
+    def __init__(self, n_obs=5, n_actions=3):
+        super().__init__()
+        if (n_obs, n_actions) != (5, 3):
+            raise ValueError("the in-kernel policy is the reference's 5-64-64-3 network")
+        ref = create_model(n_obs, n_actions)
+        parts = []
+        for m in ref:
+            if isinstance(m, torch.nn.Linear):
+                parts += [m.weight.detach().t().contiguous().reshape(-1), m.bias.detach().reshape(-1)]
+        self.theta = torch.nn.Parameter(torch.cat(parts).contiguous())
+
+    def _views(self):
+        out, at = [], 0
+        for i, o in self.SHAPES:
+            w = self.theta[at:at + i * o].view(i, o)
+            at += i * o
+            b = self.theta[at:at + o]
+            at += o
+            out.append((w, b))
+        return out
+
+    def forward(self, x):
+        (w1, b1), (w2, b2), (w3, b3) = self._views()
+        h = torch.relu(torch.addmm(b1, x, w1))
+        h = torch.relu(torch.addmm(b2, h, w2))
+        return torch.addmm(b3, h, w3)
+
+
 class ReplayBuffer(object):
     """Device-resident ring buffer of (s, a, r, s', done); replaces the deque of dqn.py:103."""
 
@@ -102,7 +138,13 @@ class ReplayBuffer(object):
 class BatchedDQN(object):
 
     def __init__(self, environment, save_directory=None, save_freq=100, hyperparams=None,
-                 reference_double=False, reference_broadcast_loss=False, seed=0, cuda_graph=False):
+                 reference_double=False, reference_broadcast_loss=False, seed=0, cuda_graph=False,
+                 in_kernel_acting=False):
+        """``in_kernel_acting``: the acting side of a vector step (normalise, online network, epsilon-greedy,
+        env step: dqn.py:161-165,212-228) is ONE launch of ``aqua_rollout_policy_dev`` -- the network is
+        evaluated by each env's own lane inside the step kernel -- instead of observe + three torch
+        Linear layers + argmax + random draws + ``aqua_step``.  The exploration draws then come from the
+        env's ACTION stream (keyed by env id and step index) instead of the torch generator."""
         hp = dict(default_hyperparam)
         hp.update(hyperparams or {})
         if hp["LOSS_STRATEGY"] not in ("double", "fixed", "standard"):
@@ -120,8 +162,10 @@ class BatchedDQN(object):
         self.gen = torch.Generator(device=self.device)
         self.gen.manual_seed(seed)
         torch.manual_seed(seed)
-        self.q_function = create_model(5, self.n_actions).to(self.device)
-        self.q_function_target = create_model(5, self.n_actions).to(self.device)
+        self.in_kernel_acting = bool(in_kernel_acting)
+        make = FlatQNetwork if self.in_kernel_acting else create_model
+        self.q_function = make(5, self.n_actions).to(self.device)
+        self.q_function_target = make(5, self.n_actions).to(self.device)
         self.q_function_target.load_state_dict(self.q_function.state_dict())
         self.optimizer = torch.optim.Adam(self.q_function.parameters(), lr=hp["LEARNING_RATE"],
                                           fused=torch.device(self.device).type == "cuda",
@@ -242,9 +286,18 @@ class BatchedDQN(object):
         it runs eagerly or as the body of a CUDA graph alike."""
         hp, env = self.hp, self.env
         state = self._state
-        action = self._epsilon_greedy_best_action(state, self._epsilon(self._decay))    # dqn.py:184
-        flags = env.step_flags(action)
-        reward = env.reward
+        if self.in_kernel_acting:
+            with torch.no_grad():
+                self._eps_dev.copy_(self._epsilon(self._decay).reshape(1))                  # dqn.py:184
+                env.rollout_policy_dev(self.q_function.theta.detach(), 1, self._eps_dev, self._step_dev,
+                                       self._act_out, self._rew_out, self._flg_out)
+                self._step_dev += 1
+                n = env.num_envs
+                action, reward, flags = self._act_out[0, :n].long(), self._rew_out[0, :n], self._flg_out[0, :n]
+        else:
+            action = self._epsilon_greedy_best_action(state, self._epsilon(self._decay))    # dqn.py:184
+            flags = env.step_flags(action)
+            reward = env.reward
         done = (flags & 1) != 0
         self._ep_ret += reward.double()
         # the env auto-resets: for a finished env the planes already hold the next episode's
@@ -281,6 +334,13 @@ class BatchedDQN(object):
         self._log_count.zero_()
         self._episodes_dev.fill_(self.episode)
         self._decay = torch.as_tensor(decay, dtype=torch.float64, device=self.device)
+        if self.in_kernel_acting:
+            stride = (n + 15) // 16 * 16
+            self._eps_dev = torch.zeros(1, dtype=torch.float32, device=self.device)
+            self._step_dev = torch.full((1,), env._step_index, dtype=torch.int64, device=self.device)
+            self._act_out = torch.zeros(1, stride, dtype=torch.int32, device=self.device)
+            self._rew_out = torch.zeros(1, stride, dtype=env.dtype, device=self.device)
+            self._flg_out = torch.zeros(1, stride, dtype=torch.uint8, device=self.device)
         self._graph = None
         t0, it = perf_counter(), 0
         next_save = (self.episode // self.save_freq + 1) * self.save_freq

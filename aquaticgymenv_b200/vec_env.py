@@ -427,6 +427,27 @@ class AquaVecEnv(object):
         self._step_index = int(first_step_index) + int(steps)
         return acts, rew, flg
 
+    def rollout_policy_dev(self, weights, steps, epsilon_dev, step_index_dev, actions_out=None, reward_out=None,
+                           flags_out=None):
+        """:meth:`rollout_policy` with the exploration rate (float32 tensor of one element) and the
+        first step index (int64 tensor of one element, >= 0) read on the device when the launch
+        runs, into caller-owned ``[steps, stride]`` outputs (``stride`` = num_envs rounded up to 16):
+        nothing here depends on a host value, so the call can be captured in a CUDA graph
+        (``aqua_rollout_policy_dev``).  The caller advances ``step_index_dev``."""
+        self._check_open()
+        stride = (self.num_envs + 15) // 16 * 16
+        for t, dt in ((actions_out, torch.int32), (reward_out, self.dtype), (flags_out, torch.uint8)):
+            if t is not None and (t.dtype != dt or tuple(t.shape) != (steps, stride) or not t.is_contiguous()):
+                raise ValueError("outputs must be contiguous [%d, %d] tensors of int32 / %s / uint8" % (steps, stride, self.dtype))
+        if weights.numel() != N.MLP_WEIGHTS or weights.dtype != torch.float32 or not weights.is_contiguous():
+            raise ValueError("weights: a contiguous float32 tensor of %d elements" % N.MLP_WEIGHTS)
+        if epsilon_dev.dtype != torch.float32 or step_index_dev.dtype != torch.int64:
+            raise ValueError("epsilon_dev: float32, step_index_dev: int64 (one element each, on the device)")
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        N.check(self.lib.aqua_rollout_policy_dev(self._h, self._stream(), int(steps), ptr(weights), ptr(epsilon_dev),
+                                                 ptr(step_index_dev), ptr(actions_out), ptr(reward_out), ptr(flags_out),
+                                                 stride))
+
     def observe(self, normalized=False, out=None):
         """Observation rows ``[N, 5]`` float32, contiguous (network input).  ``normalized`` applies
         ``AquaStateNormalizer.__call__`` (main/impl/utils.py:23-27) in the same kernel."""

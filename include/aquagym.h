@@ -219,6 +219,13 @@ int aqua_rollout_policy(aqua_env* env, void* stream, int64_t steps, const float*
                         uint64_t first_step_index, int32_t* actions_out, void* reward, uint8_t* flags,
                         int64_t row_stride);
 
+/* The same with the exploration rate and the first step index read ON THE DEVICE when the launch runs
+ * (DEVICE float[1] and uint64[1]): a CUDA graph that captured the call replays it with the values
+ * of the moment -- the acting side of a DQN loop captured as one graph per vector step. */
+int aqua_rollout_policy_dev(aqua_env* env, void* stream, int64_t steps, const float* weights, const float* epsilon_dev,
+                            const uint64_t* first_step_index_dev, int32_t* actions_out, void* reward, uint8_t* flags,
+                            int64_t row_stride);
+
 /* Host-buffer step: the call a host-side gym user makes.  Copies `actions` (HOST, preferably
  * pinned) to the device, steps, and copies obs (float[5][N] planes x,y,theta,gx,gy; double if
  * F64), reward and flags back to HOST buffers, chunked and pipelined over internal streams;

@@ -54,15 +54,19 @@ def test_random_policy_statistics_match_reference_scale():
     env.close()
 
 
+@pytest.mark.parametrize("in_kernel", [False, True])
 @pytest.mark.parametrize("cuda_graph", [False, True])
-def test_batched_dqn_trains_on_the_gpu_env(tmp_path, cuda_graph):
+def test_batched_dqn_trains_on_the_gpu_env(tmp_path, cuda_graph, in_kernel):
     """dqn_train_policy.py:19-21 flow on the batched env: a short run improves on the random
     policy's success rate and writes the reference's progress files.  Eagerly, and with one CUDA
-    graph per vector step (the env's launches captured together with the torch ops)."""
+    graph per vector step (the env's launches captured together with the torch ops).  in_kernel: the
+    acting side (normaliser, online network, epsilon-greedy, step) is one launch of
+    aqua_rollout_policy_dev, the network's weights read in place from the trainer's flat parameter."""
     import torch
     from aquaticgymenv_b200 import dqn, gym_aqua, policies
     env = gym_aqua.make("AquaEnv-v0", num_envs=2048, seed=5)
     agent = dqn.BatchedDQN(env, save_directory=str(tmp_path), save_freq=5000, cuda_graph=cuda_graph,
+                           in_kernel_acting=in_kernel,
                            hyperparams={"EPSILON_DECAY": 20000, "BUFFER_SIZE": 200000,
                                         "MINIBATCH_SIZE": 512, "UPDATES_PER_STEP": 2})
     agent.train(env_steps=1500)
@@ -77,7 +81,8 @@ def test_batched_dqn_trains_on_the_gpu_env(tmp_path, cuda_graph):
     env.close()
 
 
-def test_dqn_graph_mode_reproduces_the_eager_run():
+@pytest.mark.parametrize("in_kernel", [False, True])
+def test_dqn_graph_mode_reproduces_the_eager_run(in_kernel):
     """The captured vector step must be the eager one: same seeds (the agent's generator in eager
     mode, the default generator under capture, seeded alike and called alike) give the same
     episode log and the same network, bit for bit.  A host value baked into the graph at capture
@@ -87,7 +92,7 @@ def test_dqn_graph_mode_reproduces_the_eager_run():
     out = []
     for cuda_graph in (False, True):
         env = gym_aqua.make("AquaEnv-v0", obstacles=True, num_envs=1024, seed=3)
-        agent = dqn.BatchedDQN(env, seed=7, cuda_graph=cuda_graph,
+        agent = dqn.BatchedDQN(env, seed=7, cuda_graph=cuda_graph, in_kernel_acting=in_kernel,
                                hyperparams={"EPSILON_DECAY": 3000, "BUFFER_SIZE": 30000, "MINIBATCH_SIZE": 256})
         agent.train(env_steps=300)   # the replay ring wraps (300 * 1024 > 30000), epsilon decays to its floor
         out.append((list(agent.reward_list), list(agent.success_list),

@@ -29,7 +29,8 @@ for obstacles, published in ((False, 0.938), (True, 0.667)):
     HP["UPDATES_PER_STEP"] = int(os.environ.get("DQN_UPS", "1"))
     env = gym_aqua.make("AquaEnv-v0", obstacles=obstacles, num_envs=n, seed=1)   # dqn_train_policy.py:19
     test_env = gym_aqua.make("AquaEnv-v0", obstacles=obstacles, num_envs=2048, seed=99)
-    agent = dqn.BatchedDQN(env, hyperparams=HP, seed=0, cuda_graph=True)
+    in_kernel = os.environ.get("DQN_IN_KERNEL", "0") == "1"   # acting through aqua_rollout_policy_dev
+    agent = dqn.BatchedDQN(env, hyperparams=HP, seed=0, cuda_graph=True, in_kernel_acting=in_kernel)
     curve, busy = [], 0.0
     chunk = max(steps // 8, 1)
     done = 0
@@ -47,7 +48,7 @@ for obstacles, published in ((False, 0.938), (True, 0.667)):
     print(json.dumps({
         "config": "BASELINE config 5: batched double-DQN (5-64-64-3, Adam 1e-3, gamma 0.98, tau 0.005, eps 1.0->0.05 over "
                   "15000 episodes) on AquaEnv-v0 obstacles=%s, %d envs, batch %d, 1 learner step per vector step, "
-                  "one CUDA graph per vector step" % (obstacles, n, batch),
+                  "one CUDA graph per vector step%s" % (obstacles, n, batch, ", acting inside the step kernel" if in_kernel else ""),
         "hyperparams": HP, "vector_steps": steps, "env_steps": n * steps, "learner_steps": agent.learner_steps,
         "env_steps_per_s": n * steps / busy, "learner_steps_per_s": agent.learner_steps / busy,
         "episodes_seen": agent.episode, "greedy_success_rate": curve[-1]["greedy_success"],
