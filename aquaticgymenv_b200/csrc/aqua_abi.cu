@@ -124,13 +124,15 @@ aqua::StepArgs base_args(aqua_env* env) {
 }
 
 // Launch geometry for `n` envs.  Large slabs: wide threads (16-byte plane accesses), 256-thread
-// CTAs, a persistent grid of (resident CTAs per SM) x (SM count).  Slabs too small to give every
-// SM two wide tiles are latency-bound: they use narrow threads (one env each) in 128-thread CTAs,
-// which quarters the dependent work per thread and spreads the slab over all SMs.
+// CTAs, a persistent grid of (resident CTAs per SM) x (SM count).  Smaller slabs are latency-bound:
+// they use narrow threads (one env each) in 128-thread CTAs, which quarters the dependent work per
+// thread and spreads the slab over all SMs.  The crossover was measured on one box
+// (profiles/r03z_single_geom.txt): narrow 3.99e10 against wide 3.78e10 env-steps/s at 2^19 envs,
+// 4.61e10 against 5.35e10 at 2^20 -- about 4.5 wide tiles per resident warp.
 int pick_geom(const aqua_env* env, int64_t n, bool rollout, int action_dtype, aqua::LaunchGeom* g) {
     const int wide = aqua::envs_per_thread(env->cfg.precision);
     const bool narrow = env->cfg.geometry == AQUA_GEOM_NARROW ||
-                        (env->cfg.geometry == AQUA_GEOM_AUTO && n < (int64_t)256 * wide * env->sm_count * 2);  // ~300k envs
+                        (env->cfg.geometry == AQUA_GEOM_AUTO && n < (int64_t)256 * wide * env->sm_count * 9 / 2);  // ~680k envs
     const int V = narrow ? 1 : wide;
     const int threads = narrow ? aqua::kNarrowThreads : aqua::kWideThreads;
     const int ti = narrow ? 0 : 1;

@@ -468,7 +468,7 @@ def summarise(torch, m, world, dist_on):
                               "`frac_of_bytes_moved` what the kernel itself moves" % bpe) if m["mode"] == "many" else
                              "aqua::step_stream_kernel / step_narrow_kernel: one launch per step, %d B per env-step" % bpe,
                      "kernel": "aqua::step_many_kernel" if m["mode"] == "many" else
-                               ("aqua::step_stream_kernel" if m["n_local"] >= 303104 else "aqua::step_narrow_kernel")},
+                               ("aqua::step_stream_kernel" if m["n_local"] >= 681984 else "aqua::step_narrow_kernel")},
         "gpu_launches": m["launches"],
         "episode_stats": {k: stats[k] for k in ("episodes", "collided", "timeout", "success", "forced_resets",
                                                 "mean_episode_length", "mean_episode_return")},

@@ -52,7 +52,7 @@ enum { AQUA_F32 = 0, AQUA_F64 = 1 };
 
 /* Kernel family: wide threads own 4 (float) / 2 (double) consecutive envs (16-byte plane accesses,
  * the bandwidth layout); narrow threads own one env (small, latency-bound slabs).  AUTO picks
- * narrow below about 300k envs per launch.  Results are identical either way. */
+ * narrow below about 680k envs per launch.  Results are identical either way. */
 enum { AQUA_GEOM_AUTO = 0, AQUA_GEOM_WIDE = 1, AQUA_GEOM_NARROW = 2 };
 
 /* element type of the `actions` buffer of aqua_step */
