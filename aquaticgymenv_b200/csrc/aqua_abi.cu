@@ -517,18 +517,18 @@ int ensure_stash(aqua_env* env, cudaStream_t s) {
 // Geometry of a multi-step launch: every env belongs to one thread for the whole launch, so the
 // grid is not persistent.  More envs per thread give a thread more independent work and cost fewer
 // instructions per env-step, but leave fewer warps.  Measured over slab sizes on one box, launches
-// back to back (profiles/r03f_step_many_v_by_size_*.txt, three maps): one env per thread up to ~330
-// envs per SM and again around 660 (one full wave of its CTAs), two envs per thread otherwise --
-// at 65,536 envs (440 per SM) and from ~780 per SM on; four per thread (128 registers) no longer wins
-// anywhere.  128-thread CTAs on dense maps from ~1300 envs per SM (the culling grid is staged once
-// per CTA), 64-thread CTAs otherwise.
+// back to back (profiles/r04b_step_many_v_by_size_*.txt, three maps): one env per thread up to ~330
+// envs per SM (49,152 envs on a B200), two envs per thread above (at 65,536 envs the two are equal on the
+// default map, two is 27 % ahead with continuous actions); four per thread (128 registers) no longer
+// wins anywhere.  128-thread CTAs on dense maps from ~1300 envs per SM (the culling grid is staged
+// once per CTA), 64-thread CTAs otherwise.
 // AQUA_MANY_V / AQUA_MANY_THREADS (environment) override the choice: tuning only.
 int pick_many_geom(const aqua_env* env, int64_t n, aqua::LaunchGeom* g) {
     const int wide = aqua::envs_per_thread(env->cfg.precision);
     const int64_t per_sm = n / std::max(env->sm_count, 1);
     const bool grid = env->world.use_grid != 0;
     int threads = 64, v = 2;
-    if (per_sm <= 332 || (!grid && per_sm > 553 && per_sm <= 775)) v = 1;
+    if (per_sm <= 332) v = 1;
     if (grid && per_sm >= 1328) threads = 128;
     if (env->cfg.geometry == AQUA_GEOM_WIDE) v = wide;
     if (env->cfg.geometry == AQUA_GEOM_NARROW) v = 1;

@@ -149,7 +149,21 @@ struct LaneWork {
 #else
 #define AQUA_RING_FN __device__ __noinline__
 #endif
-template <typename R, int V, int GRID>
+// reset_blocked() through the small table (kernel parameters) where the launch has one: float only
+template <typename R, int TAB>
+__device__ __forceinline__ bool ring_blocked(const StepArgs& p, const ObstacleView<R>& tab, float x, float y) {
+    if constexpr (TAB == 1 && sizeof(R) == 4) {
+        const float px[1] = {x}, py[1] = {y};
+        float clr[1] = {kClearFar};
+        obstacle_clearance_small<1>(p.w.small, p.w.small_mode, px, py, clr);
+        if (fabsf(clr[0]) <= p.w.reset_band) return hits_obstacle_g(p.w.tab64, p.w.k_obst, (double)x, (double)y);
+        return clr[0] <= 0.f;
+    } else {
+        return reset_blocked<R, (TAB == 2 ? 1 : 0)>(tab, p.w.tab64, p.w.k_circ, p.w.k_obst, p.w.reset_band, x, y);
+    }
+}
+
+template <typename R, int V, int TAB>
 AQUA_RING_FN void ring_round(const StepArgs& p, const ObstacleView<R>& tab, const RefillQueue<V>& rq,
                                            int& n_q, int& n_act, LaneWork* sw) {
     const unsigned full = 0xffffffffu;
@@ -185,7 +199,7 @@ AQUA_RING_FN void ring_round(const StepArgs& p, const ObstacleView<R>& tab, cons
                 atomicAdd(p.w.forced, 1u);
             } else {
                 ok = !(outside_border_f(cx, cy) || (boat && reset_reached<R>(w.gx, w.gy, cx, cy)) ||
-                       reset_blocked<R, GRID>(tab, p.w.tab64, p.w.k_circ, p.w.k_obst, p.w.reset_band, cx, cy));
+                       ring_blocked<R, TAB>(p, tab, cx, cy));
             }
             w.n += 1u;
             if (ok && !boat) {  // aqua.py:102-105
@@ -445,12 +459,12 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
                 }
                 if (__any_sync(full, word != 0u)) n_q = refill_push<V>(rq, n_q, word, rel, want);
                 __syncwarp();  // queue entries are visible to the whole warp
-                while (n_q + n_act >= 32) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                while (n_q + n_act >= 32) ring_round<R, V, TAB>(p, tab, rq, n_q, n_act, sw);
             }
 #if AQUA_RING_FULL_DRAIN
             // sparse maps: a launch draws all its records here and starts with a full ring
             if constexpr (!kInLoop)
-                while (n_q + n_act > 0) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                while (n_q + n_act > 0) ring_round<R, V, TAB>(p, tab, rq, n_q, n_act, sw);
 #endif
             __syncwarp();  // orders the record stores of all lanes before the owners' loads
 #pragma unroll
@@ -502,7 +516,7 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
                     // the owner takes its record from the ring
                     cp_async_wait<0>();
                     __syncwarp();
-                    while (n_q + n_act > 0) ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                    while (n_q + n_act > 0) ring_round<R, V, TAB>(p, tab, rq, n_q, n_act, sw);
                     __syncwarp();
                     uint32_t after[V], word = 0u;
 #pragma unroll
@@ -528,7 +542,7 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
                     if (n_q + n_act >= 32) {
                         cp_async_wait<0>();
                         __syncwarp();
-                        do ring_round<R, V, (TAB == 2 ? 1 : 0)>(p, tab, rq, n_q, n_act, sw);
+                        do ring_round<R, V, TAB>(p, tab, rq, n_q, n_act, sw);
                         while (n_q + n_act >= 32);
                         __syncwarp();  // orders the record stores before the copies the owners start later
                     }
