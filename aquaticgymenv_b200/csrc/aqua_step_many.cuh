@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
                 tg[j] = make_uint4(0u, 0u, 0u, 0u);
                 if (j < nvalid) tg[j] = __ldcg(reinterpret_cast<const uint4*>(p.stash_tag) + (p.env_begin + (int64_t)rel + j));
             }
-#pragma unroll
+#pragma unroll 1
             for (int d = kRingDepth - 1; d >= 0; --d) {  // the nearest episodes last: they are taken first
                 uint32_t want[V], word = 0u;
 #pragma unroll
@@ -504,41 +504,17 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
             mlp_eps = p.mlp_eps_dev != nullptr ? __ldg(p.mlp_eps_dev) : p.mlp_eps;
             mlp_step0 = p.step0_dev != nullptr ? (uint64_t)__ldg(p.step0_dev) : p.step0;
         }
-        for (int k = 0;; ++k) {
-            // Records are written to the ring only here (and before the first step), with no copy out of
-            // the ring in flight in the warp: every lane waits for its own copies, then the warp
-            // synchronises.  A copy therefore never sees half of a record (the tag sits in its second
-            // 16 bytes), and one started later sees the finished record.
-            if (autoreset) {
-                if (__any_sync(full, pend != 0u)) {
-                    // rare: an env finished whose record was not in the ring (it finished kRingDepth times
-                    // before the records it used up were drawn again): everything queued is drawn now,
-                    // the owner takes its record from the ring
-                    cp_async_wait<0>();
-                    __syncwarp();
-                    while (n_q + n_act > 0) ring_round<R, V, TAB>(p, tab, rq, n_q, n_act, sw);
-                    __syncwarp();
-                    uint32_t after[V], word = 0u;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) {
-                        const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;
-                        after[j] = (want + kRingDepth) & kEpisodeMask;
-                        if ((pend >> (8 * j)) & 1u) {
-                            const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (want & (kRingDepth - 1)));
-                            uint4 r0, r1;
-                            record_words_global(src, r0, r1);
-                            if (r1.w != want) __trap();  // the rounds above drew exactly this record
-                            stash_unpack<R>(r0, r1, e[j]);
-                            ring_prefetch(p, rel + j, (want + 1u) & kEpisodeMask, &my_rec[2 * j]);
-                            word |= 1u << (8 * j);
-                        }
-                    }
-                    if constexpr (kInLoop) n_q = refill_push<V>(rq, n_q, word, rel, after);  // the slot it used up
-                    pend = 0u;
-                    __syncwarp();
-                }
-                // dense maps: the records used up so far are drawn again as soon as they fill a round
-                if constexpr (kInLoop) {
+        // Two forms of the step loop around the same text (aqua_step_many_body.inc = one step,
+        // aqua_step_many_pend.inc = the rare "record missing" path); which one is faster was measured on
+        // one box (profiles/r03_ring_ab.txt, r04c - r04e).  Sparse maps: the step loop proper is an inner
+        // do-while that holds nothing but the step; a warp with a missing record leaves it (+3 % over
+        // the single loop).  Dense maps (records drawn in the loop): one loop with the rare path and the
+        // rounds at its top (the nested form costs 2 to 4 % there).
+        if constexpr (kInLoop) {
+            for (int k = 0;; ++k) {
+                if (autoreset) {
+#include "aqua_step_many_pend.inc"
+                    // the records used up so far are drawn again as soon as they fill a round
                     if (n_q + n_act >= 32) {
                         cp_async_wait<0>();
                         __syncwarp();
@@ -547,171 +523,25 @@ __global__ void __launch_bounds__(kManyThreads, MLP ? 3 : AQUA_MANY_MINB(V, size
                         __syncwarp();  // orders the record stores before the copies the owners start later
                     }
                 }
+                if (k == steps) break;
+#include "aqua_step_many_body.inc"
             }
-            if (k == steps) break;
-
-            // ---- actions: this step's were loaded during the previous one ----
-            Drive<R> dr[V];
-            float nx[V], ny[V];
-#pragma unroll
-            for (int j = 0; j < V; ++j) nx[j] = ny[j] = 0.f;
-            if constexpr (MLP) {
-                // the greedy action of the Q-network on the normalised observation (test_dqn.py:14-22,
-                // utils.py:23-27), epsilon-greedy with the ACTION stream (dqn.py:212-228)
-                uint32_t a = mlp_greedy_action(s_mlp, (float)e[0].x, (float)e[0].y, (float)e[0].th, (float)e[0].gx, (float)e[0].gy);
-                if (mlp_eps > 0.f) {
-                    const uint2 w = draw_action_words(p.w.keys, env_id, mlp_step0 + (uint64_t)k);
-                    if (__fmul_rn(u24(w.x), 0x1p-24f) < mlp_eps) a = __umulhi(w.y, 3u);
-                }
-                if (p.act_out != nullptr && has) p.act_out[(size_t)k * (size_t)p.row_stride + rel] = (int32_t)a;
-                const DriveSlot<R> d = s_drive[a];
-                dr[0].phi = d.phi;
-                dr[0].h = d.h;
-                dr[0].chord = d.chord;
-                uint32_t tw[V];
-#pragma unroll
-                for (int j = 0; j < V; ++j) tw[j] = e[j].tw;
-                draw_wave_noise_v<V>(p.w.keys, env_id, tw, nx, ny);
-            } else if constexpr (TAPE) {
-                const ActVals<ACT, V> act = act_next;
-                act_next = act_next2;
-                if (k + 2 < steps && has) {
-                    act_next2 = fetch_actions<ACT, V>(act_ptr_k, V);
-                    act_ptr_k += act_row;
-                }
-                if constexpr (ACT == AQUA_ACT_F32X2) {
-                    uint32_t bad = 0u;
-                    decode_drives<R, ACT, V>(act, dr, bad);
-                    if (bad != 0u && nvalid != V) {  // the padding envs of a partial thread read what lies behind the row
-                        bad = 0u;
-#pragma unroll
-                        for (int j = 0; j < V; ++j) {
-                            const float l = __uint_as_float(act.w[2 * j]), r = __uint_as_float(act.w[2 * j + 1]);
-                            bad += (j < nvalid && !(l >= 0.2f && l <= 0.5f && r >= 0.2f && r <= 0.5f)) ? 1u : 0u;
-                        }
+        } else {
+            int k = 0;
+            bool ring_due = false;  // warp-uniform: an env waits for a record that was not in the ring
+            for (;;) {
+                if (ring_due) {
+                    if (autoreset) {
+#include "aqua_step_many_pend.inc"
                     }
-                    st.bad += bad;
-                } else {
-                    uint32_t worst = 0u;
-#pragma unroll
-                    for (int j = 0; j < V; ++j) worst = max(worst, act.w[j]);
-                    if constexpr (V == 1) {
-                        const DriveSlot<R> d = s_drive[min(act.w[0], 2u)];  // outside {0,1,2}: full throttle
-                        dr[0].phi = d.phi;
-                        dr[0].h = d.h;
-                        dr[0].chord = d.chord;
-                    } else {
-#pragma unroll
-                        for (int q = 0; q < V / 2; ++q) pair_drives<R>(s_drive2, min(act.w[2 * q], 2u), min(act.w[2 * q + 1], 2u), dr[2 * q], dr[2 * q + 1]);
-                    }
-                    if (worst > 2u) {  // rare
-#pragma unroll
-                        for (int j = 0; j < V; ++j) st.bad += (j < nvalid && act.w[j] > 2u) ? 1u : 0u;
-                    }
+                    ring_due = false;
                 }
-                {  // also without waves (the increments are unused then): no branch in the step's code
-                    uint32_t tw[V];
-#pragma unroll
-                    for (int j = 0; j < V; ++j) tw[j] = e[j].tw;
-                    draw_wave_noise_v<V>(p.w.keys, env_id, tw, nx, ny);
-                }
-            } else {
-                // synthetic random policy (test_random.py:19-20): the ACTION and WAVE_NOISE chains of
-                // the V envs advance side by side
-                const uint64_t step = p.step0 + (uint64_t)k;
-                uint32_t a0[V], a1[V], w0[V], w1[V];
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    a0[j] = w0[j] = env_id + (uint32_t)j;
-                    a1[j] = (uint32_t)step;
-                    w1[j] = e[j].tw;
-                }
-                philox2x32_10_v<V>(a0, a1, p.w.keys.action, (uint32_t)(step >> 32));
-                philox2x32_10_v<V>(w0, w1, p.w.keys.noise, 0u);
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    if constexpr (ACT == AQUA_ACT_F32X2) {
-                        uint32_t bad = 0u;
-                        dr[j] = drive_continuous<R>(draw_thrust(a0[j]), draw_thrust(a1[j]), bad);
-                    } else if constexpr (V == 1) {
-                        const DriveSlot<R> d = s_drive[__umulhi(a0[j], 3u)];
-                        dr[j].phi = d.phi;
-                        dr[j].h = d.h;
-                        dr[j].chord = d.chord;
-                    } else if ((j & 1) == 0) {
-                        pair_drives<R>(s_drive2, __umulhi(a0[j], 3u), __umulhi(a0[j + (V > 1 ? 1 : 0)], 3u), dr[j], dr[j + (V > 1 ? 1 : 0)]);
-                    }
-                    nx[j] = draw_noise(w0[j]);
-                    ny[j] = draw_noise(w1[j]);
-                }
-            }
-
-            // ---- the step ----
-            R reward[V];
-            uint32_t fw = step_envs<R, V, TAB>(e, dr, nx, ny, waves, tab, k_circ, k_obst, reward, p.w.small, small_mode);
-            fw &= valid_mask;
-            if (nvalid != V) {
-#pragma unroll
-                for (int j = 0; j < V; ++j)
-                    if (j >= nvalid) reward[j] = R(0);
-            }
-#pragma unroll
-            for (int j = 0; j < V; ++j) st.add_env<R>(reward[j]);
-            const bool any_done = __any_sync(full, fw != 0u);  // warp-uniform
-            if (any_done) st.add_flags(fw, 0);                 // (the env-steps are counted once, after the loop)
-
-            // ---- outputs of step k (full-width: a partial thread writes into the row's padding) ----
-            if (has_rew) {
-                Pack<R, V> vrew;
-#pragma unroll
-                for (int j = 0; j < V; ++j) vrew.v[j] = reward[j];
-                st_pack<R, V>(reinterpret_cast<R*>(rew_ptr_k), vrew);
-            }
-            if (has_flg) {
-                if constexpr (V == 4) *reinterpret_cast<uint32_t*>(flg_ptr_k) = fw;
-                else if constexpr (V == 2) *reinterpret_cast<uint16_t*>(flg_ptr_k) = (uint16_t)fw;
-                else *flg_ptr_k = (uint8_t)fw;
-            }
-            rew_ptr_k += rew_row;
-            flg_ptr_k += flg_row;
-
-            // ---- finished envs: the next episode comes from the stash ----
-            if (!autoreset) {
-#pragma unroll
-                for (int j = 0; j < V; ++j) st.add_length(fw >> (8 * j), e[j].tw & kTimeMask);
-            } else if (any_done) {
-                uint32_t ep[V], word = 0u;  // what gets queued: bit 0 of byte j, with episode ep[j]
-                cp_async_wait<0>();         // the records copied in after earlier swaps have landed
-#pragma unroll
-                for (int j = 0; j < V; ++j) {
-                    const uint32_t want = ((e[j].tw >> AQUA_TIME_BITS) + 1u) & kEpisodeMask;  // the episode that opens now
-                    ep[j] = want;
-                    if ((fw >> (8 * j)) & 1u) {
-                        st.length += e[j].tw & kTimeMask;  // AQUA_STAT_LENGTH_SUM: the finished episode's length
-                        if (p.term != nullptr) store_terminal<R>(p, p.env_begin + rel + j, e[j]);  // aqua.py:213
-                        uint4 r0, r1;
-                        record_words(&my_rec[2 * j], r0, r1);
-                        if (kInLoop && r1.w != want) {  // copied before the slot was drawn again?  look at the ring itself
-                            const uint4* src = p.stash + 2 * ((size_t)(p.env_begin + rel + j) * kRingDepth + (want & (kRingDepth - 1)));
-                            record_words_global(src, r0, r1);
-                        }
-                        if (r1.w == want) {  // swap it in; the slot after it is on its way
-                            stash_unpack<R>(r0, r1, e[j]);
-                            ring_prefetch(p, rel + j, (want + 1u) & kEpisodeMask, &my_rec[2 * j]);
-                            if constexpr (kInLoop) {  // queue the slot it used up
-                                word |= 1u << (8 * j);
-                                ep[j] = (want + kRingDepth) & kEpisodeMask;
-                            }
-                        } else {  // not in the ring: queue exactly this record, it is drawn before the next step
-                            word |= 1u << (8 * j);
-                            pend |= 1u << (8 * j);
-                        }
-                    }
-                }
-                if (kInLoop || __any_sync(full, word != 0u)) {
-                    n_q = refill_push<V>(rq, n_q, word, rel, ep);
-                    __syncwarp();  // queue entries are visible to the whole warp
-                }
+                if (k == steps) break;
+                do {
+#include "aqua_step_many_body.inc"
+                    ++k;
+                    if (autoreset) ring_due = __any_sync(full, pend != 0u);
+                } while (k < steps && !ring_due);
             }
         }
 
