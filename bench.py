@@ -475,16 +475,20 @@ def summarise(torch, m, world, dist_on):
     }
 
 
-def traffic_of(m):
-    """DRAM bytes per launch of this workload's kernel from the committed ncu capture, if there is
-    one for exactly this (config, envs, mode, steps per launch); else null."""
+def traffic_entry(m):
+    """The committed ncu capture of exactly this (config, envs, mode, steps per launch, precision), or None."""
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if not os.path.exists(tp):
         return None
     with open(tp) as f:
         tj = json.load(f)
     key = "%s:%d:%s:%d:%s" % (m["name"], m["n_local"], m["mode"], m["spl"] if m["mode"] == "many" else 1, m["precision"])
-    ent = tj.get("captures", {}).get(key)
+    return tj.get("captures", {}).get(key)
+
+
+def traffic_of(m):
+    """DRAM bytes per launch of this workload's kernel from that capture; else null."""
+    ent = traffic_entry(m)
     return None if ent is None else ent.get("dram_bytes_per_launch")
 
 
@@ -584,6 +588,23 @@ def run_b200(args):
         e2e = e2e_leg(torch, m["env"], args, world, dist_on)
         e2e["host_cores_bound_to_gpu"] = bound_cores
     m["env"].close()
+
+    # second view of the dominant kernel (it is bound by instruction issue, not by HBM): the warp
+    # instructions per launch of the committed ncu capture of exactly this configuration, over the
+    # launch time measured here and the SM clock sampled here -> fraction of the issue slots
+    try:
+        cap = traffic_entry(m)
+        if cap is not None and cap.get("warp_instructions_per_launch") and clocks.get("sm_mhz"):
+            props = torch.cuda.get_device_properties(local_rank)
+            slots = props.multi_processor_count * 4 * clocks["sm_mhz"] * 1e6
+            per_launch_s = m["elapsed"] / m["steps"]
+            s["roofline"]["issue_slots"] = {
+                "warp_instructions_per_launch": cap["warp_instructions_per_launch"],
+                "frac": cap["warp_instructions_per_launch"] / per_launch_s / slots,
+                "peak_warp_instructions_per_s": slots,
+                "source": "%s; %s" % (cap.get("source"), cap.get("warp_instructions_note", ""))}
+    except Exception as e:  # a supplementary figure must never cost the line
+        s["roofline"]["issue_slots"] = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": s["value"], "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
