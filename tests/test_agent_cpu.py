@@ -183,3 +183,38 @@ def test_evaluate_counts_a_fixed_quota_of_episodes_per_env():
     assert res["episodes"] == 40 and res["episodes_per_env"] == 5 and res["truncated"] == 0
     assert res["success"] == 20 and res["collided"] == 20          # not 5x more short episodes than long ones
     assert abs(res["length_mean"] - 6.0) < 1e-9 and abs(res["reward_mean"]) < 1e-9
+
+
+def test_flat_q_network_is_the_reference_network_in_keras_layout():
+    """dqn.FlatQNetwork keeps the 4,739 weights of the 5-64-64-3 network (dqn.py:301-314) in ONE flat
+    parameter laid out as Keras stores them -- the vector aqua_rollout_policy reads in place.  Same
+    function as the Sequential of create_model with those weights; AquaVecEnv.pack_q_network of that
+    Sequential gives back the flat vector; a gradient step moves the flat parameter."""
+    from aquaticgymenv_b200 import _native
+    from aquaticgymenv_b200.vec_env import AquaVecEnv
+    torch.manual_seed(3)
+    flat = dqn.FlatQNetwork()
+    assert flat.theta.numel() == _native.MLP_WEIGHTS == 5 * 64 + 64 + 64 * 64 + 64 + 64 * 3 + 3
+    seq = dqn.create_model(5, 3)
+    with torch.no_grad():
+        lin = [m for m in seq if isinstance(m, torch.nn.Linear)]
+        for m, (w, b) in zip(lin, flat._views()):
+            m.weight.copy_(w.t())   # torch keeps [out, in], Keras [in, out]
+            m.bias.copy_(b)
+    x = torch.rand(257, 5)
+    assert torch.allclose(flat(x), seq(x), atol=1e-6)
+    assert torch.equal(AquaVecEnv.pack_q_network(seq), flat.theta.detach())
+    # header and binding agree on the weight count
+    hdr = open(_native.HEADER_PATH).read()
+    assert "#define AQUA_MLP_WEIGHTS %d" % _native.MLP_WEIGHTS in hdr
+    assert "#define AQUA_GRID_DIM %d" % _native.GRID_DIM in hdr
+    before = flat.theta.detach().clone()
+    opt = torch.optim.Adam(flat.parameters(), lr=1e-2)
+    flat(x).pow(2).mean().backward()
+    opt.step()
+    assert not torch.equal(before, flat.theta.detach())
+    try:
+        AquaVecEnv.pack_q_network(torch.nn.Sequential(torch.nn.Linear(5, 32), torch.nn.ReLU(), torch.nn.Linear(32, 3)))
+        assert False, "another architecture must be refused"
+    except ValueError:
+        pass
