@@ -14,17 +14,18 @@
 // owns a RING of kRingDepth 32-byte records in global memory: slot e mod kRingDepth holds the reset
 // state of episode e, tagged e (the tags also sit in a plane of their own, 16 bytes per env).
 //   * The record of each env's NEXT episode is in shared memory.  When an env finishes, its owner
-//     swaps that record in (two 16-byte shared-memory loads), starts an asynchronous copy
-//     (cp.async) of the following slot from the ring into the same place, and queues the slot it
-//     used up for the episode kRingDepth ahead.
-//   * Queued records are drawn in ROUNDS of one try per lane (ring_round): a lane carries one record
-//     through the reference's rejection loops (aqua.py:100-126), one try per round, and takes the next
-//     queued record as soon as its own is accepted.  A round runs when 32 records are queued or in the
-//     making, so every round has all lanes busy and the rejection loops of different envs never wait
-//     for the unluckiest one; between rounds the lanes' records sit in shared memory.
-//   * A launch first reads the tags of its envs and queues every slot that does not hold one of the
-//     env's next kRingDepth episodes (still queued when the previous launch ended; never drawn; or a
-//     single-step launch / aqua_set_state moved the episode on).
+//     swaps that record in (eight 32-bit shared-memory loads: see record_words) and starts an
+//     asynchronous copy (cp.async) of the following slot from the ring into the same place.
+//   * Used-up slots are drawn again, for the episode kRingDepth ahead, in ROUNDS of one try per lane
+//     (ring_round): a lane carries one record through the reference's rejection loops
+//     (aqua.py:100-126), one try per round, and takes the next queued record as soon as its own is
+//     accepted, so the rejection loops of different envs never wait for the unluckiest one.
+//   * Where the rounds run is a template parameter (INLOOP).  Dense maps and long launches: the owner
+//     queues the slot when it swaps, and a round runs inside the step loop whenever 32 records are
+//     queued or in the making (all lanes busy); between rounds the lanes' records sit in shared
+//     memory.  Otherwise: before the first step of the next launch, which reads the tags of its envs
+//     and queues every slot that does not hold one of the env's next kRingDepth episodes (that also
+//     covers a fresh ring, and episodes moved on by a single-step launch or aqua_set_state).
 // An env that finishes kRingDepth times before its used-up slots were drawn again finds a record with
 // the wrong tag: everything queued is then drawn before the next step.  The ring is thus a cache:
 // results do not depend on it (test_step_many_equals_stepwise,
@@ -48,7 +49,7 @@ namespace aqua {
 constexpr int kManyThreads = 128;  // launch bound; the launcher picks 32 .. 128 threads per CTA
 constexpr uint32_t kStashEmpty = 0xffffffffu;
 
-// what is left below a full pass (< 32) plus the entries of two steps (a waiting env's second entry)
+// the warp's queue of records to draw: what a round left behind (< 32) plus one entry per env of the warp
 template <int V> struct RefillQueue {
     uint32_t rel[64 * V + 32];  // env index relative to env_begin
     uint32_t ep[64 * V + 32];   // episode index to draw the record for
