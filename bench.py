@@ -27,6 +27,15 @@ L2-resident sizes it is captured in a CUDA graph.  Both figures of the headline 
 the line (`extras.single_step`).  Envs shard as independent slabs; the only collective is the
 all-reduce of the 9 episode counters after the timed region.
 
+Besides the contract's keys the line carries: `roofline.traffic` (DRAM bytes per launch of the committed
+ncu capture of exactly this configuration, profiles/roofline_traffic.json), `roofline.issue_slots` (the
+kernel is bound by instruction issue: warp instructions of that capture over the launch time and SM
+clock measured here), `roofline.frac_of_bytes_moved`; `cpu_baseline.port` (the C oracle port beside the
+Python reference), `cpu_baseline.c1_single_env` (BASELINE config 1: the single-env drop-in against the
+reference's gym path, steps/s) and `cpu_baseline.parity_check` (the measured call against the oracle in
+the same run: flag mismatches and state drift, float64 and float32); `extras` with the other BASELINE
+configs at their literal sizes, the one-launch-per-step figures and the float64 (flag-exact) layout.
+
 Rank 0 prints ONE JSON line.  `--impl reference` drives the UNMODIFIED reference env
 (baseline/_ref/gym_aqua, copied there by __graft_entry__.build()) through a gym-style vector env
 on all host cores (oracle/ref_vector_env.py) and never loads the product library.
